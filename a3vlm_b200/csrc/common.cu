@@ -1,0 +1,105 @@
+// Host-side plumbing behind the C ABI: error slot, launch accounting, device queries and TMA
+// tensor-map encoding through the driver entry point (resolved at run time: no libcuda link).
+#include "common.cuh"
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+namespace a3 {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+int set_error(int code, const char* msg) {
+  std::snprintf(g_err, sizeof(g_err), "%s", msg ? msg : "");
+  return code;
+}
+
+int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    std::snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return A3_ERR_CUDA;
+  }
+  return A3_OK;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 148;
+    n = prop.multiProcessorCount;
+  }
+  return n;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+static int encode(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims,
+                  const cuuint64_t* strides, const cuuint32_t* box) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return set_error(A3_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr),
+                  dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    std::snprintf(buf, sizeof(buf),
+                  "cuTensorMapEncodeTiled failed (%d): rank %d dims {%llu,%llu,%llu} stride1 %llu "
+                  "box {%u,%u}",
+                  (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+                  (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)strides[0],
+                  box[0], box[1]);
+    return set_error(A3_ERR_CUDA, buf);
+  }
+  return A3_OK;
+}
+
+int make_tmap_2d_bf16(CUtensorMap* tm, const void* ptr, uint64_t dim0, uint64_t dim1,
+                      uint64_t stride1_bytes, uint32_t box0, uint32_t box1) {
+  cuuint64_t dims[2] = {dim0, dim1};
+  cuuint64_t strides[1] = {stride1_bytes};
+  cuuint32_t box[2] = {box0, box1};
+  return encode(tm, ptr, 2, dims, strides, box);
+}
+
+int make_tmap_3d_bf16(CUtensorMap* tm, const void* ptr, uint64_t dim0, uint64_t dim1,
+                      uint64_t dim2, uint64_t stride1_bytes, uint64_t stride2_bytes,
+                      uint32_t box0, uint32_t box1, uint32_t box2) {
+  cuuint64_t dims[3] = {dim0, dim1, dim2};
+  cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+  cuuint32_t box[3] = {box0, box1, box2};
+  return encode(tm, ptr, 3, dims, strides, box);
+}
+
+}  // namespace a3
+
+extern "C" const char* a3_last_error(void) { return a3::g_err; }
+extern "C" int a3_version(void) { return 100; }
+extern "C" long long a3_launch_count(void) { return a3::g_launches.load(); }
+extern "C" void a3_reset_launch_count(void) { a3::g_launches.store(0); }

@@ -1,0 +1,24 @@
+// Host-side helpers shared by every translation unit of liba3vlm_b200.so: error reporting behind
+// the C ABI, launch checking, device properties, and TMA tensor-map encoding (the driver entry
+// point is resolved at run time so the library carries no link-time dependency on libcuda).
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include "a3vlm_b200.h"
+
+namespace a3 {
+
+int set_error(int code, const char* msg);
+int check_launch(const char* what);
+int num_sms();
+
+// 2-D bf16 tensor map with 128-byte swizzle.  dim0 is the contiguous dimension.
+int make_tmap_2d_bf16(CUtensorMap* tm, const void* ptr, uint64_t dim0, uint64_t dim1,
+                      uint64_t stride1_bytes, uint32_t box0, uint32_t box1);
+// 3-D bf16 tensor map with 128-byte swizzle (dim0 contiguous; strides for dim1, dim2 in bytes).
+int make_tmap_3d_bf16(CUtensorMap* tm, const void* ptr, uint64_t dim0, uint64_t dim1,
+                      uint64_t dim2, uint64_t stride1_bytes, uint64_t stride2_bytes,
+                      uint32_t box0, uint32_t box1, uint32_t box2);
+
+}  // namespace a3

@@ -1,0 +1,410 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a:  TMA -> smem ring -> tcgen05.mma -> TMEM ->
+// fused epilogue.  One kernel serves every GEMM-shaped op on the A3VLM hot path (ViT / projector /
+// Llama projections and MLPs, LM head, and their dgrad / wgrad forms) through operand "majorness":
+//
+//   C[M,N] = epilogue( alpha * sum_k A(m,k) * B(n,k) )
+//     A K-major : stored [M][K] (k contiguous, row stride lda)      -- activations in forward / dgrad
+//     A MN-major: stored [K][M] (m contiguous, row stride lda)      -- dy^T in wgrad
+//     B K-major : stored [N][K] (k contiguous, row stride ldb)      -- nn.Linear weight (out,in) in forward
+//     B MN-major: stored [K][N] (n contiguous, row stride ldb)      -- weight in dgrad, x^T in wgrad
+//
+// Replaces the cuBLAS calls behind fairscale Column/RowParallelLinear and nn.Linear in
+// reference model/accessory/model/LLM/llama_ens5.py:63-90,202-210,267-269,330-333 and the
+// open_clip ViT linears (llama_ens5.py:354-370).
+//
+// CTA = 256 threads: warp 0 TMA producer, warp 1 MMA issuer (one elected lane), warp 2 TMEM
+// allocator, warps 4..7 epilogue (TMEM lane quarter = warp_idx % 4).  Tile 128 x BN x 64, 4-5 smem
+// stages, two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "ptx.cuh"
+#include "a3vlm_b200.h"
+#include "common.cuh"
+
+namespace a3 {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 256;
+
+struct GemmParams {
+  void* C;
+  const __nv_bfloat16* bias;      // [N] bf16 or null
+  const __nv_bfloat16* residual;  // [M][ldr] bf16 or null
+  const float2* rope;             // [max_pos][64] (cos, sin) or null
+  long long ldc, ldr;
+  int rope_cols, rope_period, rope_pos0;
+  int M, N, K;
+  int a_mn, b_mn;  // 1 = MN-major operand
+  int act;         // 0 none, 1 gelu (erf), 2 quick-gelu
+  int out_fp32;
+  int accumulate;
+  float alpha;
+  int group_m;  // M-blocks per rasterisation group
+};
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
+};
+
+__device__ __forceinline__ void tile_coords(int tile, int m_blocks, int n_blocks, int group_m,
+                                            int& mb, int& nb) {
+  // Grouped rasterisation: walk all N-blocks for a band of `group_m` M-blocks before moving on,
+  // so one wave of CTAs shares a small set of A rows and B rows in L2.
+  const int per_group = group_m * n_blocks;
+  const int g = tile / per_group;
+  const int first_m = g * group_m;
+  const int rows = min(group_m, m_blocks - first_m);
+  const int r = tile - g * per_group;
+  mb = first_m + r % rows;
+  nb = r / rows;
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == 1) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+  if (act == 2) return v / (1.0f + __expf(-1.702f * v));
+  return v;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const GemmParams p) {
+  using S = GemmSmem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE_BYTES);
+  uint64_t* full_bar = bars;                      // [STAGES]
+  uint64_t* empty_bar = bars + S::STAGES;         // [STAGES]
+  uint64_t* tmem_full = bars + 2 * S::STAGES;     // [2]
+  uint64_t* tmem_empty = bars + 2 * S::STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_blocks = (p.M + BM - 1) / BM;
+  const int n_blocks = (p.N + BN - 1) / BN;
+  const int k_blocks = (p.K + BK - 1) / BK;
+  const int num_tiles = m_blocks * n_blocks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < S::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 2 * BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int mb, nb;
+        tile_coords(tile, m_blocks, n_blocks, p.group_m, mb, nb);
+        const int m0 = mb * BM, n0 = nb * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * S::STAGE_BYTES;
+          uint8_t* sb = sa + S::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+          const int k0 = kb * BK;
+          if (!p.a_mn) {
+            tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0);  // box {64 k, 128 rows}
+          } else {
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c)  // box {64 m, 64 k-rows} per 64-wide chunk
+              tma_load_2d(sa + c * (BK * 128), &tmA, &full_bar[stage], m0 + c * 64, k0);
+          }
+          if (!p.b_mn) {
+            tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);  // box {64 k, BN rows}
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c)
+              tma_load_2d(sb + c * (BK * 128), &tmB, &full_bar[stage], n0 + c * 64, k0);
+          }
+          if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
+      // Descriptor template per operand; only the start-address field changes per stage / k-step.
+      const uint32_t a_lbo = p.a_mn ? BK * 128 : 16, b_lbo = p.b_mn ? BK * 128 : 16;
+      const uint32_t a_kstep = p.a_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+      const uint32_t b_kstep = p.b_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc_stage = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc_stage], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc_stage * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint32_t sb = sa + S::A_BYTES;
+          const uint64_t adesc = make_smem_desc_sw128(sa, a_lbo, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(sb, b_lbo, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            umma_bf16(d_tmem, adesc + k * a_kstep, bdesc + k * b_kstep, idesc,
+                      (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs retire
+          if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc_stage]);  // accumulator ready for the epilogue
+        if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: TMEM -> regs -> global =====================
+    const int ew = warp - 4;  // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
+    int acc_stage = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int mb, nb;
+      tile_coords(tile, m_blocks, n_blocks, p.group_m, mb, nb);
+      const int row = mb * BM + ew * 32 + lane;
+      const int n0 = nb * BN;
+      mbar_wait(&tmem_full[acc_stage], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc_stage * BN;
+      const bool row_ok = row < p.M;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_row + c * 32, r);
+        tmem_ld_wait();
+        const int col0 = n0 + c * 32;
+        if (row_ok && col0 < p.N) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+          const int ncols = min(32, p.N - col0);  // N % 8 == 0 is enforced on the host
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (j < ncols) {
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(p.bias + col0 + j));
+                const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  const float2 f = unpack_bf16x2(w[t]);
+                  v[j + 2 * t] += f.x;
+                  v[j + 2 * t + 1] += f.y;
+                }
+              }
+            }
+          }
+          if (!p.out_fp32) {
+            // bf16 path mirrors the reference's rounding points: Linear output rounds to bf16,
+            // the activation rounds, the residual add rounds.
+            if (p.act) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = apply_act(bf16_round(v[j]), p.act);
+            }
+            if (col0 < p.rope_cols) {
+              // apply_rotary_emb on the bf16-rounded projection, fp32 math, one rounding at the
+              // store.  Heads are 128 wide, so pair index = (col % 128) / 2.
+              const int pos = p.rope_pos0 + row % p.rope_period;
+              const float2* tp = p.rope + static_cast<long long>(pos) * 64 + ((col0 & 127) >> 1);
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                const float2 cs = __ldg(tp + (j >> 1));
+                const float a = bf16_round(v[j]), b = bf16_round(v[j + 1]);
+                v[j] = a * cs.x - b * cs.y;
+                v[j + 1] = a * cs.y + b * cs.x;
+              }
+            }
+            if (p.residual) {
+              const __nv_bfloat16* rp = p.residual + static_cast<long long>(row) * p.ldr + col0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                if (j < ncols) {
+                  const uint4 q = *reinterpret_cast<const uint4*>(rp + j);
+                  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                  for (int t = 0; t < 4; ++t) {
+                    const float2 f = unpack_bf16x2(w[t]);
+                    v[j + 2 * t] = bf16_round(v[j + 2 * t]) + f.x;
+                    v[j + 2 * t + 1] = bf16_round(v[j + 2 * t + 1]) + f.y;
+                  }
+                }
+              }
+            }
+            __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) +
+                                static_cast<long long>(row) * p.ldc + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (j < ncols) {
+                if (p.accumulate) {
+                  const uint4 q = *reinterpret_cast<const uint4*>(cp + j);
+                  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                  for (int t = 0; t < 4; ++t) {
+                    const float2 f = unpack_bf16x2(w[t]);
+                    v[j + 2 * t] += f.x;
+                    v[j + 2 * t + 1] += f.y;
+                  }
+                }
+                uint4 o;
+                o.x = pack_bf16x2(v[j], v[j + 1]);
+                o.y = pack_bf16x2(v[j + 2], v[j + 3]);
+                o.z = pack_bf16x2(v[j + 4], v[j + 5]);
+                o.w = pack_bf16x2(v[j + 6], v[j + 7]);
+                *reinterpret_cast<uint4*>(cp + j) = o;
+              }
+            }
+          } else {
+            if (p.act) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+            }
+            if (p.residual) {
+              const __nv_bfloat16* rp = p.residual + static_cast<long long>(row) * p.ldr + col0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols) v[j] += __bfloat162float(rp[j]);
+            }
+            float* cp = reinterpret_cast<float*>(p.C) + static_cast<long long>(row) * p.ldc + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (j < ncols) {
+                float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                if (p.accumulate) {
+                  const float4 q = *reinterpret_cast<const float4*>(cp + j);
+                  o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
+                }
+                *reinterpret_cast<float4*>(cp + j) = o;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc_stage]);
+      if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+static int encode_operand_map(CUtensorMap* tm, const void* ptr, int rows_out, int k_red,
+                              long long ld, int mn_major, int block_rows) {
+  // K-major: memory [rows_out][k_red] -> dims {k_red, rows_out}, box {64, block_rows}
+  // MN-major: memory [k_red][rows_out] -> dims {rows_out, k_red}, box {64, 64}
+  if (!mn_major)
+    return make_tmap_2d_bf16(tm, ptr, (uint64_t)k_red, (uint64_t)rows_out, (uint64_t)ld * 2, 64,
+                             (uint32_t)block_rows);
+  return make_tmap_2d_bf16(tm, ptr, (uint64_t)rows_out, (uint64_t)k_red, (uint64_t)ld * 2, 64, BK);
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
+                       cudaStream_t stream) {
+  using S = GemmSmem<BN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    if (e != cudaSuccess) return set_error(A3_ERR_CUDA, cudaGetErrorString(e));
+    configured = true;
+  }
+  const int m_blocks = (p.M + BM - 1) / BM, n_blocks = (p.N + BN - 1) / BN;
+  const int tiles = m_blocks * n_blocks;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_bf16_kernel<BN><<<grid, GEMM_THREADS, S::TOTAL, stream>>>(tmA, tmB, p);
+  return check_launch("a3_gemm_bf16");
+}
+
+}  // namespace a3
+
+extern "C" int a3_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K,
+                            long long lda, long long ldb, long long ldc, int a_mn_major,
+                            int b_mn_major, const void* bias, const void* residual,
+                            long long ldr, int act, int out_fp32, int accumulate, float alpha,
+                            const void* rope_table, int rope_cols, int rope_period, int rope_pos0,
+                            void* stream) {
+  using namespace a3;
+  if (M <= 0 || N <= 0 || K <= 0) return A3_OK;  // empty problem: nothing to do
+  if (!A || !B || !C) return set_error(A3_ERR_ARG, "a3_gemm_bf16: null operand");
+  if ((N & 7) || (lda & 7) || (ldb & 7) || (ldc & (out_fp32 ? 3 : 7)) ||
+      (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15) ||
+      (reinterpret_cast<uintptr_t>(C) & 15))
+    return set_error(A3_ERR_ARG,
+                     "a3_gemm_bf16: N, lda, ldb, ldc must be multiples of 8 elements and "
+                     "pointers 16-byte aligned");
+  if (residual && ((ldr & 7) || (reinterpret_cast<uintptr_t>(residual) & 15)))
+    return set_error(A3_ERR_ARG, "a3_gemm_bf16: residual must be 16-byte aligned, ldr % 8 == 0");
+  if (bias && (reinterpret_cast<uintptr_t>(bias) & 15))
+    return set_error(A3_ERR_ARG, "a3_gemm_bf16: bias must be 16-byte aligned");
+  if (act < 0 || act > 2) return set_error(A3_ERR_ARG, "a3_gemm_bf16: act must be 0, 1 or 2");
+  if (rope_table && rope_cols > 0 && ((rope_cols & 127) || out_fp32))
+    return set_error(A3_ERR_ARG, "a3_gemm_bf16: rope needs rope_cols % 128 == 0 and bf16 output");
+
+  const int bn = (N <= 128 || (N % 256 != 0 && N % 128 == 0 && N < 2048)) ? 128 : 256;
+  CUtensorMap tmA, tmB;
+  int rc = encode_operand_map(&tmA, A, M, K, lda, a_mn_major, BM);
+  if (rc != A3_OK) return rc;
+  rc = encode_operand_map(&tmB, B, N, K, ldb, b_mn_major, bn);
+  if (rc != A3_OK) return rc;
+
+  GemmParams p;
+  p.C = C;
+  p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
+  p.rope = reinterpret_cast<const float2*>(rope_table);
+  p.rope_cols = rope_table ? rope_cols : 0;
+  p.rope_period = rope_period > 0 ? rope_period : 1;
+  p.rope_pos0 = rope_pos0;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+  p.ldc = ldc;
+  p.ldr = ldr;
+  p.M = M; p.N = N; p.K = K;
+  p.a_mn = a_mn_major ? 1 : 0;
+  p.b_mn = b_mn_major ? 1 : 0;
+  p.act = act;
+  p.out_fp32 = out_fp32 ? 1 : 0;
+  p.accumulate = accumulate ? 1 : 0;
+  p.alpha = alpha;
+  p.group_m = 16;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  return bn == 128 ? launch_gemm<128>(tmA, tmB, p, s) : launch_gemm<256>(tmA, tmB, p, s);
+}

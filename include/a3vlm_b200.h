@@ -1,0 +1,189 @@
+/*
+ * a3vlm_b200 -- C ABI of the B200-native hot path (CLIP ViT-L/14 -> projector -> Llama decoder,
+ * forward / backward / optimiser / greedy decode) that replaces the library kernels behind the
+ * reference's `llama_type` plugin (reference model/accessory/model/meta.py:30-32 picks
+ * `accessory.model.LLM.<llama_type>`; the tensor math it then runs is
+ * model/accessory/model/LLM/llama_ens5.py:53-539 and model/accessory/model/components.py:10-53).
+ *
+ * The reference has no C ABI of its own (it is 100 % Python on top of torch / cuBLAS / cuDNN /
+ * flash-attn wheels); every entry point below cites the reference lines whose arithmetic it
+ * replaces.  Conventions:
+ *   - all pointers are DEVICE pointers borrowed from the caller (PyTorch's allocator); the library
+ *     allocates nothing and keeps no reference after the call returns;
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued, never synchronised;
+ *   - matrices are row-major; `ld*` are row strides in ELEMENTS;
+ *   - return value: A3_OK or an error code; a3_last_error() gives the message.  No CPU fallback
+ *     exists: a call on a machine without an sm_100 device fails with A3_ERR_CUDA.
+ */
+#ifndef A3VLM_B200_H_
+#define A3VLM_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define A3_OK 0
+#define A3_ERR_ARG 1
+#define A3_ERR_CUDA 2
+#define A3_ERR_UNSUPPORTED 3
+
+/* activation codes for a3_gemm_bf16 */
+#define A3_ACT_NONE 0
+#define A3_ACT_GELU 1       /* exact erf GELU: open_clip ViT built with pretrained=None (llama_ens5.py:299) */
+#define A3_ACT_QUICKGELU 2  /* x*sigmoid(1.702x): OpenAI CLIP weights (llama_ens5.py:297) */
+
+const char* a3_last_error(void);
+int a3_version(void);
+/* Number of kernels this library has launched since load / since the last reset (bench.py's
+ * `gpu_launches`). */
+long long a3_launch_count(void);
+void a3_reset_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * GEMM (tcgen05 / TMEM / TMA).  C[M,N] = epilogue(alpha * sum_k A(m,k) B(n,k)).
+ *   a_mn_major = 0: A stored [M][K] (lda >= K);  1: A stored [K][M] (lda >= M)
+ *   b_mn_major = 0: B stored [N][K] (ldb >= K);  1: B stored [K][N] (ldb >= N)
+ * Epilogue, in order: *alpha, +bias[n] (bf16, added in fp32), [round to bf16 unless out_fp32], activation,
+ * [RoPE on columns < rope_cols], +residual[m,n] (bf16), [+C if accumulate], store bf16 / fp32.
+ * The bf16 roundings reproduce autocast's: a Linear output is rounded before the activation and
+ * before the residual add.  RoPE (rope_cols > 0): columns are heads of 128, pairs
+ * (2j,2j+1) rotated by angle table[pos][j] with pos = pos0 + (m % rope_period); `rope_table` is
+ * float2 (cos,sin) [max_pos][64].
+ * Replaces: every fairscale Column/RowParallelLinear and nn.Linear on the path
+ * (llama_ens5.py:63-90,112,169,202-217,267-269,330-333,486,530), the open_clip ViT linears and the
+ * conv1 patch embedding as a GEMM (llama_ens5.py:354-370), apply_rotary_emb (llama_ens5.py:118),
+ * and their autograd dgrad / wgrad forms.
+ * ------------------------------------------------------------------------------------------- */
+int a3_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, long long lda,
+                 long long ldb, long long ldc, int a_mn_major, int b_mn_major, const void* bias,
+                 const void* residual, long long ldr, int act, int out_fp32, int accumulate,
+                 float alpha, const void* rope_table, int rope_cols, int rope_period, int rope_pos0,
+                 void* stream);
+
+/* Weight-streaming GEMV-shaped linear for decode: Y[M,N] = X[M,K] W[N,K]^T (+residual), M <= 16.
+ * HBM-bound (reads W once).  out_fp32 for the LM head (llama_ens5.py:530-531). */
+int a3_linear_small_m(const void* X, const void* W, void* Y, int M, int N, int K, long long ldx,
+                      long long ldw, long long ldy, const void* residual, long long ldr,
+                      int out_fp32, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Norms.  x,y bf16 [rows][D]; weights bf16; statistics fp32.
+ * RMSNorm: reference model/accessory/model/components.py:39-53 -- y = bf16(x*rsqrt(mean(x^2)+eps)) * w
+ * (normalise in fp32, round to bf16, then multiply by the bf16 weight and round again).
+ * LayerNorm: nn.LayerNorm eps 1e-5 of the ViT (ln_pre / ln_1 / ln_2 / ln_post) and of
+ * visual_proj[1] (llama_ens5.py:330-333): fp32 statistics, output bf16.
+ * ------------------------------------------------------------------------------------------- */
+int a3_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int rows, int D,
+                   long long ldx, long long ldy, float eps, void* stream);
+/* dx = d/dx of the above given dy; dw_partial [nparts][D] fp32 (caller sums over parts with
+ * a3_colsum_partials).  add_to_dx != 0: dx += (residual stream gradient fused). */
+int a3_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx,
+                   float* dw_partial, int nparts, int rows, int D, int add_to_dx, void* stream);
+int a3_layernorm_fwd(const void* x, const void* w, const void* b, void* y, float* mean,
+                     float* rstd, int rows, int D, long long ldx, long long ldy, float eps,
+                     void* stream);
+int a3_layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean,
+                     const float* rstd, void* dx, float* dw_partial, float* db_partial, int nparts,
+                     int rows, int D, void* stream);
+/* out[D] (bf16 or fp32) (+)= sum_p partial[p][D] */
+int a3_colsum_partials(const float* partial, int nparts, int D, void* out, int out_fp32,
+                       int accumulate, void* stream);
+/* out[N] (bf16) = sum_m X[m][N] (bias gradients). */
+int a3_colsum_bf16(const void* X, int M, int N, long long ldx, void* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * RoPE (absent reference file LLM/llama.py, call sites llama_ens5.py:118,271-274):
+ * table[pos][j] = (cos, sin)(pos * theta^(-2j/128)); interleaved pairs; fp32 math, one rounding.
+ * ------------------------------------------------------------------------------------------- */
+int a3_rope_table(float* table, int max_pos, int head_dim, float theta, void* stream);
+/* In-place rotation of `heads` heads of head_dim at x[row*ld + h*head_dim ..]; pos = pos0 + row %
+ * period.  inverse != 0 rotates by -angle (the backward pass). */
+int a3_rope_apply(void* x, long long ld, int rows, int heads, int head_dim, const float* table,
+                  int period, int pos0, int inverse, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Attention.  Element (b, t, h, d) of q lives at q + (b*Tq + t)*ldq + h*head_dim + d (same for
+ * k, v with Tk / ldk / ldv and for o with ldo); head_dim 64 (ViT) or 128 (Llama).
+ * causal != 0: right-aligned causal mask, query t sees keys <= t + (Tk - Tq)
+ * (llama_ens5.py:181-185); lse [B][H][Tq] fp32 (natural log) is written when non-null.
+ * Replaces flash_attn_func / F.scaled_dot_product_attention (llama_ens5.py:142-167) and the
+ * nn.MultiheadAttention core of open_clip's ResidualAttentionBlock.
+ * ------------------------------------------------------------------------------------------- */
+int a3_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int H,
+                int Tq, int Tk, int head_dim, long long ldq, long long ldk, long long ldv,
+                long long ldo, long long q_bstride, long long kv_bstride, float scale, int causal,
+                void* stream);
+/* Backward of the above for Tq == Tk, head_dim 128 (fine-tune path).  delta [B][H][T] fp32 scratch,
+ * dq_acc [B*T][H*128] fp32 scratch (zeroed by the call); dq/dk/dv share the q/k/v layout. */
+int a3_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout,
+                const float* lse, float* delta, float* dq_acc, void* dq, void* dk, void* dv, int B,
+                int H, int T, int head_dim, long long ldqkv, long long ldo, long long lddqkv,
+                float scale, int causal, void* stream);
+/* Single-query decode attention over the KV cache (llama_ens5.py:121-129,142-167 with seqlen 1):
+ * cache layout [B][max_seq][H][128] bf16; q [B][H*128]; ctx = number of valid positions. */
+int a3_attn_decode(const void* q, const void* kcache, const void* vcache, void* o, float* scratch,
+                   int B, int H, int head_dim, int ctx, int max_seq, long long ldq, long long ldo,
+                   float scale, void* stream);
+/* KV-cache append (llama_ens5.py:121-127): copy rows [B][T] of k and v (strided, ld) into
+ * cache[:, start:start+T]. */
+int a3_kv_append(const void* k, const void* v, long long ld, void* kcache, void* vcache, int B,
+                 int T, int H, int head_dim, int start, int max_seq, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Gated-SiLU MLP glue (llama_ens5.py:213-217): y = bf16(bf16(silu(g)) * u), gu = [rows][2F] (g | u).
+ * ------------------------------------------------------------------------------------------- */
+int a3_swiglu_fwd(const void* gu, void* y, int rows, int F, void* stream);
+int a3_swiglu_bwd(const void* gu, const void* dy, void* dgu, int rows, int F, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Embedding gather + image splice (llama_ens5.py:464-479,495-511).
+ * h[b, 0] = E[tok[b,0]]; h[b, 1] = start_img; h[b, 2..2+Nimg) = img[b]; h[b, Nimg+2] = end_img;
+ * h[b, W + t] = E[tok[b,t]], t >= 1, W = Nimg + 2 (W = 0 when img is null).
+ * ------------------------------------------------------------------------------------------- */
+int a3_embed_splice(const long long* tokens, const void* E, const void* img, const void* start_img,
+                    const void* end_img, void* h, int B, int T, int Nimg, int D, long long ld_img,
+                    void* stream);
+/* Backward: dE[tok] += dh rows of text positions (bf16 atomics), d_img, d_start, d_end. */
+int a3_embed_splice_bwd(const long long* tokens, const void* dh, void* dE, void* d_img,
+                        float* d_start_f32, float* d_end_f32, int B, int T, int Nimg, int D,
+                        void* stream);
+
+/* ViT front end (llama_ens5.py:354-363).  patches: NCHW image (fp32 or bf16) -> A [B*g*g][Kpad]
+ * bf16 with k = (c, ky, kx), zero padded to Kpad.  assemble: x[b,0] = cls + pos[0];
+ * x[b,1+p] = patch_out[b,p] + pos[1+p]; then ln_pre -> y (bf16). */
+int a3_vit_patchify(const void* image, int image_is_fp32, void* A, int B, int S, int patch, int Kpad,
+                    void* stream);
+int a3_vit_assemble_lnpre(const void* patch_out, const void* cls, const void* pos, const void* ln_w,
+                          const void* ln_b, void* x, int B, int Np, int D, float eps, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Loss (meta.py:256-262): CrossEntropyLoss(ignore_index=0), mean over non-ignored rows, computed
+ * in fp32 from bf16 logits [rows][V].  row r uses label labels[r] (already shifted by the caller).
+ * Writes per-row loss (0 for ignored) and overwrites logits with dlogits = (softmax - onehot) *
+ * grad_scale / count when want_grad != 0.  `count` (device int) = number of non-ignored rows,
+ * must be pre-computed with a3_count_nonzero.
+ * ------------------------------------------------------------------------------------------- */
+int a3_count_nonzero(const long long* labels, int n, int* count, void* stream);
+int a3_cross_entropy(void* logits, long long ld, const long long* labels, float* row_loss,
+                     const int* count, int rows, int V, float grad_scale, int want_grad,
+                     void* stream);
+/* loss = sum(row_loss) / max(count,1) -> out[0] (fp32) */
+int a3_loss_reduce(const float* row_loss, int rows, const int* count, float* out, void* stream);
+/* Greedy sampling (meta.py:461): argmax over fp32 logits [B][V], lowest index wins ties. */
+int a3_argmax(const float* logits, long long ld, int B, int V, long long* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Optimiser (main_finetune.py:284-285, util/misc.py:586-599, util/clip_grad.py:187-193).
+ * sumsq: out[0] += sum(g^2) over n bf16 gradients (fp32 accumulate).  adamw: one fused pass over
+ * a flat range -- g = bf16 grad * clip_coef(*norm_sq), m,v fp32, master fp32, shadow bf16 weight.
+ * clip: coef = min(1, max_norm / (sqrt(norm_sq) + 1e-6)); max_norm <= 0 disables clipping.
+ * ------------------------------------------------------------------------------------------- */
+int a3_sumsq_bf16(const void* g, long long n, float* out, void* stream);
+int a3_adamw(float* master, void* weight_bf16, const void* grad_bf16, float* m, float* v,
+             long long n, float lr, float beta1, float beta2, float eps, float weight_decay,
+             int step, const float* norm_sq, float max_norm, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* A3VLM_B200_H_ */
