@@ -1,0 +1,429 @@
+// FlashAttention-style backward on tcgen05 / TMEM, fed by TMA (sm_100a), head_dim 128.
+//
+// One CTA = 128 keys of one (batch, head); thread t owns key row t (TMEM lane t).  For each tile of
+// 64 queries (all five contractions on tcgen05, transposes are free through the UMMA majorness):
+//     S^T  = K Q^T            A = K  (K-major)   B = Q   (K-major)    -> TMEM [  0, 64)
+//     dP^T = V dO^T           A = V  (K-major)   B = dO  (K-major)    -> TMEM [ 64,128)
+//     P^T = exp2(S^T c - lse), dS^T = P^T (dP^T - delta) scale        -> smem (bf16, SW128)
+//     dV  += P^T  dO          A = P^T (K-major)  B = dO  (MN-major)   -> TMEM [256,384)
+//     dK  += dS^T Q           A = dS^T (K-major) B = Q   (MN-major)   -> TMEM [384,512)
+//     dQ^T = K^T dS           A = K  (MN-major)  B = dS^T (MN-major)  -> TMEM [128,192)
+// dQ^T has head-dim on lanes and queries on columns, so each warp's red.global.add.f32 on the fp32
+// dQ accumulator is a coalesced 128-byte line.  Q/dO tiles are double-buffered by TMA and the S/dP
+// MMAs of the next tile are issued behind the dV/dK/dQ MMAs of the current one.
+//
+// Replaces the autograd backward of flash_attn_func / SDPA (reference
+// model/accessory/model/LLM/llama_ens5.py:142-167) on the fine-tune path
+// (model/accessory/engine_finetune.py:60-68).
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace a3 {
+
+constexpr int BW_KEYS = 128;
+constexpr int BW_Q = 64;
+constexpr int BW_HD = 128;
+
+struct BwdSmem {
+  static constexpr int KV_BYTES = BW_KEYS * BW_HD * 2;  // 32 KB
+  static constexpr int QT_BYTES = BW_Q * BW_HD * 2;     // 16 KB
+  static constexpr int PT_BYTES = BW_KEYS * BW_Q * 2;   // 16 KB
+  static constexpr int OFF_K = 0;
+  static constexpr int OFF_V = OFF_K + KV_BYTES;
+  static constexpr int OFF_Q = OFF_V + KV_BYTES;       // [2]
+  static constexpr int OFF_DO = OFF_Q + 2 * QT_BYTES;  // [2]
+  static constexpr int OFF_P = OFF_DO + 2 * QT_BYTES;
+  static constexpr int OFF_DS = OFF_P + PT_BYTES;
+  static constexpr int OFF_STAT = OFF_DS + PT_BYTES;  // lse[2][64], delta[2][64] fp32
+  static constexpr int OFF_BAR = OFF_STAT + 4 * BW_Q * 4;
+  static constexpr int TOTAL = OFF_BAR + 128;
+};
+
+struct BwdParams {
+  const float* lse;    // [B][H][T]
+  const float* delta;  // [B][H][T]
+  float* dq_acc;       // [B*T][H*128] fp32
+  __nv_bfloat16* dk;
+  __nv_bfloat16* dv;
+  long long lddkv;
+  int B, H, T;
+  float scale;
+  int causal;
+};
+
+__device__ __forceinline__ void red_add_f32(float* addr, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(128)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                const BwdParams p) {
+  using S = BwdSmem;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (smem_u32(smem) & 1023u) __trap();
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
+  uint64_t* kv_full = bars;       // [1]
+  uint64_t* q_full = bars + 1;    // [2]
+  uint64_t* sdp_bar = bars + 3;   // S^T / dP^T of the current tile ready
+  uint64_t* grad_bar = bars + 4;  // dV / dK / dQ^T MMAs of the current tile retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  float* s_lse = reinterpret_cast<float*>(smem + S::OFF_STAT);   // [2][64]
+  float* s_delta = s_lse + 2 * BW_Q;                             // [2][64]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  const int key0 = blockIdx.x * BW_KEYS, h = blockIdx.y, b = blockIdx.z;
+  const int T = p.T;
+  const int n_q_tiles = (T + BW_Q - 1) / BW_Q;
+  const int i_start = p.causal ? key0 / BW_Q : 0;  // first query tile that can see these keys
+  const int n_iter = n_q_tiles - i_start;
+
+  if (tid == 0) {
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmK);
+    prefetch_tmap(&tmV);
+    prefetch_tmap(&tmDO);
+    mbar_init(kv_full, 1);
+    mbar_init(&q_full[0], 1);
+    mbar_init(&q_full[1], 1);
+    mbar_init(sdp_bar, 1);
+    mbar_init(grad_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  constexpr uint32_t C_S = 0, C_DP = 64, C_DQ = 128, C_DV = 256, C_DK = 384;
+
+  const uint32_t sb = smem_u32(smem);
+  const uint32_t sK = sb + S::OFF_K, sV = sb + S::OFF_V, sQ = sb + S::OFF_Q, sDO = sb + S::OFF_DO,
+                 sP = sb + S::OFF_P, sDS = sb + S::OFF_DS;
+  constexpr uint32_t idesc_sdp = make_idesc_bf16(128, BW_Q, 0, 0);   // [keys x q]
+  constexpr uint32_t idesc_dkv = make_idesc_bf16(128, BW_HD, 0, 1);  // [keys x hd], B MN-major
+  constexpr uint32_t idesc_dq = make_idesc_bf16(128, BW_Q, 1, 1);    // [hd x q], both MN-major
+
+  const long long stat_base = (static_cast<long long>(b) * p.H + h) * T;
+  auto load_stats = [&](int i) {  // lse / delta of query tile i -> smem stage i&1
+    const int st = i & 1;
+    const int qi = i * BW_Q + (tid & 63);
+    if (tid < 64) s_lse[st * BW_Q + tid] = qi < T ? p.lse[stat_base + qi] : INFINITY;
+    else s_delta[st * BW_Q + (tid - 64)] = qi < T ? p.delta[stat_base + qi] : 0.f;
+  };
+  auto load_q = [&](int i) {  // TMA: Q_i and dO_i -> stage i&1
+    const int st = i & 1;
+    mbar_arrive_expect_tx(&q_full[st], 2 * S::QT_BYTES);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      tma_load_3d(smem + S::OFF_Q + st * S::QT_BYTES + c * (BW_Q * 128), &tmQ, &q_full[st],
+                  h * BW_HD + c * 64, i * BW_Q, b);
+      tma_load_3d(smem + S::OFF_DO + st * S::QT_BYTES + c * (BW_Q * 128), &tmDO, &q_full[st],
+                  h * BW_HD + c * 64, i * BW_Q, b);
+    }
+  };
+  auto issue_sdp = [&](int i) {
+    const int st = i & 1;
+#pragma unroll
+    for (int kk = 0; kk < BW_HD / 16; ++kk) {
+      const uint32_t ch = kk >> 2, inner = (kk & 3) * 32;
+      const uint64_t ak = make_smem_desc_sw128(sK + ch * (BW_KEYS * 128) + inner, 16, 1024);
+      const uint64_t bq =
+          make_smem_desc_sw128(sQ + st * S::QT_BYTES + ch * (BW_Q * 128) + inner, 16, 1024);
+      umma_bf16(tmem_base + C_S, ak, bq, idesc_sdp, kk > 0 ? 1u : 0u);
+    }
+#pragma unroll
+    for (int kk = 0; kk < BW_HD / 16; ++kk) {
+      const uint32_t ch = kk >> 2, inner = (kk & 3) * 32;
+      const uint64_t av = make_smem_desc_sw128(sV + ch * (BW_KEYS * 128) + inner, 16, 1024);
+      const uint64_t bd =
+          make_smem_desc_sw128(sDO + st * S::QT_BYTES + ch * (BW_Q * 128) + inner, 16, 1024);
+      umma_bf16(tmem_base + C_DP, av, bd, idesc_sdp, kk > 0 ? 1u : 0u);
+    }
+  };
+  auto issue_grads = [&](int i, bool first) {
+    const int st = i & 1;
+#pragma unroll
+    for (int kk = 0; kk < BW_Q / 16; ++kk) {  // reduce over the 64 queries
+      const uint64_t ap = make_smem_desc_sw128(sP + kk * 32, 16, 1024);
+      const uint64_t ads = make_smem_desc_sw128(sDS + kk * 32, 16, 1024);
+      const uint64_t bdo =
+          make_smem_desc_sw128(sDO + st * S::QT_BYTES + kk * (16 * 128), BW_Q * 128, 1024);
+      const uint64_t bq =
+          make_smem_desc_sw128(sQ + st * S::QT_BYTES + kk * (16 * 128), BW_Q * 128, 1024);
+      const uint32_t acc = (!first || kk > 0) ? 1u : 0u;
+      umma_bf16(tmem_base + C_DV, ap, bdo, idesc_dkv, acc);
+      umma_bf16(tmem_base + C_DK, ads, bq, idesc_dkv, acc);
+    }
+#pragma unroll
+    for (int kk = 0; kk < BW_KEYS / 16; ++kk) {  // reduce over the 128 keys
+      const uint64_t ak = make_smem_desc_sw128(sK + kk * (16 * 128), BW_KEYS * 128, 1024);
+      const uint64_t bds = make_smem_desc_sw128(sDS + kk * (16 * 128), BW_KEYS * 128, 1024);
+      umma_bf16(tmem_base + C_DQ, ak, bds, idesc_dq, kk > 0 ? 1u : 0u);
+    }
+  };
+
+  if (n_iter > 0) {
+    if (tid == 0) {
+      mbar_arrive_expect_tx(kv_full, 2 * S::KV_BYTES);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        tma_load_3d(smem + S::OFF_K + c * (BW_KEYS * 128), &tmK, kv_full, h * BW_HD + c * 64, key0, b);
+        tma_load_3d(smem + S::OFF_V + c * (BW_KEYS * 128), &tmV, kv_full, h * BW_HD + c * 64, key0, b);
+      }
+      load_q(i_start);
+      mbar_wait(kv_full, 0);
+      mbar_wait(&q_full[i_start & 1], 0);
+      tc_fence_after();
+      issue_sdp(i_start);
+      umma_commit(sdp_bar);
+      if (n_iter > 1) load_q(i_start + 1);
+    }
+    load_stats(i_start);
+  }
+  __syncthreads();
+
+  const int key = key0 + warp * 32 + lane;
+  const bool key_ok = key < T;
+  const float c2 = p.scale * 1.4426950408889634f;
+  const float LOG2E = 1.4426950408889634f;
+  uint8_t* p_row = smem + S::OFF_P + (warp * 32 + lane) * 128;
+  uint8_t* ds_row = smem + S::OFF_DS + (warp * 32 + lane) * 128;
+  const int sw = lane & 7;
+
+  for (int it = 0; it < n_iter; ++it) {
+    const int i = i_start + it;
+    const int st = i & 1;
+    // prefetch the statistics of the next tile (consumed after this iteration's barrier)
+    if (it + 1 < n_iter) load_stats(i + 1);
+    mbar_wait(sdp_bar, it & 1);
+    tc_fence_after();
+    const int qbase = i * BW_Q;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t s[32], dp[32];
+      tmem_ld_32x32(t_lane + C_S + half * 32, s);
+      tmem_ld_32x32(t_lane + C_DP + half * 32, dp);
+      tmem_ld_wait();
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        uint32_t pw[4], dw[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          float pv[2], dv[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int idx = u * 8 + t * 2 + e;
+            const int qc = half * 32 + idx;
+            const int qi = qbase + qc;
+            const bool vis = key_ok && (!p.causal || key <= qi);
+            const float l2 = s_lse[st * BW_Q + qc] * LOG2E;
+            const float pr = vis ? exp2f(__uint_as_float(s[idx]) * c2 - l2) : 0.f;
+            pv[e] = pr;
+            dv[e] = pr * (__uint_as_float(dp[idx]) - s_delta[st * BW_Q + qc]) * p.scale;
+          }
+          pw[t] = pack_bf16x2(pv[0], pv[1]);
+          dw[t] = pack_bf16x2(dv[0], dv[1]);
+        }
+        const int unit = half * 4 + u;
+        *reinterpret_cast<uint4*>(p_row + ((unit ^ sw) << 4)) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+        *reinterpret_cast<uint4*>(ds_row + ((unit ^ sw) << 4)) = make_uint4(dw[0], dw[1], dw[2], dw[3]);
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      issue_grads(i, it == 0);
+      umma_commit(grad_bar);
+      if (it + 1 < n_iter) {
+        mbar_wait(&q_full[(i + 1) & 1], ((it + 1) >> 1) & 1);
+        tc_fence_after();
+        issue_sdp(i + 1);
+        umma_commit(sdp_bar);
+      }
+    }
+    __syncwarp();
+    // dQ^T readout: lanes = head dims, columns = queries -> coalesced fp32 reductions
+    mbar_wait(grad_bar, it & 1);
+    tc_fence_after();
+    if (tid == 0 && it + 2 < n_iter) load_q(i + 2);  // stage st is free: its MMAs have retired
+    __syncwarp();
+    {
+      float* dq_col = p.dq_acc + (static_cast<long long>(b) * T + qbase) * (p.H * BW_HD) + h * BW_HD +
+                      warp * 32 + lane;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t dq[32];
+        tmem_ld_32x32(t_lane + C_DQ + half * 32, dq);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const int qc = half * 32 + c;
+          if (qbase + qc < T) red_add_f32(dq_col + static_cast<long long>(qc) * (p.H * BW_HD), __uint_as_float(dq[c]));
+        }
+      }
+    }
+    // The next iteration's issue_grads overwrites dQ^T; order the reads above before it.
+    tc_fence_before();
+  }
+
+  // ---- epilogue: dV, dK -> bf16
+  if (n_iter > 0) {
+    // grad_bar of the last iteration has been waited on above by every thread
+    __nv_bfloat16* dvr = p.dv + (static_cast<long long>(b) * T + key) * p.lddkv + h * BW_HD;
+    __nv_bfloat16* dkr = p.dk + (static_cast<long long>(b) * T + key) * p.lddkv + h * BW_HD;
+#pragma unroll
+    for (int c = 0; c < BW_HD / 32; ++c) {
+      uint32_t a[32], d[32];
+      tmem_ld_32x32(t_lane + C_DV + c * 32, a);
+      tmem_ld_32x32(t_lane + C_DK + c * 32, d);
+      tmem_ld_wait();
+      if (key_ok) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 q;
+          q.x = pack_bf16x2(__uint_as_float(a[i]), __uint_as_float(a[i + 1]));
+          q.y = pack_bf16x2(__uint_as_float(a[i + 2]), __uint_as_float(a[i + 3]));
+          q.z = pack_bf16x2(__uint_as_float(a[i + 4]), __uint_as_float(a[i + 5]));
+          q.w = pack_bf16x2(__uint_as_float(a[i + 6]), __uint_as_float(a[i + 7]));
+          *reinterpret_cast<uint4*>(dvr + c * 32 + i) = q;
+          q.x = pack_bf16x2(__uint_as_float(d[i]), __uint_as_float(d[i + 1]));
+          q.y = pack_bf16x2(__uint_as_float(d[i + 2]), __uint_as_float(d[i + 3]));
+          q.z = pack_bf16x2(__uint_as_float(d[i + 4]), __uint_as_float(d[i + 5]));
+          q.w = pack_bf16x2(__uint_as_float(d[i + 6]), __uint_as_float(d[i + 7]));
+          *reinterpret_cast<uint4*>(dkr + c * 32 + i) = q;
+        }
+      }
+    }
+  } else if (key_ok) {
+    // keys no query can see (cannot happen for causal Tq == Tk, kept for safety): zero gradient
+    __nv_bfloat16* dvr = p.dv + (static_cast<long long>(b) * T + key) * p.lddkv + h * BW_HD;
+    __nv_bfloat16* dkr = p.dk + (static_cast<long long>(b) * T + key) * p.lddkv + h * BW_HD;
+    for (int c = 0; c < BW_HD / 8; ++c) {
+      reinterpret_cast<uint4*>(dvr)[c] = make_uint4(0, 0, 0, 0);
+      reinterpret_cast<uint4*>(dkr)[c] = make_uint4(0, 0, 0, 0);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// delta[b][h][t] = sum_d dO[b,t,h,d] * O[b,t,h,d]   (one warp per (b,t,h))
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o,
+                                  const __nv_bfloat16* __restrict__ dout, float* __restrict__ delta,
+                                  int B, int H, int T, long long ldo) {
+  const long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= (long long)B * T * H) return;
+  const int hh = (int)(w % H);
+  const long long bt = w / H;
+  const long long off = bt * ldo + hh * BW_HD + lane * 4;
+  const uint2 a = *reinterpret_cast<const uint2*>(o + off);
+  const uint2 d = *reinterpret_cast<const uint2*>(dout + off);
+  const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y);
+  const float2 d0 = unpack_bf16x2(d.x), d1 = unpack_bf16x2(d.y);
+  float s = a0.x * d0.x + a0.y * d0.y + a1.x * d1.x + a1.y * d1.y;
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+  if (lane == 0) {
+    const int bb = (int)(bt / T), t = (int)(bt % T);
+    delta[((long long)bb * H + hh) * T + t] = s;
+  }
+}
+
+// dq (bf16, strided) = dq_acc (fp32, dense [B*T][H*128])
+__global__ void attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq,
+                                       long long rows, int width, long long lddq) {
+  const int cpr = width / 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < rows * cpr;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cpr;
+    const int c = (int)(i - r * cpr);
+    const float4 a = *reinterpret_cast<const float4*>(acc + r * width + c * 8);
+    const float4 b = *reinterpret_cast<const float4*>(acc + r * width + c * 8 + 4);
+    uint4 q;
+    q.x = pack_bf16x2(a.x, a.y);
+    q.y = pack_bf16x2(a.z, a.w);
+    q.z = pack_bf16x2(b.x, b.y);
+    q.w = pack_bf16x2(b.z, b.w);
+    *reinterpret_cast<uint4*>(dq + r * lddq + c * 8) = q;
+  }
+}
+
+}  // namespace a3
+
+extern "C" int a3_attn_bwd(const void* q, const void* k, const void* v, const void* o,
+                           const void* dout, const float* lse, float* delta, float* dq_acc, void* dq,
+                           void* dk, void* dv, int B, int H, int T, int head_dim, long long ldqkv,
+                           long long ldo, long long lddqkv, float scale, int causal, void* stream) {
+  using namespace a3;
+  if (B <= 0 || H <= 0 || T <= 0) return A3_OK;
+  if (head_dim != BW_HD) return set_error(A3_ERR_UNSUPPORTED, "a3_attn_bwd: head_dim must be 128");
+  if ((ldqkv & 7) || (ldo & 7) || (lddqkv & 7))
+    return set_error(A3_ERR_ARG, "a3_attn_bwd: strides must be multiples of 8 elements");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int width = H * BW_HD;
+  {
+    const long long warps = (long long)B * T * H;
+    const long long blocks = (warps * 32 + 255) / 256;
+    attn_delta_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(o),
+                                                       reinterpret_cast<const __nv_bfloat16*>(dout),
+                                                       delta, B, H, T, ldo);
+    int rc = check_launch("a3_attn_bwd(delta)");
+    if (rc) return rc;
+  }
+  cudaError_t e = cudaMemsetAsync(dq_acc, 0, (size_t)B * T * width * sizeof(float), s);
+  if (e != cudaSuccess) return set_error(A3_ERR_CUDA, cudaGetErrorString(e));
+
+  CUtensorMap tmQ, tmK, tmV, tmDO;
+  int rc = make_tmap_3d_bf16(&tmQ, q, (uint64_t)width, (uint64_t)T, (uint64_t)B, (uint64_t)ldqkv * 2,
+                             (uint64_t)T * ldqkv * 2, 64, BW_Q, 1);
+  if (rc) return rc;
+  rc = make_tmap_3d_bf16(&tmK, k, (uint64_t)width, (uint64_t)T, (uint64_t)B, (uint64_t)ldqkv * 2,
+                         (uint64_t)T * ldqkv * 2, 64, BW_KEYS, 1);
+  if (rc) return rc;
+  rc = make_tmap_3d_bf16(&tmV, v, (uint64_t)width, (uint64_t)T, (uint64_t)B, (uint64_t)ldqkv * 2,
+                         (uint64_t)T * ldqkv * 2, 64, BW_KEYS, 1);
+  if (rc) return rc;
+  rc = make_tmap_3d_bf16(&tmDO, dout, (uint64_t)width, (uint64_t)T, (uint64_t)B, (uint64_t)ldo * 2,
+                         (uint64_t)T * ldo * 2, 64, BW_Q, 1);
+  if (rc) return rc;
+
+  static bool configured = false;
+  if (!configured) {
+    e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             BwdSmem::TOTAL);
+    if (e != cudaSuccess) return set_error(A3_ERR_CUDA, cudaGetErrorString(e));
+    configured = true;
+  }
+  BwdParams p;
+  p.lse = lse;
+  p.delta = delta;
+  p.dq_acc = dq_acc;
+  p.dk = reinterpret_cast<__nv_bfloat16*>(dk);
+  p.dv = reinterpret_cast<__nv_bfloat16*>(dv);
+  p.lddkv = lddqkv;
+  p.B = B; p.H = H; p.T = T;
+  p.scale = scale;
+  p.causal = causal ? 1 : 0;
+  dim3 grid((T + BW_KEYS - 1) / BW_KEYS, H, B);
+  attn_bwd_kernel<<<grid, 128, BwdSmem::TOTAL, s>>>(tmQ, tmK, tmV, tmDO, p);
+  rc = check_launch("a3_attn_bwd");
+  if (rc) return rc;
+  const long long rows = (long long)B * T;
+  long long blocks = (rows * (width / 8) + 255) / 256;
+  if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
+  attn_dq_convert_kernel<<<(unsigned)blocks, 256, 0, s>>>(dq_acc, reinterpret_cast<__nv_bfloat16*>(dq),
+                                                          rows, width, lddqkv);
+  return check_launch("a3_attn_bwd(dq)");
+}

@@ -1,0 +1,526 @@
+// Gather / scatter, ViT front end, loss, sampling and optimiser kernels of the hot path.  All are
+// HBM-bound byte movers or row reductions: 16-byte vector accesses, one CTA per row or a
+// grid-stride over flat ranges sized in multiples of the SM count.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace a3 {
+
+__device__ __forceinline__ float warp_sum_m(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max_m(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float block_sum_m(float v, float* red) {
+  v = warp_sum_m(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float t = (l < (blockDim.x >> 5)) ? red[l] : 0.f;
+  return warp_sum_m(t);
+}
+__device__ __forceinline__ float block_max_m(float v, float* red) {
+  v = warp_max_m(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float t = (l < (blockDim.x >> 5)) ? red[l] : -INFINITY;
+  return warp_max_m(t);
+}
+__device__ __forceinline__ void ld8(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 q = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float2 v = unpack_bf16x2(w[t]);
+    f[2 * t] = v.x;
+    f[2 * t + 1] = v.y;
+  }
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&f)[8]) {
+  uint4 o;
+  o.x = pack_bf16x2(f[0], f[1]);
+  o.y = pack_bf16x2(f[2], f[3]);
+  o.z = pack_bf16x2(f[4], f[5]);
+  o.w = pack_bf16x2(f[6], f[7]);
+  *reinterpret_cast<uint4*>(p) = o;
+}
+
+// ------------------------------------------------------------------ embedding gather + splice
+// One CTA per output row of h [B][L][D], L = T + W, W = Nimg + 2 (0 without image).
+__global__ void embed_splice_kernel(const long long* __restrict__ tokens,
+                                    const __nv_bfloat16* __restrict__ E,
+                                    const __nv_bfloat16* __restrict__ img,
+                                    const __nv_bfloat16* __restrict__ start_img,
+                                    const __nv_bfloat16* __restrict__ end_img,
+                                    __nv_bfloat16* __restrict__ h, int T, int Nimg, int D,
+                                    long long ld_img) {
+  const int W = img ? Nimg + 2 : 0;
+  const int L = T + W;
+  const int b = blockIdx.x / L, l = blockIdx.x % L;
+  const __nv_bfloat16* src;
+  if (l == 0) src = E + tokens[(long long)b * T] * D;
+  else if (l > W) src = E + tokens[(long long)b * T + (l - W)] * D;
+  else if (l == 1) src = start_img;
+  else if (l == W) src = end_img;
+  else src = img + ((long long)b * Nimg + (l - 2)) * ld_img;
+  // note: for W == 0, l >= 1 > W takes the text branch.
+  __nv_bfloat16* dst = h + (long long)blockIdx.x * D;
+  for (int c = threadIdx.x; c < D / 8; c += blockDim.x)
+    reinterpret_cast<uint4*>(dst)[c] = __ldg(reinterpret_cast<const uint4*>(src) + c);
+}
+
+// Backward.  Text rows scatter-add into dE with bf16x2 atomics (dE pre-zeroed by the caller);
+// image rows are copied to d_img; start / end tags are summed over the batch in fp32.
+__global__ void embed_splice_bwd_kernel(const long long* __restrict__ tokens,
+                                        const __nv_bfloat16* __restrict__ dh,
+                                        __nv_bfloat16* __restrict__ dE,
+                                        __nv_bfloat16* __restrict__ d_img, int T, int Nimg, int D,
+                                        int has_img) {
+  const int W = has_img ? Nimg + 2 : 0;
+  const int L = T + W;
+  const int b = blockIdx.x / L, l = blockIdx.x % L;
+  const __nv_bfloat16* src = dh + (long long)blockIdx.x * D;
+  if (l == 0 || l > W) {
+    const long long tok = tokens[(long long)b * T + (l == 0 ? 0 : l - W)];
+    __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(dE + tok * D);
+    for (int c = threadIdx.x; c < D / 2; c += blockDim.x)
+      atomicAdd(dst + c, reinterpret_cast<const __nv_bfloat162*>(src)[c]);
+  } else if (l >= 2 && l < W) {
+    if (d_img) {
+      __nv_bfloat16* dst = d_img + ((long long)b * Nimg + (l - 2)) * D;
+      for (int c = threadIdx.x; c < D / 8; c += blockDim.x)
+        reinterpret_cast<uint4*>(dst)[c] = reinterpret_cast<const uint4*>(src)[c];
+    }
+  }
+}
+__global__ void tag_grad_kernel(const __nv_bfloat16* __restrict__ dh, float* __restrict__ d_start,
+                                float* __restrict__ d_end, int B, int L, int W, int D) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= D) return;
+  float s = 0.f, e = 0.f;
+  for (int b = 0; b < B; ++b) {
+    s += __bfloat162float(dh[((long long)b * L + 1) * D + c]);
+    e += __bfloat162float(dh[((long long)b * L + W) * D + c]);
+  }
+  d_start[c] = s;
+  d_end[c] = e;
+}
+
+// ------------------------------------------------------------------ ViT front end
+// A[(b, py, px)][k], k = c*P*P + ky*P + kx (conv1.weight.reshape(1024,-1) order), zero padded.
+template <typename T>
+__global__ void vit_patchify_kernel(const T* __restrict__ image, __nv_bfloat16* __restrict__ A,
+                                    int S, int P, int Kpad) {
+  const int g = S / P;
+  const int b = blockIdx.x / (g * g);
+  const int pp = blockIdx.x % (g * g);
+  const int py = pp / g, px = pp % g;
+  const int K = 3 * P * P;
+  __nv_bfloat16* dst = A + (long long)blockIdx.x * Kpad;
+  for (int k = threadIdx.x; k < Kpad; k += blockDim.x) {
+    float v = 0.f;
+    if (k < K) {
+      const int c = k / (P * P), r = k % (P * P);
+      const int ky = r / P, kx = r % P;
+      v = (float)image[(((long long)b * 3 + c) * S + (py * P + ky)) * S + px * P + kx];
+    }
+    dst[k] = __float2bfloat16_rn(v);
+  }
+}
+
+// t = bf16(patch_out + pos) (cls row: bf16(cls + pos[0])); y = bf16(LayerNorm(t)).  D <= 2048.
+__global__ void __launch_bounds__(256)
+vit_assemble_lnpre_kernel(const __nv_bfloat16* __restrict__ patch_out,
+                          const __nv_bfloat16* __restrict__ cls,
+                          const __nv_bfloat16* __restrict__ pos, const __nv_bfloat16* __restrict__ lw,
+                          const __nv_bfloat16* __restrict__ lb, __nv_bfloat16* __restrict__ x, int Np,
+                          int D, float eps) {
+  __shared__ float red[32];
+  const int N = Np + 1;
+  const int b = blockIdx.x / N, t = blockIdx.x % N;
+  const __nv_bfloat16* src = t == 0 ? cls : patch_out + ((long long)b * Np + (t - 1)) * D;
+  const int c = threadIdx.x;
+  const bool on = c < D / 8;
+  float v[8];
+  float s = 0.f;
+  if (on) {
+    float pv[8];
+    ld8(src + c * 8, v);
+    ld8(pos + (long long)t * D + c * 8, pv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[j] = bf16_round(v[j] + pv[j]);
+      s += v[j];
+    }
+  }
+  const float mean = block_sum_m(s, red) / (float)D;
+  float ss = 0.f;
+  if (on) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ss += (v[j] - mean) * (v[j] - mean);
+  }
+  const float rstd = rsqrtf(block_sum_m(ss, red) / (float)D + eps);
+  if (on) {
+    float wv[8], bv[8], o[8];
+    ld8(lw + c * 8, wv);
+    ld8(lb + c * 8, bv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = (v[j] - mean) * rstd * wv[j] + bv[j];
+    st8(x + (long long)blockIdx.x * D + c * 8, o);
+  }
+}
+
+// ------------------------------------------------------------------ loss
+__global__ void count_nonzero_kernel(const long long* __restrict__ labels, int n,
+                                     int* __restrict__ count) {
+  __shared__ int red[32];
+  int c = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) c += labels[i] != 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    *count = t;
+  }
+}
+
+// One CTA per row.  CrossEntropyLoss(ignore_index=0) in fp32 on bf16 logits; optionally
+// overwrites the row with dlogits = (softmax - onehot) * grad_scale / count.
+__global__ void __launch_bounds__(256)
+cross_entropy_kernel(__nv_bfloat16* __restrict__ logits, long long ld,
+                     const long long* __restrict__ labels, float* __restrict__ row_loss,
+                     const int* __restrict__ count, int V, float grad_scale, int want_grad) {
+  __shared__ float red[32];
+  const int row = blockIdx.x;
+  __nv_bfloat16* lr = logits + row * ld;
+  const long long label = labels[row];
+  const int nchunks = V >> 3;
+  if (label == 0) {  // ignored row: zero loss, zero gradient
+    if (threadIdx.x == 0) row_loss[row] = 0.f;
+    if (want_grad) {
+      const uint4 z = make_uint4(0, 0, 0, 0);
+      for (int c = threadIdx.x; c < nchunks; c += blockDim.x) reinterpret_cast<uint4*>(lr)[c] = z;
+    }
+    return;
+  }
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < nchunks; c += blockDim.x) {
+    float v[8];
+    ld8(lr + c * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mx = fmaxf(mx, v[j]);
+  }
+  mx = block_max_m(mx, red);
+  float sum = 0.f;
+  for (int c = threadIdx.x; c < nchunks; c += blockDim.x) {
+    float v[8];
+    ld8(lr + c * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum += __expf(v[j] - mx);
+  }
+  sum = block_sum_m(sum, red);
+  const float lse = mx + logf(sum);
+  if (threadIdx.x == 0) row_loss[row] = lse - __bfloat162float(lr[label]);
+  if (want_grad) {
+    const float scale = grad_scale / (float)max(*count, 1);
+    const float inv = 1.f / sum;
+    for (int c = threadIdx.x; c < nchunks; c += blockDim.x) {
+      float v[8], o[8];
+      ld8(lr + c * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float pr = __expf(v[j] - mx) * inv;
+        o[j] = (pr - ((long long)(c * 8 + j) == label ? 1.f : 0.f)) * scale;
+      }
+      st8(lr + c * 8, o);
+    }
+  }
+}
+
+__global__ void loss_reduce_kernel(const float* __restrict__ row_loss, int rows,
+                                   const int* __restrict__ count, float* __restrict__ out) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < rows; i += blockDim.x) s += row_loss[i];
+  s = block_sum_m(s, red);
+  if (threadIdx.x == 0) out[0] = s / (float)max(*count, 1);
+}
+
+// argmax over fp32 rows, lowest index wins ties (torch.argmax on CUDA returns the first maximum).
+__global__ void __launch_bounds__(256)
+argmax_kernel(const float* __restrict__ logits, long long ld, int V, long long* __restrict__ out) {
+  __shared__ float sv[8];
+  __shared__ int si[8];
+  const float* lr = logits + blockIdx.x * ld;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+    const float v = lr[i];
+    if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w)
+      if (sv[w] > best || (sv[w] == best && si[w] < bi)) { best = sv[w]; bi = si[w]; }
+    out[blockIdx.x] = bi == 0x7fffffff ? 0 : bi;
+  }
+}
+
+// ------------------------------------------------------------------ optimiser
+constexpr int SUMSQ_BLOCKS = 1184;  // 148 SMs x 8
+__device__ float g_sumsq_partial[SUMSQ_BLOCKS];
+__device__ unsigned int g_sumsq_done = 0;
+
+// out[0] += sum(g^2).  Fixed grid, partials combined by the last CTA in index order -> the result
+// is deterministic (no float atomics).
+__global__ void __launch_bounds__(256)
+sumsq_kernel(const __nv_bfloat16* __restrict__ g, long long n, float* __restrict__ out) {
+  __shared__ float red[32];
+  __shared__ bool last;
+  float s = 0.f;
+  const long long nchunks = n >> 3;
+  for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < nchunks;
+       c += (long long)gridDim.x * blockDim.x) {
+    float v[8];
+    ld8(g + c * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[j] * v[j];
+  }
+  if (blockIdx.x == 0)
+    for (long long i = (nchunks << 3) + threadIdx.x; i < n; i += blockDim.x) {
+      const float v = __bfloat162float(g[i]);
+      s += v * v;
+    }
+  s = block_sum_m(s, red);
+  if (threadIdx.x == 0) {
+    g_sumsq_partial[blockIdx.x] = s;
+    __threadfence();
+    const unsigned int t = atomicAdd(&g_sumsq_done, 1u);
+    last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    float t = 0.f;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x)
+      t += reinterpret_cast<volatile float*>(g_sumsq_partial)[i];
+    t = block_sum_m(t, red);
+    if (threadIdx.x == 0) {
+      out[0] += t;
+      g_sumsq_done = 0;
+    }
+  }
+}
+
+// torch.optim.AdamW semantics (decoupled weight decay, bias correction) on fp32 masters with a
+// bf16 shadow copy written in the same pass.  Gradient = bf16 grad * clip coefficient, where
+// coef = min(1, max_norm / (sqrt(norm_sq) + 1e-6))  (util/clip_grad.py:187-193).
+__global__ void __launch_bounds__(256)
+adamw_kernel(float* __restrict__ master, __nv_bfloat16* __restrict__ wbf,
+             const __nv_bfloat16* __restrict__ grad, float* __restrict__ m, float* __restrict__ v,
+             long long n, float lr, float beta1, float beta2, float eps, float wd, float bc1,
+             float bc2_sqrt, const float* __restrict__ norm_sq, float max_norm) {
+  float coef = 1.f;
+  if (norm_sq && max_norm > 0.f) coef = fminf(1.f, max_norm / (sqrtf(*norm_sq) + 1e-6f));
+  const float step_size = lr / bc1;
+  const long long nchunks = n >> 3;
+  for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < nchunks;
+       c += (long long)gridDim.x * blockDim.x) {
+    float g[8], o[8];
+    ld8(grad + c * 8, g);
+    float4 p0 = reinterpret_cast<float4*>(master)[2 * c], p1 = reinterpret_cast<float4*>(master)[2 * c + 1];
+    float4 m0 = reinterpret_cast<float4*>(m)[2 * c], m1 = reinterpret_cast<float4*>(m)[2 * c + 1];
+    float4 v0 = reinterpret_cast<float4*>(v)[2 * c], v1 = reinterpret_cast<float4*>(v)[2 * c + 1];
+    float pp[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+    float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+    float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float gj = g[j] * coef;
+      pp[j] *= (1.f - lr * wd);
+      mm[j] = beta1 * mm[j] + (1.f - beta1) * gj;
+      vv[j] = beta2 * vv[j] + (1.f - beta2) * gj * gj;
+      const float denom = sqrtf(vv[j]) / bc2_sqrt + eps;
+      pp[j] -= step_size * (mm[j] / denom);
+      o[j] = pp[j];
+    }
+    reinterpret_cast<float4*>(master)[2 * c] = make_float4(pp[0], pp[1], pp[2], pp[3]);
+    reinterpret_cast<float4*>(master)[2 * c + 1] = make_float4(pp[4], pp[5], pp[6], pp[7]);
+    reinterpret_cast<float4*>(m)[2 * c] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    reinterpret_cast<float4*>(m)[2 * c + 1] = make_float4(mm[4], mm[5], mm[6], mm[7]);
+    reinterpret_cast<float4*>(v)[2 * c] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    reinterpret_cast<float4*>(v)[2 * c + 1] = make_float4(vv[4], vv[5], vv[6], vv[7]);
+    st8(wbf + c * 8, o);
+  }
+  // scalar tail (n % 8)
+  if (blockIdx.x == 0) {
+    for (long long i = (nchunks << 3) + threadIdx.x; i < n; i += blockDim.x) {
+      const float gj = __bfloat162float(grad[i]) * coef;
+      float p = master[i] * (1.f - lr * wd);
+      const float mj = beta1 * m[i] + (1.f - beta1) * gj;
+      const float vj = beta2 * v[i] + (1.f - beta2) * gj * gj;
+      p -= step_size * (mj / (sqrtf(vj) / bc2_sqrt + eps));
+      master[i] = p; m[i] = mj; v[i] = vj;
+      wbf[i] = __float2bfloat16_rn(p);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ KV cache append
+__global__ void kv_append_kernel(const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
+                                 long long ld, __nv_bfloat16* __restrict__ kc,
+                                 __nv_bfloat16* __restrict__ vc, int T, int HD, int start,
+                                 int max_seq) {
+  const int b = blockIdx.x / T, t = blockIdx.x % T;
+  const long long src = (long long)blockIdx.x * ld;
+  const long long dst = ((long long)b * max_seq + start + t) * HD;
+  for (int c = threadIdx.x; c < HD / 8; c += blockDim.x) {
+    reinterpret_cast<uint4*>(kc + dst)[c] = reinterpret_cast<const uint4*>(k + src)[c];
+    reinterpret_cast<uint4*>(vc + dst)[c] = reinterpret_cast<const uint4*>(v + src)[c];
+  }
+}
+
+}  // namespace a3
+
+using namespace a3;
+#define BF(p) reinterpret_cast<const __nv_bfloat16*>(p)
+#define BFM(p) reinterpret_cast<__nv_bfloat16*>(p)
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" int a3_embed_splice(const long long* tokens, const void* E, const void* img,
+                               const void* start_img, const void* end_img, void* h, int B, int T,
+                               int Nimg, int D, long long ld_img, void* stream) {
+  if (D & 7) return set_error(A3_ERR_ARG, "a3_embed_splice: D % 8 != 0");
+  if (img && (!start_img || !end_img)) return set_error(A3_ERR_ARG, "a3_embed_splice: tags missing");
+  const int L = T + (img ? Nimg + 2 : 0);
+  if (B * L <= 0) return A3_OK;
+  embed_splice_kernel<<<B * L, 128, 0, ST(stream)>>>(tokens, BF(E), BF(img), BF(start_img),
+                                                     BF(end_img), BFM(h), T, Nimg, D, ld_img);
+  return check_launch("a3_embed_splice");
+}
+
+extern "C" int a3_embed_splice_bwd(const long long* tokens, const void* dh, void* dE, void* d_img,
+                                   float* d_start_f32, float* d_end_f32, int B, int T, int Nimg,
+                                   int D, void* stream) {
+  if (D & 7) return set_error(A3_ERR_ARG, "a3_embed_splice_bwd: D % 8 != 0");
+  const int has_img = d_start_f32 != nullptr;
+  const int W = has_img ? Nimg + 2 : 0;
+  const int L = T + W;
+  if (B * L <= 0) return A3_OK;
+  embed_splice_bwd_kernel<<<B * L, 128, 0, ST(stream)>>>(tokens, BF(dh), BFM(dE), BFM(d_img), T, Nimg,
+                                                         D, has_img);
+  int rc = check_launch("a3_embed_splice_bwd");
+  if (rc != A3_OK || !has_img) return rc;
+  tag_grad_kernel<<<(D + 255) / 256, 256, 0, ST(stream)>>>(BF(dh), d_start_f32, d_end_f32, B, L, W, D);
+  return check_launch("a3_embed_splice_bwd(tags)");
+}
+
+extern "C" int a3_vit_patchify(const void* image, int image_is_fp32, void* A, int B, int S,
+                               int patch, int Kpad, void* stream) {
+  if (patch <= 0 || S % patch || Kpad < 3 * patch * patch || (Kpad & 7))
+    return set_error(A3_ERR_ARG, "a3_vit_patchify: S % patch == 0, Kpad >= 3*patch^2, Kpad % 8 == 0");
+  const int g = S / patch;
+  if (B * g * g <= 0) return A3_OK;
+  if (image_is_fp32)
+    vit_patchify_kernel<float><<<B * g * g, 128, 0, ST(stream)>>>(
+        reinterpret_cast<const float*>(image), BFM(A), S, patch, Kpad);
+  else
+    vit_patchify_kernel<__nv_bfloat16><<<B * g * g, 128, 0, ST(stream)>>>(BF(image), BFM(A), S, patch, Kpad);
+  return check_launch("a3_vit_patchify");
+}
+
+extern "C" int a3_vit_assemble_lnpre(const void* patch_out, const void* cls, const void* pos,
+                                     const void* ln_w, const void* ln_b, void* x, int B, int Np, int D,
+                                     float eps, void* stream) {
+  if ((D & 7) || D > 2048) return set_error(A3_ERR_ARG, "a3_vit_assemble_lnpre: D % 8 == 0, D <= 2048");
+  if (B * (Np + 1) <= 0) return A3_OK;
+  vit_assemble_lnpre_kernel<<<B * (Np + 1), 256, 0, ST(stream)>>>(BF(patch_out), BF(cls), BF(pos),
+                                                                  BF(ln_w), BF(ln_b), BFM(x), Np, D, eps);
+  return check_launch("a3_vit_assemble_lnpre");
+}
+
+extern "C" int a3_count_nonzero(const long long* labels, int n, int* count, void* stream) {
+  count_nonzero_kernel<<<1, 1024, 0, ST(stream)>>>(labels, n, count);
+  return check_launch("a3_count_nonzero");
+}
+
+extern "C" int a3_cross_entropy(void* logits, long long ld, const long long* labels, float* row_loss,
+                                const int* count, int rows, int V, float grad_scale, int want_grad,
+                                void* stream) {
+  if ((V & 7) || (ld & 7)) return set_error(A3_ERR_ARG, "a3_cross_entropy: V % 8 == 0 and ld % 8 == 0");
+  if (rows <= 0) return A3_OK;
+  cross_entropy_kernel<<<rows, 256, 0, ST(stream)>>>(BFM(logits), ld, labels, row_loss, count, V,
+                                                     grad_scale, want_grad);
+  return check_launch("a3_cross_entropy");
+}
+
+extern "C" int a3_loss_reduce(const float* row_loss, int rows, const int* count, float* out,
+                              void* stream) {
+  loss_reduce_kernel<<<1, 1024, 0, ST(stream)>>>(row_loss, rows, count, out);
+  return check_launch("a3_loss_reduce");
+}
+
+extern "C" int a3_argmax(const float* logits, long long ld, int B, int V, long long* out, void* stream) {
+  if (B <= 0) return A3_OK;
+  argmax_kernel<<<B, 256, 0, ST(stream)>>>(logits, ld, V, out);
+  return check_launch("a3_argmax");
+}
+
+extern "C" int a3_sumsq_bf16(const void* g, long long n, float* out, void* stream) {
+  if (n <= 0) return A3_OK;
+  if (reinterpret_cast<uintptr_t>(g) & 15) return set_error(A3_ERR_ARG, "a3_sumsq_bf16: 16-byte alignment");
+  long long blocks = ((n >> 3) + 255) / 256;
+  if (blocks > SUMSQ_BLOCKS) blocks = SUMSQ_BLOCKS;
+  if (blocks < 1) blocks = 1;
+  sumsq_kernel<<<(int)blocks, 256, 0, ST(stream)>>>(BF(g), n, out);
+  return check_launch("a3_sumsq_bf16");
+}
+
+extern "C" int a3_adamw(float* master, void* weight_bf16, const void* grad_bf16, float* m, float* v,
+                        long long n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                        int step, const float* norm_sq, float max_norm, void* stream) {
+  if (n <= 0) return A3_OK;
+  if (step < 1) return set_error(A3_ERR_ARG, "a3_adamw: step starts at 1");
+  if ((reinterpret_cast<uintptr_t>(master) & 31) || (reinterpret_cast<uintptr_t>(m) & 31) ||
+      (reinterpret_cast<uintptr_t>(v) & 31) || (reinterpret_cast<uintptr_t>(weight_bf16) & 15) ||
+      (reinterpret_cast<uintptr_t>(grad_bf16) & 15))
+    return set_error(A3_ERR_ARG, "a3_adamw: buffers must be 32-byte (fp32) / 16-byte (bf16) aligned");
+  const double bc1 = 1.0 - pow((double)beta1, step);
+  const double bc2 = 1.0 - pow((double)beta2, step);
+  long long blocks = ((n >> 3) + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  adamw_kernel<<<(int)blocks, 256, 0, ST(stream)>>>(master, BFM(weight_bf16), BF(grad_bf16), m, v, n, lr,
+                                                    beta1, beta2, eps, weight_decay, (float)bc1,
+                                                    (float)sqrt(bc2), norm_sq, max_norm);
+  return check_launch("a3_adamw");
+}
+
+extern "C" int a3_kv_append(const void* k, const void* v, long long ld, void* kcache, void* vcache,
+                            int B, int T, int H, int head_dim, int start, int max_seq, void* stream) {
+  if (((H * head_dim) & 7) || (ld & 7)) return set_error(A3_ERR_ARG, "a3_kv_append: alignment");
+  if (start < 0 || start + T > max_seq) return set_error(A3_ERR_ARG, "a3_kv_append: cache overflow");
+  if (B * T <= 0) return A3_OK;
+  kv_append_kernel<<<B * T, 128, 0, ST(stream)>>>(BF(k), BF(v), ld, BFM(kcache), BFM(vcache), T,
+                                                  H * head_dim, start, max_seq);
+  return check_launch("a3_kv_append");
+}

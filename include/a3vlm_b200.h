@@ -93,9 +93,10 @@ int a3_colsum_bf16(const void* X, int M, int N, long long ldx, void* out, void* 
 
 /* ---------------------------------------------------------------------------------------------
  * RoPE (absent reference file LLM/llama.py, call sites llama_ens5.py:118,271-274):
- * table[pos][j] = (cos, sin)(pos * theta^(-2j/128)); interleaved pairs; fp32 math, one rounding.
+ * table[pos][j] = (cos, sin)(pos * theta^(-2j/128)) as float2 -- built once at init on the host side
+ * with the reference's own torch expression (precompute_freqs_cis) so the angles are bit-identical;
+ * interleaved pairs; fp32 math, one rounding.
  * ------------------------------------------------------------------------------------------- */
-int a3_rope_table(float* table, int max_pos, int head_dim, float theta, void* stream);
 /* In-place rotation of `heads` heads of head_dim at x[row*ld + h*head_dim ..]; pos = pos0 + row %
  * period.  inverse != 0 rotates by -angle (the backward pass). */
 int a3_rope_apply(void* x, long long ld, int rows, int heads, int head_dim, const float* table,
