@@ -1,0 +1,245 @@
+"""Pins for the CPU oracle (oracle/a3vlm_oracle.py).  The reference has no golden vectors for this path
+(SURVEY section 4), so the oracle is pinned against two independent implementations of the same
+published architectures that ARE installed -- transformers.LlamaForCausalLM and
+transformers.CLIPVisionModel -- plus committed golden vectors (tests/golden/) and control-flow cases
+of MetaModel.generate / forward restated from M/model/meta.py."""
+import math
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import a3vlm_oracle as O  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def tiny_args(**kw):
+    d = dict(dim=64, n_layers=2, n_heads=4, vocab_size=97, multiple_of=16, max_seq_len=64, max_batch_size=4)
+    d.update(kw)
+    return O.ModelArgs(**d)
+
+
+def tiny_vis(**kw):
+    d = dict(image_size=28, patch=14, width=32, layers=2, heads=2, mlp=64)
+    d.update(kw)
+    return O.VisionArgs(**d)
+
+
+def test_ffn_hidden_dim_rule():
+    # LLM/llama_ens5.py:196-200: 11008 for 7B, 13824 for 13B
+    assert O.ffn_hidden_dim(4096, 256, None) == 11008
+    assert O.ffn_hidden_dim(5120, 256, None) == 13824
+
+
+def test_causal_mask_right_aligned():
+    m = O.make_causal_mask(3, 7)
+    exp = torch.tensor([[1, 1, 1, 1, 1, 0, 0], [1, 1, 1, 1, 1, 1, 0], [1, 1, 1, 1, 1, 1, 1]]).bool()
+    assert torch.equal(m, exp)  # the diagram at LLM/llama_ens5.py:138-141
+
+
+def test_decoder_matches_hf_llama():
+    from transformers import LlamaConfig, LlamaForCausalLM
+
+    a = tiny_args()
+    sd = O.init_params(a, None, seed=0, dtype=torch.float32, init="kaiming")
+    for k in sd:
+        if k.endswith("norm.weight"):
+            sd[k] = 1 + 0.1 * torch.randn_like(sd[k])
+    model = O.OracleTransformer(a, None, sd, act_dtype=torch.float32)
+    Fh = O.ffn_hidden_dim(a.dim, a.multiple_of, None)
+    cfg = LlamaConfig(vocab_size=a.vocab_size, hidden_size=a.dim, intermediate_size=Fh, num_hidden_layers=a.n_layers,
+                      num_attention_heads=a.n_heads, num_key_value_heads=a.n_heads, rms_norm_eps=a.norm_eps,
+                      rope_theta=a.rope_theta, attention_bias=False, tie_word_embeddings=False,
+                      max_position_embeddings=128)
+    hf = LlamaForCausalLM(cfg).eval()
+    hd = a.dim // a.n_heads
+
+    def permute(w):  # M/tools/convert_weights_to_hf.py:209-219
+        return w.view(a.n_heads, hd // 2, 2, a.dim).transpose(1, 2).reshape(a.dim, a.dim)
+
+    m = {"model.embed_tokens.weight": sd["tok_embeddings.weight"], "model.norm.weight": sd["norm.weight"],
+         "lm_head.weight": sd["output.weight"]}
+    for i in range(a.n_layers):
+        p, h = f"layers.{i}.", f"model.layers.{i}."
+        m[h + "self_attn.q_proj.weight"] = permute(sd[p + "attention.wq.weight"])
+        m[h + "self_attn.k_proj.weight"] = permute(sd[p + "attention.wk.weight"])
+        m[h + "self_attn.v_proj.weight"] = sd[p + "attention.wv.weight"]
+        m[h + "self_attn.o_proj.weight"] = sd[p + "attention.wo.weight"]
+        m[h + "mlp.gate_proj.weight"] = sd[p + "feed_forward.w1.weight"]
+        m[h + "mlp.up_proj.weight"] = sd[p + "feed_forward.w3.weight"]
+        m[h + "mlp.down_proj.weight"] = sd[p + "feed_forward.w2.weight"]
+        m[h + "input_layernorm.weight"] = sd[p + "attention_norm.weight"]
+        m[h + "post_attention_layernorm.weight"] = sd[p + "ffn_norm.weight"]
+    missing, unexpected = hf.load_state_dict(m, strict=False)
+    assert not [k for k in missing if "rotary" not in k] and not unexpected
+    tok = torch.randint(1, a.vocab_size, (2, 11), generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        ref = hf(tok).logits
+        got = model.forward(tok)
+    torch.testing.assert_close(got, ref, rtol=1e-4, atol=2e-5)
+    # prefill + decode through the KV cache reproduces the no-cache forward (LLM/llama_ens5.py:490-531)
+    l0 = model.forward_inference(tok[:, :7], 0)
+    torch.testing.assert_close(l0, ref[:, 6], rtol=1e-4, atol=2e-5)
+    l1 = model.forward_inference(tok[:, 7:8], 7)
+    torch.testing.assert_close(l1, ref[:, 7], rtol=1e-4, atol=2e-5)
+    l2 = model.forward_inference(tok[:, 8:11], 8)  # multi-token step with cache: right-aligned mask
+    torch.testing.assert_close(l2, ref[:, 10], rtol=1e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("quick", [False, True])
+def test_vit_matches_hf_clip(quick):
+    from transformers import CLIPVisionConfig, CLIPVisionModel
+
+    v = tiny_vis(quick_gelu=quick)
+    a = tiny_args()
+    sd = O.init_params(a, v, seed=3, dtype=torch.float32)
+    for k in sd:
+        if k.startswith("clip.") and (".ln_" in k or "ln_pre" in k or "ln_post" in k):
+            sd[k] = sd[k] + 0.1 * torch.randn_like(sd[k])
+    model = O.OracleTransformer(a, v, sd, act_dtype=torch.float32)
+    cfg = CLIPVisionConfig(hidden_size=v.width, intermediate_size=v.mlp, num_hidden_layers=v.layers,
+                           num_attention_heads=v.heads, image_size=v.image_size, patch_size=v.patch,
+                           hidden_act="quick_gelu" if quick else "gelu", layer_norm_eps=v.ln_eps)
+    hf = CLIPVisionModel(cfg).eval()
+    c, W = "clip.visual.", v.width
+    m = {"embeddings.patch_embedding.weight": sd[c + "conv1.weight"], "embeddings.class_embedding": sd[c + "class_embedding"],
+         "embeddings.position_embedding.weight": sd[c + "positional_embedding"],
+         "pre_layrnorm.weight": sd[c + "ln_pre.weight"], "pre_layrnorm.bias": sd[c + "ln_pre.bias"],
+         "post_layernorm.weight": sd[c + "ln_post.weight"], "post_layernorm.bias": sd[c + "ln_post.bias"]}
+    for i in range(v.layers):
+        r, h = f"{c}transformer.resblocks.{i}.", f"encoder.layers.{i}."
+        for j, n in enumerate(("q_proj", "k_proj", "v_proj")):
+            m[h + f"self_attn.{n}.weight"] = sd[r + "attn.in_proj_weight"][j * W:(j + 1) * W]
+            m[h + f"self_attn.{n}.bias"] = sd[r + "attn.in_proj_bias"][j * W:(j + 1) * W]
+        m[h + "self_attn.out_proj.weight"], m[h + "self_attn.out_proj.bias"] = sd[r + "attn.out_proj.weight"], sd[r + "attn.out_proj.bias"]
+        m[h + "layer_norm1.weight"], m[h + "layer_norm1.bias"] = sd[r + "ln_1.weight"], sd[r + "ln_1.bias"]
+        m[h + "layer_norm2.weight"], m[h + "layer_norm2.bias"] = sd[r + "ln_2.weight"], sd[r + "ln_2.bias"]
+        m[h + "mlp.fc1.weight"], m[h + "mlp.fc1.bias"] = sd[r + "mlp.c_fc.weight"], sd[r + "mlp.c_fc.bias"]
+        m[h + "mlp.fc2.weight"], m[h + "mlp.fc2.bias"] = sd[r + "mlp.c_proj.weight"], sd[r + "mlp.c_proj.bias"]
+    missing, unexpected = hf.vision_model.load_state_dict(m, strict=False)
+    assert not [k for k in missing if "position_ids" not in k] and not unexpected
+    img = torch.randn(2, 3, v.image_size, v.image_size, generator=torch.Generator().manual_seed(4))
+    with torch.no_grad():
+        ref = hf.vision_model.post_layernorm(hf(img).last_hidden_state)
+        got = model.clip_encode_image(img)
+    torch.testing.assert_close(got, ref, rtol=1e-4, atol=2e-5)
+
+
+def test_sequence_layout_and_logit_rows():
+    """BOS | start_img | N image tokens | end_img | text; forward returns T rows that line up
+    with `examples` for the shift in M/model/meta.py:256-257."""
+    a, v = tiny_args(), tiny_vis()
+    sd = O.init_params(a, v, seed=5, dtype=torch.float32)
+    model = O.OracleTransformer(a, v, sd, act_dtype=torch.float32)
+    assert model.image_words == v.tokens + 2 == 7
+    tok = torch.randint(1, a.vocab_size, (2, 9))
+    img = torch.randn(2, 3, 28, 28)
+    out = model.forward(tok, img)
+    assert out.shape == (2, 9, a.vocab_size)
+    # the same rows through the inference path: prefill then compare last-position logits
+    last = model.forward_inference(tok, 0, img)
+    torch.testing.assert_close(last, out[:, -1], rtol=1e-4, atol=1e-5)
+    assert model.cache_image_words == 7
+    nxt = torch.randint(1, a.vocab_size, (2, 1))
+    l_dec = model.forward_inference(nxt, 9)  # text-relative start_pos; offset added inside (:520)
+    full = model.forward(torch.cat([tok, nxt], 1), img)
+    torch.testing.assert_close(l_dec, full[:, -1], rtol=1e-4, atol=1e-5)
+
+
+def test_loss_trim_and_ignore_index():
+    a = tiny_args()
+    sd = O.init_params(a, None, seed=6, dtype=torch.float32)
+    model = O.OracleTransformer(a, None, sd, act_dtype=torch.float32)
+    ex = torch.randint(1, a.vocab_size, (2, 12))
+    lab = ex.clone()
+    lab[:, :4] = 0
+    lab[:, 9:] = 0
+    ex[:, 9:] = 0  # padded tail
+    e2, l2 = O.trim_trailing_pad(ex, lab)
+    assert e2.shape[1] == 9 and l2.shape[1] == 9
+    loss = O.meta_forward_loss(model, ex, lab)
+    logits = model.forward(ex[:, :9])
+    ref = torch.nn.functional.cross_entropy(logits[:, :-1].reshape(-1, a.vocab_size), lab[:, 1:9].flatten(), ignore_index=0)
+    torch.testing.assert_close(loss, ref)
+    z = O.meta_forward_loss(model, ex, torch.zeros_like(lab))  # nothing to predict: meta.py:244-247,259-260
+    assert z.item() == 0.0
+    e3, _ = O.trim_trailing_pad(ex, torch.zeros_like(lab))
+    assert e3.shape[1] == 3
+
+
+def test_generate_control_flow():
+    """M/model/meta.py:379-485: force-feeding of longer prompts, multi-token stop, left truncation."""
+    a = tiny_args(max_seq_len=32)
+    sd = O.init_params(a, None, seed=7, dtype=torch.float32, output_scale=30.0)
+    model = O.OracleTransformer(a, None, sd, act_dtype=torch.float32)
+    p0, p1 = [1, 5, 6, 7], [1, 9, 10, 11, 12, 13, 14]
+    out, tokens, stop_pos = O.generate_tokens(model, [p0, p1], max_gen_len=6, eos_id=2)
+    assert tokens.shape[1] == min(32, 6 + 7)
+    assert tokens[1, :7].tolist() == p1  # prompt tokens are force-fed, never overwritten (:463-465)
+    # row 0 generated independently with batch 1 gives the same continuation (greedy, no padding leaks in)
+    solo, _, _ = O.generate_tokens(model, [p0], max_gen_len=6, eos_id=2)
+    n = min(len(solo[0]), len(out[0]))
+    assert n > 0 and solo[0][:n] == out[0][:n]
+    # multi-token stop: use the first two generated tokens of row 0 as a stop sequence
+    if len(solo[0]) >= 3:
+        st = solo[0][1:3]
+        cut, _, sp = O.generate_tokens(model, [p0], max_gen_len=6, eos_id=2, stop_sequences=[st])
+        assert cut[0] == solo[0][:1] and sp[0].item() == len(p0) + 1
+    # left truncation (:428-429): prompt longer than max_seq_len - max_gen_len keeps its tail
+    longp = [1] + list(range(3, 40))
+    o3, t3, _ = O.generate_tokens(model, [longp], max_gen_len=8, eos_id=2)
+    assert t3.shape[1] == 32 and t3[0, :24].tolist() == longp[-24:]
+
+
+def test_adamw_matches_torch():
+    torch.manual_seed(0)
+    names = ["layers.0.attention.wq.weight", "layers.0.attention_norm.weight", "visual_proj.0.bias"]
+    master = {n: torch.randn(8, 8) for n in names}
+    grads = {n: torch.randn(8, 8) for n in names}
+    ref = {n: torch.nn.Parameter(master[n].clone()) for n in names}
+    opt = torch.optim.AdamW([{"params": [ref[names[0]]], "weight_decay": 0.1},
+                             {"params": [ref[names[1]], ref[names[2]]], "weight_decay": 0.0}], lr=1e-2, betas=(0.9, 0.95))
+    state = {n: (torch.zeros(8, 8), torch.zeros(8, 8)) for n in names}
+    for step in (1, 2):
+        for n in names:
+            ref[n].grad = grads[n].clone()
+        total = torch.nn.utils.clip_grad_norm_([ref[n] for n in names], 8.0)
+        opt.step()
+        got = O.adamw_step(master, grads, state, step, 1e-2, 0.1, 8.0)
+        assert abs(got - total.item()) < 1e-4
+        for n in names:
+            torch.testing.assert_close(master[n], ref[n].detach(), rtol=1e-5, atol=1e-6)
+
+
+def test_bf16_rounding_points():
+    """RMSNorm rounds before the weight multiply; logits are a bf16 result cast to fp32."""
+    x = torch.randn(3, 64).bfloat16()
+    w = (1 + 0.1 * torch.randn(64)).bfloat16()
+    y = O.rmsnorm(x, w, 1e-5)
+    n = (x.float() * torch.rsqrt(x.float().pow(2).mean(-1, keepdim=True) + 1e-5)).bfloat16()
+    assert torch.equal(y, n * w)
+    a = tiny_args()
+    model = O.OracleTransformer(a, None, O.init_params(a, None, seed=8))
+    lg = model.forward_inference(torch.randint(1, 97, (1, 5)), 0)
+    assert lg.dtype == torch.float32 and torch.equal(lg, lg.bfloat16().float())
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(GOLD, "tiny_e2e.pt")), reason="golden vectors not generated")
+def test_golden_vectors_reproduce():
+    """tests/golden/make_golden.py wrote these from this oracle; they pin the oracle against drift and
+    are what the GPU path is compared with on the GPU box (where /root/reference does not exist)."""
+    g = torch.load(os.path.join(GOLD, "tiny_e2e.pt"))
+    sys.path.insert(0, GOLD)
+    import make_golden as MG
+
+    a, v = MG.tiny_cfg()
+    sd = O.init_params(a, v, seed=g["seed"], output_scale=g["output_scale"])
+    model = O.OracleTransformer(a, v, sd)
+    out = model.forward(g["tokens"], g["image"])
+    assert torch.equal(out, g["train_logits"])
+    gen, _, _ = O.generate_tokens(model, g["prompts"], images=g["image"], max_gen_len=g["max_gen_len"], eos_id=2)
+    assert gen == g["generated"]
