@@ -195,6 +195,28 @@ __global__ void count_nonzero_kernel(const long long* __restrict__ labels, int n
   }
 }
 
+__global__ void shift_labels_kernel(const long long* __restrict__ labels, long long ld,
+                                    long long* __restrict__ shifted, int B, int T,
+                                    int* __restrict__ count) {
+  __shared__ int red[32];
+  int c = 0;
+  for (int i = threadIdx.x; i < B * T; i += blockDim.x) {
+    const int b = i / T, t = i - b * T;
+    const long long v = t + 1 < T ? labels[b * ld + t + 1] : 0;
+    shifted[i] = v;
+    c += v != 0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    *count = t;
+  }
+}
+
 // One CTA per row.  CrossEntropyLoss(ignore_index=0) in fp32 on bf16 logits; optionally
 // overwrites the row with dlogits = (softmax - onehot) * grad_scale / count.
 __global__ void __launch_bounds__(256)
@@ -460,6 +482,13 @@ extern "C" int a3_vit_assemble_lnpre(const void* patch_out, const void* cls, con
 extern "C" int a3_count_nonzero(const long long* labels, int n, int* count, void* stream) {
   count_nonzero_kernel<<<1, 1024, 0, ST(stream)>>>(labels, n, count);
   return check_launch("a3_count_nonzero");
+}
+
+extern "C" int a3_shift_labels(const long long* labels, long long ld_labels, long long* shifted, int B,
+                               int T, int* count, void* stream) {
+  if (B <= 0 || T <= 0) return set_error(A3_ERR_ARG, "a3_shift_labels: empty batch");
+  shift_labels_kernel<<<1, 1024, 0, ST(stream)>>>(labels, ld_labels, shifted, B, T, count);
+  return check_launch("a3_shift_labels");
 }
 
 extern "C" int a3_cross_entropy(void* logits, long long ld, const long long* labels, float* row_loss,

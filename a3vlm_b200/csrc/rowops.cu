@@ -303,7 +303,7 @@ __global__ void colsum_partials_kernel(const float* __restrict__ partial, int np
 // out[n] = sum_m X[m][n].  CTA = 32 x 8 threads over a 32-column strip; rows strided by 8 and
 // then reduced through shared memory.  Deterministic.
 __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, int M, int N,
-                                   long long ldx, __nv_bfloat16* __restrict__ out) {
+                                   long long ldx, __nv_bfloat16* __restrict__ out, int accumulate) {
   __shared__ float red[8][33];
   const int col = blockIdx.x * 32 + threadIdx.x;
   float s = 0.f;
@@ -315,6 +315,7 @@ __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, int M, i
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    if (accumulate) t += __bfloat162float(out[col]);
     out[col] = __float2bfloat16_rn(t);
   }
 }
@@ -459,9 +460,11 @@ extern "C" int a3_colsum_partials(const float* partial, int nparts, int D, void*
   return check_launch("a3_colsum_partials");
 }
 
-extern "C" int a3_colsum_bf16(const void* X, int M, int N, long long ldx, void* out, void* stream) {
+extern "C" int a3_colsum_bf16(const void* X, int M, int N, long long ldx, void* out, int accumulate,
+                              void* stream) {
   if (N <= 0) return A3_OK;
-  colsum_bf16_kernel<<<(N + 31) / 32, dim3(32, 8), 0, ST(stream)>>>(BF(X), M, N, ldx, BFM(out));
+  colsum_bf16_kernel<<<(N + 31) / 32, dim3(32, 8), 0, ST(stream)>>>(BF(X), M, N, ldx, BFM(out),
+                                                                    accumulate);
   return check_launch("a3_colsum_bf16");
 }
 

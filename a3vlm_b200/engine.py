@@ -1,0 +1,574 @@
+"""Execution engine of the hot path: owns the flat weight / gradient / optimiser buffers in HBM and
+the activation workspaces, and sequences the sm_100a kernels (through `ops`) for
+
+  * the frozen CLIP ViT tower + visual_proj      (reference LLM/llama_ens5.py:351-375,450-452)
+  * the Llama decoder training forward + loss    (LLM/llama_ens5.py:461-487, M/model/meta.py:251-262)
+  * the hand-written backward of all of it       (autograd of the above in the reference)
+  * grad all-reduce + global-norm clip + AdamW   (M/util/misc.py:302-315, M/util/clip_grad.py:187-193,
+                                                  M/main_finetune.py:284-285)
+  * prefill / decode with a KV cache             (LLM/llama_ens5.py:490-531)
+
+No autograd graph is built: every activation the backward needs is kept in a pre-sized workspace and
+the backward is an explicit kernel sequence.  torch is used for memory, streams and the NCCL
+process group only.  Layout in HBM: one bf16 flat buffer for the trainable
+weights with wq|wk|wv and w1|w3 of a layer adjacent (so the fused QKV / gate-up GEMMs read one
+[N][K] matrix while the reference's parameter names stay views of it), one bf16 flat gradient buffer
+of the same layout (bucketed per layer for the all-reduce), fp32 master / m / v flats for AdamW.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import ops
+
+bf16 = torch.bfloat16
+
+
+def _no_decay(name: str) -> bool:
+    # M/util/misc.py:586-599 (add_weight_decay): no weight decay for biases and norm weights
+    return name.endswith(".bias") or name.endswith("norm.weight")
+
+
+class FlatParams:
+    """Flat bf16 storage for a set of named parameters.  `layout` is an ordered list of
+    (name, shape); views[name] aliases the flat buffer."""
+
+    def __init__(self, layout: List[Tuple[str, Tuple[int, ...]]], device, align: int = 64):
+        self.offsets: Dict[str, Tuple[int, int, Tuple[int, ...]]] = {}
+        off = 0
+        for name, shape in layout:
+            n = int(math.prod(shape))
+            self.offsets[name] = (off, n, tuple(shape))
+            off += (n + align - 1) // align * align
+        self.numel = off
+        self.flat = torch.zeros(max(off, align), device=device, dtype=bf16)
+        self.views = {n: self.flat[o:o + k].view(s) for n, (o, k, s) in self.offsets.items()}
+
+    def like(self, dtype) -> torch.Tensor:
+        return torch.zeros(self.flat.numel(), device=self.flat.device, dtype=dtype)
+
+
+class Workspace:
+    """Activation + gradient scratch for one (B, T, W) shape.  Sized once, reused every step."""
+
+    def __init__(self, eng: "Engine", B: int, T: int, W: int, train: bool):
+        a, dev = eng.args, eng.device
+        D, F, V, NL = a.dim, eng.ffn_dim, a.vocab_size, a.n_layers
+        L = T + W
+        M = B * L
+        self.B, self.T, self.W, self.L, self.M = B, T, W, L, M
+        e = lambda *s, dt=bf16: torch.empty(*s, device=dev, dtype=dt)
+        keep = NL if train else 1
+        self.x = [e(M, D) for _ in range(keep + 1)]
+        self.xn = [e(M, D) for _ in range(keep)]
+        self.qkv = [e(M, 3 * D) for _ in range(keep)]
+        self.o = [e(M, D) for _ in range(keep)]
+        self.h = [e(M, D) for _ in range(keep)]
+        self.hn = [e(M, D) for _ in range(keep)]
+        self.gu = [e(M, 2 * F) for _ in range(keep)]
+        self.y = e(M, F)
+        self.lse = [e(B, a.n_heads, L, dt=torch.float32) for _ in range(keep)]
+        self.rstd1 = [e(M, dt=torch.float32) for _ in range(keep)]
+        self.rstd2 = [e(M, dt=torch.float32) for _ in range(keep)]
+        if train:
+            R = B * T
+            self.fn = e(R, D)
+            self.rstd_f = e(R, dt=torch.float32)
+            self.logits = e(R, V)
+            self.shift = e(R, dt=torch.int64)
+            self.count = torch.zeros(1, device=dev, dtype=torch.int32)
+            self.row_loss = e(R, dt=torch.float32)
+            self.loss = torch.zeros(1, device=dev, dtype=torch.float32)
+            self.dfn = e(R, D)
+            self.d = e(M, D)        # running gradient of the residual stream
+            self.dtmp = e(M, D)     # dgrad outputs into the norms / attention
+            self.dy = e(M, F)
+            self.dgu = e(M, 2 * F)
+            self.dqkv = e(M, 3 * D)
+            self.dq_acc = e(M, D, dt=torch.float32)
+            self.delta = e(B, a.n_heads, L, dt=torch.float32)
+            self.nparts = 2 * eng.n_sms
+            self.part = e(max(B, 1) * self.nparts, D, dt=torch.float32)
+            self.part2 = e(self.nparts, D, dt=torch.float32)
+            self.tag_grad = e(2, D, dt=torch.float32)
+        if W:
+            self.vit = eng._vit_workspace(B, train)
+
+
+class Engine:
+    def __init__(self, args, vis, device):
+        """args: ModelArgs-like (dim, n_layers, n_heads, n_kv_heads, vocab_size, multiple_of,
+        ffn_dim_multiplier, norm_eps, rope_theta, rope_scaling, max_seq_len); vis: vision geometry or
+        None."""
+        self.args, self.vis, self.device = args, vis, torch.device(device)
+        if self.device.type != "cuda":
+            raise ops._lib.A3Error("a3vlm_b200.Engine needs a CUDA (sm_100a) device: there is no CPU path")
+        ops._L()  # fail loudly now if the native library is missing
+        a = args
+        if a.n_kv_heads not in (None, a.n_heads):
+            raise NotImplementedError("grouped-query attention (n_kv_heads != n_heads) is not built: "
+                                      "the 7B / 13B configs on the path use n_kv_heads = None")
+        if a.rope_scaling is not None:
+            raise NotImplementedError("rope_scaling: direction cannot be verified from the reference tree")
+        self.head_dim = a.dim // a.n_heads
+        if self.head_dim != 128:
+            raise NotImplementedError("decoder head_dim must be 128 (7B / 13B)")
+        hidden = int(2 * (4 * a.dim) / 3)  # LLM/llama_ens5.py:196-200
+        if a.ffn_dim_multiplier is not None:
+            hidden = int(a.ffn_dim_multiplier * hidden)
+        self.ffn_dim = a.multiple_of * ((hidden + a.multiple_of - 1) // a.multiple_of)
+        self.n_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        self.rope = ops.rope_table(self.head_dim, a.max_seq_len * 2, a.rope_theta, device=self.device)
+        self.image_words = (vis.tokens + 2) if vis is not None else 0
+        self.scale = 1.0 / math.sqrt(self.head_dim)
+        self._build_layouts()
+        self._ws: Dict[Tuple, Workspace] = {}
+        self.master = self.m = self.v = None
+        self.opt_step = 0
+        self.norm_sq = torch.zeros(1, device=self.device, dtype=torch.float32)
+        self.kcache: List[torch.Tensor] = []
+        self.vcache: List[torch.Tensor] = []
+        self.cache_B = 0
+        self.cache_image_words = 0
+        self.dec = None
+        self.comm_stream = None
+
+    # ------------------------------------------------------------------------------------ layouts
+    def _build_layouts(self):
+        a, D, F, V = self.args, self.args.dim, self.ffn_dim, self.args.vocab_size
+        decay: List[Tuple[str, Tuple[int, ...]]] = [("tok_embeddings.weight", (V, D))]
+        nodecay: List[Tuple[str, Tuple[int, ...]]] = []
+        for i in range(a.n_layers):
+            p = f"layers.{i}."
+            decay += [(p + "wqkv", (3 * D, D)), (p + "attention.wo.weight", (D, D)),
+                      (p + "w13", (2 * F, D)), (p + "feed_forward.w2.weight", (D, F))]
+            nodecay += [(p + "attention_norm.weight", (D,)), (p + "ffn_norm.weight", (D,))]
+        decay.append(("output.weight", (V, D)))
+        nodecay.append(("norm.weight", (D,)))
+        frozen: List[Tuple[str, Tuple[int, ...]]] = []
+        if self.vis is not None:
+            v, c = self.vis, "clip.visual."
+            Wv = v.width
+            self.kpad = (3 * v.patch * v.patch + 7) // 8 * 8
+            decay += [("visual_proj.0.weight", (D, Wv)), ("start_img", (1, 1, D)), ("end_img", (1, 1, D))]
+            nodecay += [("visual_proj.0.bias", (D,)), ("visual_proj.1.weight", (D,)), ("visual_proj.1.bias", (D,))]
+            frozen += [(c + "conv1.weight", (Wv, 3, v.patch, v.patch)), (c + "conv1_padded", (Wv, self.kpad)),
+                       (c + "class_embedding", (Wv,)), (c + "positional_embedding", (v.tokens, Wv)),
+                       (c + "ln_pre.weight", (Wv,)), (c + "ln_pre.bias", (Wv,)),
+                       (c + "ln_post.weight", (Wv,)), (c + "ln_post.bias", (Wv,))]
+            for i in range(v.layers):
+                r = f"{c}transformer.resblocks.{i}."
+                frozen += [(r + "ln_1.weight", (Wv,)), (r + "ln_1.bias", (Wv,)),
+                           (r + "attn.in_proj_weight", (3 * Wv, Wv)), (r + "attn.in_proj_bias", (3 * Wv,)),
+                           (r + "attn.out_proj.weight", (Wv, Wv)), (r + "attn.out_proj.bias", (Wv,)),
+                           (r + "ln_2.weight", (Wv,)), (r + "ln_2.bias", (Wv,)),
+                           (r + "mlp.c_fc.weight", (v.mlp, Wv)), (r + "mlp.c_fc.bias", (v.mlp,)),
+                           (r + "mlp.c_proj.weight", (Wv, v.mlp)), (r + "mlp.c_proj.bias", (Wv,))]
+        self.n_decay_names = len(decay)
+        self.w = FlatParams(decay + nodecay, self.device)
+        self.decay_numel = self.w.offsets[nodecay[0][0]][0]  # no-decay region starts here
+        self.fz = FlatParams(frozen, self.device) if frozen else None
+        self.g: Optional[FlatParams] = None  # gradients: allocated on first training use
+        self._layout = decay + nodecay
+
+    def param_views(self) -> Dict[str, torch.Tensor]:
+        """Reference-named views (SURVEY 8b state-dict names) into the flat buffers."""
+        D, F = self.args.dim, self.ffn_dim
+        out: Dict[str, torch.Tensor] = {}
+        for name, t in self.w.views.items():
+            if name.endswith(".wqkv"):
+                p = name[:-4] + "attention."
+                out[p + "wq.weight"], out[p + "wk.weight"], out[p + "wv.weight"] = t[:D], t[D:2 * D], t[2 * D:]
+            elif name.endswith(".w13"):
+                p = name[:-3] + "feed_forward."
+                out[p + "w1.weight"], out[p + "w3.weight"] = t[:F], t[F:]
+            else:
+                out[name] = t
+        if self.fz is not None:
+            for name, t in self.fz.views.items():
+                if not name.endswith("conv1_padded"):
+                    out[name] = t
+        return out
+
+    def grad_views(self) -> Dict[str, torch.Tensor]:
+        self._ensure_grads()
+        D, F = self.args.dim, self.ffn_dim
+        out: Dict[str, torch.Tensor] = {}
+        for name, t in self.g.views.items():
+            if name.endswith(".wqkv"):
+                p = name[:-4] + "attention."
+                out[p + "wq.weight"], out[p + "wk.weight"], out[p + "wv.weight"] = t[:D], t[D:2 * D], t[2 * D:]
+            elif name.endswith(".w13"):
+                p = name[:-3] + "feed_forward."
+                out[p + "w1.weight"], out[p + "w3.weight"] = t[:F], t[F:]
+            else:
+                out[name] = t
+        return out
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        views = self.param_views()
+        missing = [k for k in views if k not in sd]
+        if missing:
+            raise KeyError(f"missing parameters: {missing[:5]} ... ({len(missing)})")
+        for k, v in views.items():
+            v.copy_(sd[k].to(device=self.device, dtype=bf16).view(v.shape))
+        self.weights_changed()
+
+    def weights_changed(self) -> None:
+        """Re-derive the kernel-side layouts from the reference-named weights (conv1 flattened to
+        K-major [1024][588 -> 592 zero-padded]) and invalidate fp32 masters."""
+        if self.fz is not None:
+            c = "clip.visual."
+            v = self.vis
+            pad = self.fz.views[c + "conv1_padded"]
+            pad.zero_()
+            pad[:, :3 * v.patch * v.patch] = self.fz.views[c + "conv1.weight"].reshape(v.width, -1)
+        self.master = None
+
+    # ------------------------------------------------------------------------------------ workspaces
+    def _vit_workspace(self, B: int, train: bool):
+        v, D, dev = self.vis, self.args.dim, self.device
+        g2, N, Wv = v.grid * v.grid, v.tokens, v.width
+        e = lambda *s, dt=bf16: torch.empty(*s, device=dev, dtype=dt)
+        ws = {"A": e(B * g2, self.kpad), "po": e(B * g2, Wv), "x": e(B * N, Wv), "y": e(B * N, Wv),
+              "qkv": e(B * N, 3 * Wv), "o": e(B * N, Wv), "fc": e(B * N, v.mlp), "feats": e(B * N, Wv),
+              "pre": e(B * N, D), "tok": e(B * N, D), "mean": e(B * N, dt=torch.float32),
+              "rstd": e(B * N, dt=torch.float32)}
+        if train:
+            ws["dtok"] = e(B * N, D)
+            ws["dpre"] = e(B * N, D)
+            ws["pw"] = e(self.n_sms, D, dt=torch.float32)
+            ws["pb"] = e(self.n_sms, D, dt=torch.float32)
+        return ws
+
+    def workspace(self, B: int, T: int, W: int, train: bool) -> Workspace:
+        key = (B, T, W, train)
+        ws = self._ws.get(key)
+        if ws is None:
+            # one live shape per mode: drop workspaces of other shapes (they are GBs at 7B)
+            for k in [k for k in self._ws if k[3] == train]:
+                del self._ws[k]
+            ws = self._ws[key] = Workspace(self, B, T, W, train)
+        return ws
+
+    def _ensure_grads(self):
+        if self.g is None:
+            self.g = FlatParams(self._layout, self.device)
+
+    # ------------------------------------------------------------------------------------ ViT + projector
+    def vit_forward(self, image: torch.Tensor, vw) -> torch.Tensor:
+        """clip_encode_image (LLM/llama_ens5.py:351-375) + visual_proj (:330-333,451), frozen tower.
+        image (B,3,S,S) fp32 or bf16 on the device -> image tokens [B*N][D] (vw['tok'])."""
+        v, f = self.vis, self.fz.views
+        c = "clip.visual."
+        B = image.shape[0]
+        if tuple(image.shape[1:]) != (3, v.image_size, v.image_size):
+            raise ValueError(f"image must be (B,3,{v.image_size},{v.image_size}), got {tuple(image.shape)}")
+        if image.dtype not in (torch.float32, bf16):
+            image = image.float()
+        image = image.contiguous()
+        N, Wv, g2 = v.tokens, v.width, v.grid * v.grid
+        act = ops.ACT_QUICKGELU if v.quick_gelu else ops.ACT_GELU
+        ops.vit_patchify(image, vw["A"], B, v.image_size, v.patch, self.kpad)
+        ops.gemm(vw["A"], f[c + "conv1_padded"], vw["po"])
+        ops.vit_assemble_lnpre(vw["po"], f[c + "class_embedding"], f[c + "positional_embedding"],
+                               f[c + "ln_pre.weight"], f[c + "ln_pre.bias"], vw["x"], B, g2, Wv, v.ln_eps)
+        x, y, qkv, o, fc = vw["x"], vw["y"], vw["qkv"], vw["o"], vw["fc"]
+        hd = Wv // v.heads
+        sc = 1.0 / math.sqrt(hd)
+        for i in range(v.layers):
+            r = f"{c}transformer.resblocks.{i}."
+            ops.layernorm_fwd(x, f[r + "ln_1.weight"], f[r + "ln_1.bias"], v.ln_eps, out=y)
+            ops.gemm(y, f[r + "attn.in_proj_weight"], qkv, bias=f[r + "attn.in_proj_bias"])
+            ops.attn_fwd(qkv[:, :Wv], qkv[:, Wv:2 * Wv], qkv[:, 2 * Wv:], B, v.heads, N, N, hd, sc, False, out=o)
+            ops.gemm(o, f[r + "attn.out_proj.weight"], x, bias=f[r + "attn.out_proj.bias"], residual=x)
+            ops.layernorm_fwd(x, f[r + "ln_2.weight"], f[r + "ln_2.bias"], v.ln_eps, out=y)
+            ops.gemm(y, f[r + "mlp.c_fc.weight"], fc, bias=f[r + "mlp.c_fc.bias"], act=act)
+            ops.gemm(fc, f[r + "mlp.c_proj.weight"], x, bias=f[r + "mlp.c_proj.bias"], residual=x)
+        ops.layernorm_fwd(x, f[c + "ln_post.weight"], f[c + "ln_post.bias"], v.ln_eps, out=vw["feats"])
+        w = self.w.views
+        ops.gemm(vw["feats"], w["visual_proj.0.weight"], vw["pre"], bias=w["visual_proj.0.bias"])
+        ops.layernorm_fwd(vw["pre"], w["visual_proj.1.weight"], w["visual_proj.1.bias"], 1e-5, out=vw["tok"],
+                          mean=vw["mean"], rstd=vw["rstd"])
+        return vw["tok"]
+
+    # ------------------------------------------------------------------------------------ decoder layer
+    def _layer_fwd(self, i, x, xn, qkv, o, h, hn, gu, y, out, lse, rstd1, rstd2, B, L, pos0=0,
+                   kv=None):
+        a, w, D = self.args, self.w.views, self.args.dim
+        p = f"layers.{i}."
+        ops.rmsnorm_fwd(x, w[p + "attention_norm.weight"], a.norm_eps, out=xn, rstd=rstd1)
+        ops.gemm(xn, w[p + "wqkv"], qkv, rope=self.rope, rope_cols=2 * D, rope_period=L, rope_pos0=pos0)
+        q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+        if kv is not None:  # LLM/llama_ens5.py:121-127
+            ops.kv_append(k, v, self.kcache[i], self.vcache[i], B, L, a.n_heads, self.head_dim, pos0,
+                          a.max_seq_len)
+        if kv is not None and pos0 > 0:  # multi-token step against the cache, right-aligned causal
+            Wd = a.n_heads * self.head_dim
+            ops.attn_fwd(q, self.kcache[i].view(-1, Wd), self.vcache[i].view(-1, Wd), B, a.n_heads, L,
+                         pos0 + L, self.head_dim, self.scale, True, out=o, lse=lse,
+                         kv_bstride=a.max_seq_len * Wd)
+        else:
+            ops.attn_fwd(q, k, v, B, a.n_heads, L, L, self.head_dim, self.scale, True, out=o, lse=lse)
+        ops.gemm(o, w[p + "attention.wo.weight"], h, residual=x)
+        ops.rmsnorm_fwd(h, w[p + "ffn_norm.weight"], a.norm_eps, out=hn, rstd=rstd2)
+        ops.gemm(hn, w[p + "w13"], gu)
+        ops.swiglu_fwd(gu, y)
+        ops.gemm(y, w[p + "feed_forward.w2.weight"], out, residual=h)
+
+    # ------------------------------------------------------------------------------------ training forward
+    def forward_train(self, examples: torch.Tensor, image: Optional[torch.Tensor], labels=None,
+                      grad_scale: float = 1.0, want_grad: bool = True):
+        """Transformer.forward (LLM/llama_ens5.py:461-487) keeping what the backward needs.
+        Returns (workspace, logits [B*T][V] view).  With labels: also runs the shifted cross entropy
+        of M/model/meta.py:256-262 (loss in ws.loss; logits are overwritten by dlogits)."""
+        a, w = self.args, self.w.views
+        B, T = examples.shape
+        W = self.image_words if image is not None else 0
+        ws = self.workspace(B, T, W, True)
+        L, D = ws.L, a.dim
+        if L > 2 * a.max_seq_len:
+            raise ValueError("sequence longer than the RoPE table (2 * max_seq_len)")
+        examples = examples.contiguous()
+        img = self.vit_forward(image, ws.vit) if W else None
+        ops.embed_splice(examples, w["tok_embeddings.weight"], img, w["start_img"] if W else None,
+                         w["end_img"] if W else None, ws.x[0], B, T, self.vis.tokens if W else 0, D)
+        for i in range(a.n_layers):
+            self._layer_fwd(i, ws.x[i], ws.xn[i], ws.qkv[i], ws.o[i], ws.h[i], ws.hn[i], ws.gu[i], ws.y,
+                            ws.x[i + 1], ws.lse[i], ws.rstd1[i], ws.rstd2[i], B, L)
+        xf = ws.x[a.n_layers].view(B, L, D)
+        for b in range(B):  # final norm on the text rows only (llama_ens5.py:485-486)
+            ops.rmsnorm_fwd(xf[b, W:], w["norm.weight"], a.norm_eps, out=ws.fn[b * T:(b + 1) * T],
+                            rstd=ws.rstd_f[b * T:(b + 1) * T])
+        ops.gemm(ws.fn, w["output.weight"], ws.logits)
+        if labels is not None:
+            ops.shift_labels(labels, ws.shift, ws.count)
+            ops.cross_entropy(ws.logits, ws.shift, ws.row_loss, ws.count, grad_scale, want_grad)
+            ops.loss_reduce(ws.row_loss, ws.count, ws.loss)
+        return ws, ws.logits
+
+    # ------------------------------------------------------------------------------------ backward
+    def backward(self, ws: Workspace, examples: torch.Tensor, dlogits: torch.Tensor,
+                 accumulate: bool = False, on_bucket=None, scale: float = 1.0) -> None:
+        """Backward of forward_train given dlogits [B*T][V] (bf16).  Weight gradients go to the flat
+        bf16 gradient buffer (overwritten, or added to when `accumulate`).  `on_bucket(lo, hi)` is
+        called with the flat element range whose gradients are complete (all-reduce overlap).
+        `scale` multiplies dlogits on the fly (the upstream d loss, and 1/world for data parallel)."""
+        self._ensure_grads()
+        a, w, g = self.args, self.w.views, self.g.views
+        B, T, W, L, M, D, F = ws.B, ws.T, ws.W, ws.L, ws.M, a.dim, self.ffn_dim
+        NL, acc = a.n_layers, accumulate
+        wg = lambda dy, x, out: ops.gemm(dy, x, out, a_mn=True, b_mn=True, accumulate=acc)   # dW = dy^T x
+        dg = lambda dy, wt, out: ops.gemm(dy, wt, out, b_mn=True)                             # dx = dy W
+        np_ = ws.nparts
+        # LM head + final norm
+        ops.gemm(dlogits, ws.fn, g["output.weight"], a_mn=True, b_mn=True, accumulate=acc, alpha=scale)
+        ops.gemm(dlogits, w["output.weight"], ws.dfn, b_mn=True, alpha=scale)
+        if on_bucket:
+            on_bucket(*self._range("output.weight"))
+        ws.d.zero_()
+        xf, dv = ws.x[NL].view(B, L, D), ws.d.view(B, L, D)
+        for b in range(B):
+            ops.rmsnorm_bwd(ws.dfn[b * T:(b + 1) * T], xf[b, W:], w["norm.weight"], ws.rstd_f[b * T:(b + 1) * T],
+                            dv[b, W:], ws.part[b * np_:(b + 1) * np_])
+        ops.colsum_partials(ws.part[:B * np_], g["norm.weight"], accumulate=acc)
+        d, t = ws.d, ws.dtmp
+        for i in reversed(range(NL)):
+            p = f"layers.{i}."
+            ops.swiglu_fwd(ws.gu[i], ws.y)                                   # recompute y
+            wg(d, ws.y, g[p + "feed_forward.w2.weight"])
+            dg(d, w[p + "feed_forward.w2.weight"], ws.dy)
+            ops.swiglu_bwd(ws.gu[i], ws.dy, ws.dgu)
+            wg(ws.dgu, ws.hn[i], g[p + "w13"])
+            dg(ws.dgu, w[p + "w13"], t)
+            ops.rmsnorm_bwd(t, ws.h[i], w[p + "ffn_norm.weight"], ws.rstd2[i], d, ws.part2, add_to_dx=True)
+            ops.colsum_partials(ws.part2, g[p + "ffn_norm.weight"], accumulate=acc)
+            wg(d, ws.o[i], g[p + "attention.wo.weight"])
+            dg(d, w[p + "attention.wo.weight"], t)
+            qkv, dqkv = ws.qkv[i], ws.dqkv
+            ops.attn_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], ws.o[i], t, ws.lse[i], ws.delta, ws.dq_acc,
+                         dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], B, a.n_heads, L, self.head_dim,
+                         self.scale, True)
+            ops.rope_apply(dqkv[:, :2 * D], 2 * a.n_heads, self.head_dim, self.rope, L, 0, inverse=True)
+            wg(dqkv, ws.xn[i], g[p + "wqkv"])
+            dg(dqkv, w[p + "wqkv"], t)
+            ops.rmsnorm_bwd(t, ws.x[i], w[p + "attention_norm.weight"], ws.rstd1[i], d, ws.part2, add_to_dx=True)
+            ops.colsum_partials(ws.part2, g[p + "attention_norm.weight"], accumulate=acc)
+            if on_bucket:
+                lo, _ = self._range(p + "wqkv")
+                _, hi = self._range(p + "feed_forward.w2.weight")
+                on_bucket(lo, hi)
+        # embedding scatter-add, tags, projector
+        if not acc:
+            g["tok_embeddings.weight"].zero_()
+        vw = ws.vit if W else None
+        ops.embed_splice_bwd(examples, d, g["tok_embeddings.weight"], vw["dtok"] if W else None,
+                             ws.tag_grad[0] if W else None, ws.tag_grad[1] if W else None, B, T,
+                             self.vis.tokens if W else 0, D)
+        if W:
+            ops.colsum_partials(ws.tag_grad[0:1], g["start_img"].view(-1), accumulate=acc)
+            ops.colsum_partials(ws.tag_grad[1:2], g["end_img"].view(-1), accumulate=acc)
+            ops.layernorm_bwd(vw["dtok"], vw["pre"], w["visual_proj.1.weight"], vw["mean"], vw["rstd"],
+                              vw["dpre"], vw["pw"], vw["pb"])
+            ops.colsum_partials(vw["pw"], g["visual_proj.1.weight"], accumulate=acc)
+            ops.colsum_partials(vw["pb"], g["visual_proj.1.bias"], accumulate=acc)
+            wg(vw["dpre"], vw["feats"], g["visual_proj.0.weight"])
+            ops.colsum_bf16(vw["dpre"], g["visual_proj.0.bias"], accumulate=acc)
+        elif not acc and "start_img" in g:
+            for n in ("start_img", "end_img", "visual_proj.0.weight", "visual_proj.0.bias",
+                      "visual_proj.1.weight", "visual_proj.1.bias"):
+                g[n].zero_()
+        if on_bucket:
+            on_bucket(0, self._range("tok_embeddings.weight")[1])
+            on_bucket(self._range("output.weight")[1], self.g.numel)
+
+    def _range(self, name: str) -> Tuple[int, int]:
+        o, n, _ = self.w.offsets[name]
+        return o, o + n
+
+    # ------------------------------------------------------------------------------------ optimiser
+    def _ensure_opt(self):
+        if self.master is None:
+            self.master = self.w.flat.float()
+        if self.m is None:
+            self.m, self.v = self.w.like(torch.float32), self.w.like(torch.float32)
+
+    def optimizer_step(self, lr: float, weight_decay: float = 0.0, max_norm: float = 0.0,
+                       betas=(0.9, 0.95), eps: float = 1e-8) -> torch.Tensor:
+        """Global-L2 clip (M/util/clip_grad.py:187-193) + AdamW on fp32 masters with the bf16 weights
+        rewritten in the same pass (M/main_finetune.py:284-285; M/util/misc.py:586-599 decay groups).
+        Returns the device tensor holding the squared gradient norm (no host sync)."""
+        self._ensure_grads()
+        self._ensure_opt()
+        self.opt_step += 1
+        n, nd = self.w.flat.numel(), self.decay_numel
+        self.norm_sq.zero_()
+        ops.sumsq_bf16(self.g.flat, self.norm_sq)
+        for lo, hi, wd in ((0, nd, weight_decay), (nd, n, 0.0)):
+            if hi > lo:
+                ops.adamw(self.master[lo:hi], self.w.flat[lo:hi], self.g.flat[lo:hi], self.m[lo:hi],
+                          self.v[lo:hi], lr, betas[0], betas[1], eps, wd, self.opt_step, self.norm_sq, max_norm)
+        return self.norm_sq
+
+    # ------------------------------------------------------------------------------------ data-parallel
+    def allreduce_hook(self, group=None):
+        """Returns (on_bucket, finish): on_bucket enqueues an NCCL all-reduce (sum) of a finished flat
+        gradient range on a side stream behind an event, so it overlaps the rest of the backward;
+        finish() makes the compute stream wait for all of them.  The 1/world factor is folded into
+        grad_scale by the caller."""
+        import torch.distributed as dist
+
+        if self.comm_stream is None:
+            self.comm_stream = torch.cuda.Stream(device=self.device)
+        cs = self.comm_stream
+
+        def on_bucket(lo, hi):
+            if hi <= lo:
+                return
+            ev = torch.cuda.Event()
+            ev.record()
+            cs.wait_event(ev)
+            with torch.cuda.stream(cs):
+                dist.all_reduce(self.g.flat[lo:hi], op=dist.ReduceOp.SUM, group=group)
+
+        def finish():
+            torch.cuda.current_stream().wait_stream(cs)
+
+        return on_bucket, finish
+
+    # ------------------------------------------------------------------------------------ inference
+    def allocate_kv_cache(self, B: int) -> None:
+        """LLM/llama_ens5.py:171-176,533-535: (B, max_seq_len, H, 128) x 2 per layer, reused while the
+        shape is unchanged."""
+        a = self.args
+        if self.cache_B == B and self.kcache:
+            return
+        self.kcache = self.vcache = []
+        shape = (B, a.max_seq_len, a.n_heads, self.head_dim)
+        self.kcache = [torch.empty(shape, device=self.device, dtype=bf16) for _ in range(a.n_layers)]
+        self.vcache = [torch.empty(shape, device=self.device, dtype=bf16) for _ in range(a.n_layers)]
+        self.cache_B = B
+        self.dec = None
+
+    def destroy_kv_cache(self) -> None:
+        self.kcache, self.vcache, self.cache_B, self.dec = [], [], 0, None
+
+    def forward_inference(self, tokens: torch.Tensor, start_pos: int, image=None) -> torch.Tensor:
+        """Transformer.forward_inference (LLM/llama_ens5.py:490-531): fp32 last-position logits (B,V)."""
+        a, w = self.args, self.w.views
+        B, l = tokens.shape
+        D, V = a.dim, a.vocab_size
+        if start_pos == 0:
+            self.allocate_kv_cache(B)
+        elif B != self.cache_B:
+            raise ValueError("batch size changed between prefill and decode")
+        if image is not None:
+            assert start_pos == 0  # llama_ens5.py:499
+            self.cache_image_words = self.image_words
+        elif start_pos == 0:
+            self.cache_image_words = 0
+        else:
+            start_pos = start_pos + self.cache_image_words  # llama_ens5.py:520
+        if l == 1 and start_pos > 0:
+            return self._decode_step(tokens, start_pos)
+        W = self.image_words if image is not None else 0
+        L = l + W
+        if start_pos + L > a.max_seq_len:
+            raise ValueError(f"sequence {start_pos + L} exceeds max_seq_len {a.max_seq_len}")
+        ws = self.workspace(B, l, W, False)
+        tokens = tokens.contiguous()
+        img = self.vit_forward(image, ws.vit) if W else None
+        ops.embed_splice(tokens, w["tok_embeddings.weight"], img, w["start_img"] if W else None,
+                         w["end_img"] if W else None, ws.x[0], B, l, self.vis.tokens if W else 0, D)
+        xa, xb = ws.x[0], ws.x[1]
+        for i in range(a.n_layers):
+            self._layer_fwd(i, xa, ws.xn[0], ws.qkv[0], ws.o[0], ws.h[0], ws.hn[0], ws.gu[0], ws.y, xb,
+                            None, None, None, B, L, pos0=start_pos, kv=True)
+            xa, xb = xb, xa
+        last = xa.view(B, L, D)[:, L - 1]  # (B, D) strided view: last position of every sample
+        fn = ops.rmsnorm_fwd(last, w["norm.weight"], a.norm_eps)
+        return self._lm_head(fn)
+
+    def _lm_head(self, fn: torch.Tensor) -> torch.Tensor:
+        w, B = self.w.views, fn.shape[0]
+        if B <= 16:
+            return ops.linear_small_m(fn, w["output.weight"], out_fp32=True)
+        return ops.gemm(fn, w["output.weight"]).float()
+
+    def _decode_step(self, tokens: torch.Tensor, pos: int) -> torch.Tensor:
+        """One-token step (q_len = 1): weight-streaming linears + split-KV attention over the cache."""
+        a, w = self.args, self.w.views
+        B, D, F = tokens.shape[0], a.dim, self.ffn_dim
+        if pos + 1 > a.max_seq_len:
+            raise ValueError("KV cache overflow")
+        if self.dec is None or self.dec["B"] != B:
+            e = lambda *s, dt=bf16: torch.empty(*s, device=self.device, dtype=dt)
+            self.dec = {"B": B, "x": e(B, D), "x2": e(B, D), "xn": e(B, D), "qkv": e(B, 3 * D), "o": e(B, D),
+                        "h": e(B, D), "gu": e(B, 2 * F), "y": e(B, F),
+                        "scratch": e(B * a.n_heads * 32 * (self.head_dim + 2), dt=torch.float32)}
+        d = self.dec
+        small = B <= 16
+        lin = (lambda x, wt, out, residual=None: ops.linear_small_m(x, wt, out=out, residual=residual)) if small \
+            else (lambda x, wt, out, residual=None: ops.gemm(x, wt, out, residual=residual))
+        ops.embed_splice(tokens.contiguous(), w["tok_embeddings.weight"], None, None, None, d["x"], B, 1, 0, D)
+        x, x2 = d["x"], d["x2"]
+        for i in range(a.n_layers):
+            p = f"layers.{i}."
+            ops.rmsnorm_fwd(x, w[p + "attention_norm.weight"], a.norm_eps, out=d["xn"])
+            lin(d["xn"], w[p + "wqkv"], d["qkv"])
+            ops.rope_apply(d["qkv"][:, :2 * D], 2 * a.n_heads, self.head_dim, self.rope, 1, pos)
+            ops.kv_append(d["qkv"][:, D:2 * D], d["qkv"][:, 2 * D:], self.kcache[i], self.vcache[i], B, 1,
+                          a.n_heads, self.head_dim, pos, a.max_seq_len)
+            ops.attn_decode(d["qkv"][:, :D], self.kcache[i], self.vcache[i], d["o"], d["scratch"], B,
+                            a.n_heads, self.head_dim, pos + 1, a.max_seq_len, self.scale)
+            lin(d["o"], w[p + "attention.wo.weight"], d["h"], residual=x)
+            ops.rmsnorm_fwd(d["h"], w[p + "ffn_norm.weight"], a.norm_eps, out=d["xn"])
+            lin(d["xn"], w[p + "w13"], d["gu"])
+            ops.swiglu_fwd(d["gu"], d["y"])
+            lin(d["y"], w[p + "feed_forward.w2.weight"], x2, residual=d["h"])
+            x, x2 = x2, x
+        fn = ops.rmsnorm_fwd(x, w["norm.weight"], a.norm_eps, out=d["xn"])
+        return self._lm_head(fn)

@@ -1,0 +1,290 @@
+"""`MetaModel` with the reference's surface (model/accessory/model/meta.py): construction from
+`llama_type` + json configs + tokenizer, `forward(examples, labels, images) -> (loss, dict)`,
+`generate`, `stream_generate`, `compute_logits`, `evaluate_examples`, `sample_top_p`,
+`get_trainable_params`, `get_image_words`.  The host-side control flow (pad trimming, prompt
+force-feeding, stop sequences, left truncation) is restated from the reference line by line; every
+tensor op underneath runs in the sm_100a kernels of the `llama_b200` plugin.
+"""
+from __future__ import annotations
+
+import importlib
+import json
+from typing import Dict, Iterable, List, Optional, Sequence, Union
+
+import torch
+import torch.nn as nn
+
+
+class MetaModel(nn.Module):
+    def __init__(self, llama_type: str = "llama_b200", llama_config: Union[str, dict, Sequence] = (),
+                 tokenizer_path: Optional[str] = None, with_visual: bool = False, max_seq_len: int = 4096,
+                 pretrain_stage: bool = False, max_batch_size: int = 32) -> None:
+        """meta.py:21-86.  `llama_config`: json path(s) and / or dicts merged left to right (:34-39).
+        `tokenizer_path=None` is an extension for token-level use (synthetic benchmarks): then
+        `vocab_size` must come from the config and the string entry points raise.  `max_batch_size`
+        is 32 in the reference (:41); it is a parameter here because BASELINE's sweep goes to 64."""
+        super().__init__()
+        self.llama_type = llama_type
+        self.with_visual = with_visual
+        module = importlib.import_module(f"{__package__}.LLM.{llama_type}")  # the plugin seam, meta.py:30-32
+        ModelArgs, Transformer = module.ModelArgs, module.Transformer
+        llama_args: Dict = {}
+        if isinstance(llama_config, (str, dict)):
+            llama_config = [llama_config]
+        for c in llama_config:
+            if isinstance(c, dict):
+                llama_args.update(c)
+            else:
+                with open(c, "r") as f:
+                    llama_args.update(json.loads(f.read()))
+        llama_args["max_seq_len"] = max_seq_len
+        llama_args["max_batch_size"] = max_batch_size
+        if tokenizer_path is not None:
+            from .tokenizer import Tokenizer
+
+            self.tokenizer = Tokenizer(model_path=tokenizer_path)
+            llama_args["vocab_size"] = self.tokenizer.n_words
+        else:
+            self.tokenizer = None
+            if llama_args.get("vocab_size", -1) <= 0:
+                raise ValueError("without a tokenizer the config must carry vocab_size")
+        args = ModelArgs(**llama_args)
+        self.llma = Transformer(args, with_visual=with_visual)
+        self.criterion = torch.nn.CrossEntropyLoss(ignore_index=0)
+        self._set_default_trainability(pretrain_stage)
+        self.is_peft = getattr(self.llma, "is_peft", False)
+
+    # ------------------------------------------------------------------ trainability (meta.py:224-232)
+    def get_trainable_params(self, pretrain_stage: bool = False):
+        inner = self.llma.get_trainable_params(pretrain_stage)
+        return {"llma." + n: p for n, p in inner.items()}
+
+    def _set_default_trainability(self, pretrain_stage: bool = False):
+        for _, v in self.named_parameters():
+            v.requires_grad = False
+        for _, v in self.get_trainable_params(pretrain_stage).items():
+            v.requires_grad = True
+
+    # ------------------------------------------------------------------ training forward (meta.py:234-263)
+    def forward(self, examples, labels, images=None, depth_imgs=None):
+        with torch.no_grad():
+            non_zero_ = torch.count_nonzero(labels, dim=0)
+            pos = non_zero_.shape[0] - 1
+            nz = non_zero_.tolist()  # one host sync (the reference syncs once per probed column)
+            while pos >= 0 and nz[pos] == 0:
+                pos -= 1
+            if pos == -1:  # nothing to predict in the whole batch
+                print("nothing to predict in the whole batch!")
+                pos = 2
+            examples = examples[:, :pos + 1]
+            labels = labels[:, :pos + 1]
+        if hasattr(self.llma, "loss_forward"):
+            # fused LM-head + shifted CE(ignore_index=0): same value as :251-262, logits stay on chip
+            c_loss = self.llma.loss_forward(examples, labels, images)
+            return c_loss, {}
+        output = self.llma(examples, images)
+        additional_loss = {}
+        if isinstance(output, tuple):
+            output, additional_loss = output
+        output = output[:, :-1, :]
+        labels = labels[:, 1:]
+        if labels.sum() == 0:
+            c_loss = output.mean() * 0
+        else:
+            c_loss = self.criterion(output.reshape(-1, output.shape[-1]), labels.flatten())
+        return c_loss, additional_loss
+
+    # ------------------------------------------------------------------ generation (meta.py:379-485)
+    def _device(self):
+        return next(self.parameters()).device
+
+    @torch.inference_mode()
+    def generate_tokens(self, prompt_tokens: Sequence[Sequence[int]], images=None, max_gen_len: int = 512,
+                        temperature: float = 0.0, top_p: float = 0.95,
+                        stop_sequences: Iterable[Sequence[int]] = (), eos_id: Optional[int] = None):
+        """The token-level body of `generate` (meta.py:414-479).  Returns (generated ids per row,
+        tokens tensor, stop_pos)."""
+        dev = self._device()
+        if images is not None:
+            images = images.to(dev)
+        bsz = len(prompt_tokens)
+        args = self.llma.args
+        assert bsz <= args.max_batch_size, (bsz, args.max_batch_size)
+        prompt_tokens = [list(t) for t in prompt_tokens]
+        min_prompt_size = min(len(t) for t in prompt_tokens)
+        max_prompt_size = max(len(t) for t in prompt_tokens)
+        max_seq_len = args.max_seq_len
+        if images is not None:
+            max_seq_len -= self.llma.image_words
+        total_len = min(max_seq_len, max_gen_len + max_prompt_size)
+        for k, t in enumerate(prompt_tokens):
+            prompt_tokens[k] = t[-(max_seq_len - max_gen_len):]
+        tokens = torch.full((bsz, total_len), 0, device=dev, dtype=torch.long)
+        input_text_mask = torch.full((bsz, total_len), False, device=dev)
+        for k, t in enumerate(prompt_tokens):
+            tokens[k, :len(t)] = torch.tensor(t, device=dev).long()
+            input_text_mask[k, :len(t)] = True
+        start_pos, prev_pos = min_prompt_size, 0
+        if eos_id is None:
+            eos_id = self.tokenizer.eos_id
+        l_stop_tokens = [[eos_id]] + [list(s) for s in stop_sequences]
+        l_stop_tokens = [torch.tensor(s, dtype=tokens.dtype, device=dev) for s in l_stop_tokens]
+        stopped = torch.zeros(bsz, dtype=torch.bool, device=dev)
+        stop_pos = torch.full((bsz,), start_pos + 1, device=dev)
+        for cur_pos in range(start_pos, total_len):
+            logits = self.llma.forward_inference(tokens[:, prev_pos:cur_pos], prev_pos,
+                                                 images if prev_pos == 0 else None).float()
+            if temperature > 0:
+                probs = torch.softmax(logits / temperature, dim=-1)
+                next_token = self.sample_top_p(probs, top_p)
+            else:
+                next_token = self._argmax(logits)
+            next_token = next_token.reshape(-1)
+            next_token = torch.where(input_text_mask[:, cur_pos], tokens[:, cur_pos], next_token)
+            tokens[:, cur_pos] = next_token
+            stop_pos = torch.where(stopped, stop_pos, cur_pos + 1)
+            for stop_token in l_stop_tokens:
+                if cur_pos + 1 - len(stop_token) >= 0:
+                    cond1 = (tokens[:, cur_pos + 1 - len(stop_token):cur_pos + 1] == stop_token.unsqueeze(0)).all(dim=-1)
+                    cond2 = ~input_text_mask[:, cur_pos]
+                    new_stop_cond = cond1 * cond2 * (~stopped)
+                    stop_pos = torch.where(new_stop_cond, cur_pos + 1 - len(stop_token), stop_pos)
+                    stopped = torch.logical_or(new_stop_cond, stopped)
+            if stopped.all():
+                break
+            prev_pos = cur_pos
+        rows = tokens.tolist()
+        sp = stop_pos.tolist()
+        out = [rows[i][len(prompt_tokens[i]):sp[i]] for i in range(bsz)]
+        return out, tokens, stop_pos
+
+    def _argmax(self, logits: torch.Tensor) -> torch.Tensor:
+        """Greedy choice (meta.py:461) on the device kernel: lowest index wins ties like torch.argmax."""
+        from .. import ops
+
+        out = torch.empty(logits.shape[0], device=logits.device, dtype=torch.int64)
+        return ops.argmax(logits.contiguous(), out)
+
+    @torch.inference_mode()
+    def generate(self, prompts: List[str], images=None, depth_images=None, max_gen_len: int = 512,
+                 temperature: float = 0.0, top_p: float = 0.95,
+                 additional_stop_symbols: Iterable[str] = ()) -> List[str]:
+        if isinstance(prompts, str):
+            raise ValueError(f"{self.__class__}.generate expects a batched LIST of prompts, but str is given")
+        if self.tokenizer is None:
+            raise RuntimeError("generate(prompts: List[str]) needs a tokenizer; use generate_tokens")
+        if depth_images is not None:
+            raise NotImplementedError("the RGB-D variant (llama_ens5_2images) is out of scope (SURVEY 8f)")
+        prompt_tokens = [self.tokenizer.encode(x, bos=True, eos=False) for x in prompts]
+        stops = [self.tokenizer.encode_segment(s) for s in additional_stop_symbols]
+        stops += [self.tokenizer.encode_wo_prefix_space(s) for s in additional_stop_symbols]
+        out, _, _ = self.generate_tokens(prompt_tokens, images, max_gen_len, temperature, top_p, stops)
+        return [self.tokenizer.decode(t) for t in out]
+
+    @torch.inference_mode()
+    def stream_generate(self, prompt: str, image=None, max_gen_len: int = 512, temperature: float = 0.0,
+                        top_p: float = 0.95, additional_stop_symbols: Iterable[str] = ()):
+        """meta.py:487-566: batch-1 generator yielding {"text", "end_of_content"}."""
+        dev = self._device()
+        args = self.llma.args
+        if image is not None:
+            image = image.to(dev)
+        prompt_tokens = self.tokenizer.encode(prompt, bos=True, eos=False)
+        max_seq_len = args.max_seq_len
+        if image is not None:
+            max_seq_len -= self.llma.image_words
+        max_prompt_size = max_seq_len - max_gen_len
+        prompt_tokens = prompt_tokens[-max_prompt_size:]
+        prompt_size = len(prompt_tokens)
+        total_len = min(max_seq_len, max_gen_len + prompt_size)
+        tokens = torch.full([total_len], 0, device=dev, dtype=torch.long)
+        tokens[:prompt_size] = torch.tensor(prompt_tokens, device=dev).long()
+        start_pos, prev_pos, generate_until = prompt_size, 0, prompt_size
+        generated = ""
+        for cur_pos in range(start_pos, total_len):
+            logits = self.llma.forward_inference(tokens[None, prev_pos:cur_pos], prev_pos,
+                                                 image if prev_pos == 0 else None).float()
+            if temperature > 0:
+                next_token = self.sample_top_p(torch.softmax(logits / temperature, dim=-1), top_p)
+            else:
+                next_token = self._argmax(logits)
+            next_token = next_token.item()
+            if next_token == self.tokenizer.eos_id:
+                break
+            tokens[cur_pos] = next_token
+            prev_pos = cur_pos
+            generate_until = cur_pos + 1
+            generated = self.tokenizer.decode(tokens[start_pos:generate_until].tolist())
+            stop = False
+            for sym in additional_stop_symbols:
+                idx = generated.find(sym)
+                if idx != -1:
+                    generated, stop = generated[:idx], True
+                    break
+            if stop:
+                break
+            yield {"text": generated, "end_of_content": False}
+        yield {"text": generated, "end_of_content": True}
+
+    def sample_top_p(self, probs, p):
+        """meta.py:568-583 (kept on torch: not on the measured greedy path)."""
+        probs_sort, probs_idx = torch.sort(probs, dim=-1, descending=True)
+        probs_sum = torch.cumsum(probs_sort, dim=-1)
+        mask = probs_sum - probs_sort > p
+        probs_sort[mask] = 0.0
+        probs_sort.div_(probs_sort.sum(dim=-1, keepdim=True))
+        next_token = torch.multinomial(probs_sort, num_samples=1)
+        return torch.gather(probs_idx, -1, next_token)
+
+    # ------------------------------------------------------------------ scoring API (meta.py:265-377)
+    @torch.inference_mode()
+    def compute_logits(self, examples: List[Union[str, List[int]]], images=None, bos=True, eos=False):
+        """meta.py:265-304: per-example (T_i, V) logits of a padded batch."""
+        if self.tokenizer is not None:
+            examples = [self.tokenizer.encode(x, bos, eos) if isinstance(x, str) else x for x in examples]
+        l_seq_len = [len(x) for x in examples]
+        assert max(l_seq_len) <= self.llma.args.max_seq_len
+        dev = self._device()
+        token_tensor = torch.full((len(examples), max(l_seq_len)), 0, device=dev, dtype=torch.long)
+        for i, item in enumerate(examples):
+            token_tensor[i, :len(item)] = torch.tensor(item, device=dev).long()
+        logits = self.llma.forward(token_tensor, images)
+        return [lg[:n] for lg, n in zip(logits, l_seq_len)]
+
+    @torch.inference_mode()
+    def evaluate_examples(self, examples, contexts=None, images=None):
+        """meta.py:306-377: per-example log-likelihood / perplexity of the non-context part."""
+        if contexts is not None:
+            assert len(contexts) == len(examples)
+        if self.tokenizer is not None:
+            examples = [self.tokenizer.encode(x, True, True) if isinstance(x, str) else x for x in examples]
+            if contexts is not None:
+                contexts = [self.tokenizer.encode(x, True, False) if isinstance(x, str) else x for x in contexts]
+        if contexts is not None:
+            for c, e in zip(contexts, examples):
+                assert c == e[:len(c)], "contexts should be prefixes of examples"
+        l_logits = self.compute_logits(examples, images)
+        result = {"logits": l_logits, "log_likelihood": [], "ppl": []}
+        for i, (item, logits) in enumerate(zip(examples, l_logits)):
+            logits = logits.float()[:-1]
+            labels = torch.tensor(item, device=logits.device).long()[1:]
+            if contexts is not None:
+                n_ctx = len(contexts[i]) - 1
+                logits, labels = logits[n_ctx:], labels[n_ctx:]
+            ll = -torch.nn.functional.cross_entropy(logits, labels, reduction="sum").item()
+            result["log_likelihood"].append(ll)
+            result["ppl"].append(float(torch.exp(torch.tensor(-ll / max(len(labels), 1)))))
+        return result
+
+    def get_image_words(self):
+        return self.llma.image_words
+
+    def get_quant_blocklist(self) -> List[str]:
+        if hasattr(self.llma, "get_quant_blocklist"):
+            return ["llma." + x for x in self.llma.get_quant_blocklist()]
+        return []
+
+    def get_basic_block_classes(self):
+        if hasattr(self.llma, "get_basic_block_classes"):
+            return self.llma.get_basic_block_classes()
+        return [type(self.llma.layers[0])]

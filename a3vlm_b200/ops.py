@@ -128,9 +128,9 @@ def colsum_partials(partial, out, accumulate=False):
     return out
 
 
-def colsum_bf16(x, out):
+def colsum_bf16(x, out, accumulate=False):
     M, N = x.shape
-    rc = _L().a3_colsum_bf16(_p(x), M, N, x.stride(0), _p(out), _st())
+    rc = _L().a3_colsum_bf16(_p(x), M, N, x.stride(0), _p(out), int(accumulate), _st())
     _lib.check(rc, "a3_colsum_bf16")
     return out
 
@@ -242,6 +242,12 @@ def vit_assemble_lnpre(patch_out, cls, pos, ln_w, ln_b, out, B, Np, D, eps):
 # ----------------------------------------------------------------------------------------- loss / sampling
 def count_nonzero(labels, count):
     _lib.check(_L().a3_count_nonzero(_p(labels), labels.numel(), _p(count), _st()), "a3_count_nonzero")
+
+
+def shift_labels(labels, shifted, count):
+    B, T = labels.shape
+    rc = _L().a3_shift_labels(_p(labels), labels.stride(0), _p(shifted), B, T, _p(count), _st())
+    _lib.check(rc, "a3_shift_labels")
 
 
 def cross_entropy(logits, labels, row_loss, count, grad_scale=1.0, want_grad=True):

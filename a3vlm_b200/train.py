@@ -1,0 +1,70 @@
+"""Fine-tune step plumbing with the reference's call shapes (model/accessory/engine_finetune.py:44-79,
+model/accessory/util/misc.py:296-321): an optimiser object and a loss scaler that drive the engine's
+fused all-reduce / global-norm clip / AdamW kernels instead of FSDP + apex FusedAdam."""
+from __future__ import annotations
+
+import contextlib
+from typing import Optional
+
+import torch
+
+
+class AdamW(torch.optim.Optimizer):
+    """torch.optim.AdamW-shaped front end (M/main_finetune.py:284-285: AdamW(param_groups, lr,
+    betas=(0.9, 0.95))) over the engine's flat fp32 master / m / v buffers.  The decay / no-decay split
+    of M/util/misc.py:586-599 is built into the flat layout; `weight_decay` applies to the decay
+    region only.  `step(max_norm=...)` fuses the global-L2 clip of M/util/clip_grad.py."""
+
+    def __init__(self, model, lr: float = 1e-3, betas=(0.9, 0.95), eps: float = 1e-8, weight_decay: float = 0.0):
+        llma = getattr(model, "llma", model)
+        self.engine = llma.engine
+        params = [p for p in llma.parameters() if p.requires_grad]
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+
+    @torch.no_grad()
+    def step(self, closure=None, max_norm: Optional[float] = None):
+        g = self.param_groups[0]
+        self.last_norm_sq = self.engine.optimizer_step(g["lr"], g["weight_decay"], max_norm or 0.0, g["betas"], g["eps"])
+        return None
+
+    def grad_norm(self) -> torch.Tensor:
+        """Pre-clip global gradient norm of the last step (device tensor; reading it syncs)."""
+        return self.last_norm_sq.sqrt()
+
+
+class NativeScalerWithGradNormCount:
+    """M/util/misc.py:296-321 for bf16 (no loss scaling needed -- the reference's ShardedGradScaler is
+    only enabled for fp16, :299-300): backward, inside no_sync() on accumulation micro-steps, then
+    clip + step."""
+
+    state_dict_key = "amp_scaler"
+
+    def __init__(self, args=None):
+        pass
+
+    def __call__(self, loss, optimizer, model, parameters=None, clip_grad=None, update_grad=True):
+        llma = getattr(model, "llma", model)
+        if update_grad:
+            loss.backward()
+            optimizer.step(max_norm=clip_grad)
+            return optimizer.grad_norm()
+        with no_sync(llma):
+            loss.backward()
+        return None
+
+    def state_dict(self):
+        return {}
+
+    def load_state_dict(self, state_dict):
+        pass
+
+
+@contextlib.contextmanager
+def no_sync(llma):
+    """FSDP.no_sync() equivalent (M/util/misc.py:311-313): skip the gradient all-reduce."""
+    prev = llma.sync_grads
+    llma.sync_grads = False
+    try:
+        yield
+    finally:
+        llma.sync_grads = prev

@@ -88,8 +88,9 @@ int a3_layernorm_bwd(const void* dy, const void* x, const void* w, const float* 
 /* out[D] (bf16 or fp32) (+)= sum_p partial[p][D] */
 int a3_colsum_partials(const float* partial, int nparts, int D, void* out, int out_fp32,
                        int accumulate, void* stream);
-/* out[N] (bf16) = sum_m X[m][N] (bias gradients). */
-int a3_colsum_bf16(const void* X, int M, int N, long long ldx, void* out, void* stream);
+/* out[N] (bf16) (+)= sum_m X[m][N] (bias gradients). */
+int a3_colsum_bf16(const void* X, int M, int N, long long ldx, void* out, int accumulate,
+                   void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * RoPE (absent reference file LLM/llama.py, call sites llama_ens5.py:118,271-274):
@@ -165,6 +166,11 @@ int a3_vit_assemble_lnpre(const void* patch_out, const void* cls, const void* po
  * must be pre-computed with a3_count_nonzero.
  * ------------------------------------------------------------------------------------------- */
 int a3_count_nonzero(const long long* labels, int n, int* count, void* stream);
+/* The shift of meta.py:256-257 (logits[:, :-1] vs labels[:, 1:]) as a label buffer aligned with the
+ * logit rows: shifted[b][t] = labels[b][t+1] for t < T-1, 0 (ignored) for t = T-1; labels has row
+ * stride ld_labels.  count = number of non-zero shifted labels. */
+int a3_shift_labels(const long long* labels, long long ld_labels, long long* shifted, int B, int T,
+                    int* count, void* stream);
 int a3_cross_entropy(void* logits, long long ld, const long long* labels, float* row_loss,
                      const int* count, int rows, int V, float grad_scale, int want_grad,
                      void* stream);

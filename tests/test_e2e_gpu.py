@@ -1,0 +1,215 @@
+"""End-to-end parity of the CUDA path (through the reference-facing API: MetaModel / llama_b200
+Transformer) against the committed golden vectors and against the CPU oracle run live on a second,
+larger configuration.
+
+Tolerances (stated here as the north star asks): the activations are bf16, whose spacing (2^-8
+relative) is coarser than rtol 1e-3, and the oracle accumulates in a different order, so element-wise
+agreement is bounded by a few bf16 ulps that compound through the layers.  We therefore check
+(a) relative L2 error of each tensor <= 1e-2 (typically ~3e-3), (b) max |err| <= 4 ulps of the
+tensor's max magnitude, (c) the scalar loss to rtol 2e-3, (d) greedy token ids EXACTLY, and
+(e) fp32 quantities that do not pass through bf16 storage (AdamW update given equal grads) to 1e-5."""
+import math
+import os
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+bf16 = torch.bfloat16
+
+
+def rel_l2(got, ref):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    return ((got - ref).norm() / ref.norm().clamp_min(1e-12)).item()
+
+
+def check(name, got, ref, rel=1e-2, ulps=4):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    assert got.shape == ref.shape, (name, got.shape, ref.shape)
+    r = rel_l2(got, ref)
+    print(f"{name}: rel l2 {r:.3e}")
+    mx = (got - ref).abs().max().item()
+    bound = ulps * 2.0 ** -8 * max(ref.abs().max().item(), 1e-6)
+    assert r <= rel, f"{name}: rel l2 {r:.3e} > {rel}"
+    assert mx <= bound, f"{name}: max err {mx:.3e} > {bound:.3e}"
+    return r
+
+
+def build(a, v, sd, max_seq_len=None):
+    from a3vlm_b200.model import MetaModel
+
+    cfg = dict(dim=a.dim, n_layers=a.n_layers, n_heads=a.n_heads, vocab_size=a.vocab_size,
+               multiple_of=a.multiple_of, norm_eps=a.norm_eps)
+    if v is not None:
+        cfg.update(image_size=v.image_size, vit_patch=v.patch, vit_width=v.width, vit_layers=v.layers,
+                   vit_heads=v.heads, vit_mlp=v.mlp, vit_quick_gelu=v.quick_gelu)
+    m = MetaModel("llama_b200", cfg, None, with_visual=v is not None, max_seq_len=max_seq_len or a.max_seq_len,
+                  max_batch_size=a.max_batch_size)
+    missing, unexpected = m.llma.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    return m
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return torch.load(os.path.join(ROOT, "tests", "golden", "tiny_e2e.pt"))
+
+
+@pytest.fixture(scope="module")
+def tiny(gold):
+    import a3vlm_oracle as O
+    import make_golden as MG
+
+    a, v = MG.tiny_cfg()
+    sd = O.init_params(a, v, seed=gold["seed"], output_scale=gold["output_scale"])
+    return build(a, v, sd), sd
+
+
+def test_state_dict_names_and_roundtrip(tiny):
+    m, sd = tiny
+    got = m.llma.state_dict()
+    assert set(got.keys()) == set(sd.keys())
+    for k in sd:
+        assert torch.equal(got[k].cpu(), sd[k]), k
+    assert all(k.startswith("llma.") for k in m.get_trainable_params())
+    assert not any("clip." in k for k in m.get_trainable_params())
+    assert m.get_image_words() == 5 + 2
+
+
+def test_forward_logits_match_golden(tiny, gold):
+    m, _ = tiny
+    with torch.no_grad():
+        eng = m.llma.engine
+        ws = eng.workspace(2, 9, eng.image_words, True)
+        tok = eng.vit_forward(gold["image"].cuda(), ws.vit)
+        check("image_tokens", tok.view(2, 5, -1), gold["image_tokens"])
+        lg = m.llma(gold["tokens"], gold["image"])
+        check("train_logits", lg, gold["train_logits"])
+        lg = m.llma(gold["tokens"], None)
+        check("train_logits_noimg", lg, gold["train_logits_noimg"])
+
+
+def test_inference_prefill_decode_match_golden(tiny, gold):
+    m, _ = tiny
+    pl = m.llma.forward_inference(gold["tokens"][:, :6], 0, gold["image"])
+    assert pl.dtype == torch.float32 and pl.shape == (2, 512)
+    check("prefill_logits", pl, gold["prefill_logits"])
+    assert m.llma.cache_image_words == 7
+    dl = m.llma.forward_inference(gold["tokens"][:, 6:7], 6)
+    check("decode_logits", dl, gold["decode_logits"])
+    # decode through the cache == prefill of the longer prompt (cache vs no-cache equivalence)
+    pl7 = m.llma.forward_inference(gold["tokens"][:, :7], 0, gold["image"])
+    check("decode_vs_prefill", dl, pl7, rel=1e-2)
+
+
+def test_greedy_generate_token_exact(tiny, gold):
+    m, _ = tiny
+    out, toks, _ = m.generate_tokens(gold["prompts"], gold["image"], max_gen_len=gold["max_gen_len"], eos_id=2)
+    assert out == gold["generated"], (out, gold["generated"])
+    assert torch.equal(toks.cpu(), gold["gen_tokens"])
+
+
+def test_loss_grads_and_adamw_step_match_golden(tiny, gold):
+    from a3vlm_b200.train import AdamW, NativeScalerWithGradNormCount
+
+    m, sd = tiny
+    m.llma.load_state_dict(sd)
+    opt = AdamW(m, lr=1e-3, betas=(0.9, 0.95), weight_decay=0.1)
+    m.zero_grad(set_to_none=True)
+    loss, extra = m(gold["tokens"].cuda(), gold["labels"].cuda(), images=gold["image"].cuda())
+    assert extra == {}
+    assert abs(loss.item() - gold["loss"].item()) <= 2e-3 * abs(gold["loss"].item()), (loss.item(), gold["loss"].item())
+    scaler = NativeScalerWithGradNormCount()
+    norm = scaler(loss, opt, m, clip_grad=0.5, update_grad=True)
+    named = dict(m.llma.named_parameters())
+    worst = 0.0
+    for k, gn in gold["grad_norm"].items():
+        g = named[k].grad
+        assert g is not None, k
+        n = g.float().norm().item()
+        assert abs(n - gn) <= 2e-2 * gn + 1e-4, (k, n, gn)
+        worst = max(worst, rel_l2(g.flatten()[:64], gold["grad_head"][k]))
+    for k, gref in gold["grad_full"].items():
+        check("grad " + k, named[k].grad, gref, rel=2e-2, ulps=6)
+    assert abs(norm.item() - gold["total_norm"]) <= 1e-2 * gold["total_norm"]
+    for k, pref in gold["post_step"].items():
+        # bf16 shadow of the fp32 master after one clipped AdamW step.  Step 1 of Adam moves every weight
+        # by lr * sign(g) (m / sqrt(v) = +-1), so elements whose gradient is rounding noise around zero
+        # may legitimately land 2*lr apart; everything else must agree to bf16 resolution.  (The update
+        # rule itself is checked exactly against torch.optim.AdamW in test_kernels_gpu.py.)
+        got, ref = named[k].float().cpu(), pref.to(bf16).float()
+        bad = (got - ref).abs() > (1e-5 + 2 ** -7 * ref.abs())
+        assert bad.float().mean().item() <= 0.02, (k, bad.float().mean().item())
+        assert (got - ref).abs().max().item() <= 2.5e-3, k  # never more than 2*lr (+ rounding) away
+
+
+def test_autograd_logits_path_and_accumulation(tiny, gold):
+    """Transformer.forward returns differentiable logits (reference engine path: CE outside the model);
+    two accumulated micro-steps double the gradients (M/util/misc.py:311-313 no_sync semantics)."""
+    m, sd = tiny
+    m.llma.load_state_dict(sd)
+    m.zero_grad(set_to_none=True)
+    tok, lab, img = gold["tokens"].cuda(), gold["labels"].cuda(), gold["image"].cuda()
+    logits = m.llma(tok, img)
+    loss = torch.nn.functional.cross_entropy(logits[:, :-1].reshape(-1, 512).float(), lab[:, 1:].flatten(), ignore_index=0)
+    assert abs(loss.item() - gold["loss"].item()) <= 2e-3 * abs(gold["loss"].item())
+    loss.backward()
+    named = dict(m.llma.named_parameters())
+    g1 = {k: named[k].grad.clone() for k in gold["grad_full"]}
+    for k, gref in gold["grad_full"].items():
+        check("grad(autograd) " + k, g1[k], gref, rel=2e-2, ulps=6)
+    loss2, _ = m(tok, lab, images=img)
+    loss2.backward()  # grads not reset -> accumulate
+    for k in g1:
+        check("accumulated " + k, named[k].grad, 2 * g1[k].float(), rel=2e-2, ulps=8)
+
+
+def test_live_oracle_midsize():
+    """A second configuration checked against the oracle run live on the host CPU (seconds): wider
+    model, 4 heads, ViT grid 4x4, ragged labels with a padded tail (pad trimming, meta.py:235-249)."""
+    import a3vlm_oracle as O
+
+    a = O.ModelArgs(dim=512, n_layers=3, n_heads=4, vocab_size=1024, multiple_of=128, max_seq_len=128, max_batch_size=8)
+    v = O.VisionArgs(image_size=56, patch=14, width=256, layers=3, heads=4, mlp=512, quick_gelu=True)
+    sd = O.init_params(a, v, seed=21, output_scale=6.0)
+    orc = O.OracleTransformer(a, v, sd)
+    m = build(a, v, sd)
+    g = torch.Generator().manual_seed(3)
+    B, T = 3, 40
+    tok = torch.randint(3, 1024, (B, T), generator=g)
+    tok[:, 0] = 1
+    lab = tok.clone()
+    lab[:, :10] = 0
+    tok[:, 33:] = 0
+    lab[:, 33:] = 0
+    img = torch.randn(B, 3, 56, 56, generator=g)
+    exact = O.OracleTransformer(a, v, sd, act_dtype=torch.float32)  # same bf16 weights, no activation rounding
+    with torch.no_grad():
+        ref_loss = O.meta_forward_loss(orc, tok, lab, img)
+        ref_logits = orc.forward(tok[:, :33], img)
+        exact_logits = exact.forward(tok[:, :33], img)
+        got_logits = m.llma(tok[:, :33], img)
+        got_loss, _ = m(tok.cuda(), lab.cuda(), images=img.cuda())
+    # both bf16 paths are rounding-noise away from the unrounded model; ours must not be further than
+    # the oracle's own bf16 path by more than 25 %, and the two bf16 paths agree to 2e-2
+    e_ref, e_got = rel_l2(ref_logits, exact_logits), rel_l2(got_logits, exact_logits)
+    print(f"midsize: |oracle_bf16 - fp32| = {e_ref:.3e}, |cuda - fp32| = {e_got:.3e}, |cuda - oracle_bf16| = {rel_l2(got_logits, ref_logits):.3e}")
+    assert e_got <= 1.25 * e_ref + 1e-3, (e_got, e_ref)
+    check("midsize logits", got_logits, ref_logits, rel=2e-2, ulps=6)
+    assert abs(got_loss.item() - ref_loss.item()) <= 2e-3 * abs(ref_loss.item())
+    prompts = [[1, 5, 9], [1, 7, 8, 9, 10], [1, 3]]
+    ref_gen, ref_tok, _ = O.generate_tokens(orc, prompts, images=img, max_gen_len=6, eos_id=2)
+    got_gen, got_tok, _ = m.generate_tokens(prompts, img, max_gen_len=6, eos_id=2)
+    assert got_gen == ref_gen
+
+
+def test_no_cpu_fallback():
+    from a3vlm_b200 import ops
+    from a3vlm_b200._lib import A3Error
+
+    with pytest.raises(A3Error):
+        ops.rmsnorm_fwd(torch.zeros(2, 8, dtype=bf16), torch.ones(8, dtype=bf16), 1e-5)
