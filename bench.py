@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""Headline benchmark (BASELINE.json): images/sec for a 336x336 image + 256-token prompt through the
+fine-tune step (frozen ViT-L/14 forward, visual_proj + Llama-2-7B forward + backward, gradient
+all-reduce for N > 1, global-norm clip, AdamW) at batch 8 per GPU, random-init weights, synthetic data.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One JSON line on stdout (rank 0).  `value` = device-resident inputs; `e2e` = the same step driven
+through the reference-facing API (MetaModel.forward -> loss.backward -> optimiser.step) with pinned
+HOST inputs copied in and the loss read back every step.  `roofline` is for the dominant kernel (the
+tcgen05 GEMM): total algorithmic GEMM FLOPs of one step / the summed CUDA-event durations of its
+launches in an instrumented step.  `cpu_baseline` / `--impl reference` time the CPU oracle restatement of
+the reference path (oracle/a3vlm_oracle.py; the reference itself cannot be imported) on the
+host cores on a bounded sample (batch 1, a few decoder layers, extrapolated to 32).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODELS = {
+    "7b": dict(dim=4096, n_layers=32, n_heads=32, vocab_size=32000, multiple_of=256, norm_eps=1e-5),
+    "13b": dict(dim=5120, n_layers=40, n_heads=40, vocab_size=32000, multiple_of=256, norm_eps=1e-5),
+    "tiny": dict(dim=256, n_layers=2, n_heads=2, vocab_size=512, multiple_of=64, norm_eps=1e-5),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(bf16=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained"), hbm=d["hbm_gbs"], src="measured")
+    return dict(bf16=1590.0, bf16_sustained=1400.0, hbm=6650.0, src="fallback")
+
+
+# ------------------------------------------------------------------------------------------ flops
+def flops_per_sample(cfg, S, T, train=True):
+    """causal attention counted at half, LM head on the T text positions, frozen ViT
+    fwd-only, trainable parts 3x fwd."""
+    D, NL, V = cfg["dim"], cfg["n_layers"], cfg["vocab_size"]
+    hidden = int(2 * 4 * D / 3)
+    F = cfg["multiple_of"] * ((hidden + cfg["multiple_of"] - 1) // cfg["multiple_of"])
+    g = S // 14
+    N = g * g + 1
+    L = T + N + 2
+    vit = 2 * g * g * 588 * 1024 + 24 * (2 * N * 12 * 1024 ** 2 + 4 * N * N * 1024)
+    proj = 2 * N * 1024 * D
+    lin = 2 * NL * (4 * D * D + 3 * D * F) * L
+    attn = NL * 2 * L * L * D
+    head = 2 * D * V * T
+    fwd = vit + proj + lin + attn + head
+    total = vit + 3 * (proj + lin + attn + head) if train else fwd
+    return dict(fwd=fwd, total=total, L=L, N=N, F=F)
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in self.rows)]
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------ reference / CPU arm
+def cpu_reference_sample(cfg, S, T, sample_layers=2, repeats=1):
+    """Times the oracle restatement (PyTorch eager, bf16 linears on the host cores) on a bounded sample
+    of the workload: batch 1, full ViT forward, `sample_layers` decoder layers fwd+bwd, LM head + loss
+    fwd+bwd; the decoder time is extrapolated linearly to n_layers.  Returns seconds per image."""
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import a3vlm_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    a_small = O.ModelArgs(**{**cfg, "n_layers": sample_layers, "max_seq_len": 2048})
+    a_zero = O.ModelArgs(**{**cfg, "n_layers": 0, "max_seq_len": 2048})
+    v = O.VisionArgs(image_size=S)
+    sd = O.init_params(a_small, v, seed=2)
+    g = torch.Generator().manual_seed(1)
+    tok = torch.randint(3, cfg["vocab_size"], (1, T), generator=g)
+    tok[:, 0] = 1
+    lab = tok.clone()
+    lab[:, : T // 2] = 0
+    img = torch.randn(1, 3, S, S, generator=g)
+    train = [k for k in sd if not k.startswith("clip.")]
+
+    def run(args):
+        for k in train:
+            sd[k].requires_grad_(True)
+            sd[k].grad = None
+        m = O.OracleTransformer(args, v, sd, native_linear=True)
+        t0 = time.perf_counter()
+        loss = O.meta_forward_loss(m, tok, lab, img)
+        loss.backward()
+        return time.perf_counter() - t0
+
+    t_small = min(run(a_small) for _ in range(repeats))
+    t_zero = min(run(a_zero) for _ in range(repeats))
+    per_layer = max(t_small - t_zero, 0.0) / sample_layers
+    full = t_zero + per_layer * cfg["n_layers"]
+    sample = (f"oracle (torch eager, bf16 linears) batch 1, {S}px + {T} tok: ViT fwd + head/loss fwd+bwd = {t_zero:.2f}s, "
+              f"{sample_layers} decoder layers fwd+bwd = {t_small - t_zero:.2f}s, extrapolated x{cfg['n_layers']}/{sample_layers}")
+    return full, cores, sample
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    S, T = args.image_size, args.text_len
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_sample(cfg, S, T, sample_layers=1)
+    times = []
+    t_start = time.perf_counter()
+    for _ in range(args.steps):
+        full, cores, sample = cpu_reference_sample(cfg, S, T)
+        times.append(full)
+        if time.perf_counter() - t_start > 240:
+            break
+    sec = statistics.mean(times)
+    val = 1.0 / sec
+    fl = flops_per_sample(cfg, S, T)
+    line = {"impl": "reference", "metric": "images/sec (336x336 + 256-tok prompt) fwd+bwd", "value": val, "unit": "images/s",
+            "n_gpus": args.gpus, "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(args, cfg, fl, 1),
+            "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, cfg, fl, n):
+    return {"workload": f"finetune step llama-{args.model} + ViT-L/14@{args.image_size}: batch {args.batch}/GPU, "
+                        f"T={args.text_len} text tokens, W={fl['N'] + 2} image words, L={fl['L']}",
+            "step": "ViT fwd (frozen) + visual_proj/LLM fwd+bwd + fused CE + grad all-reduce (N>1) + global-norm clip + AdamW",
+            "global_batch": args.batch * n, "text_len": args.text_len, "seq_len": fl["L"], "image_size": args.image_size,
+            "parallelism": f"dp{n}", "l2_policy": "working set (13.5 GB weights + activations) >> 126 MB L2, no flush needed",
+            "tflop_per_image": fl["total"] / 1e12}
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="7b", choices=list(MODELS))
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--text-len", type=int, default=256)
+    ap.add_argument("--image-size", type=int, default=336)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu", action="store_true",
+                    help="profiling aid: warm up, run ONE device step between cudaProfilerStart/Stop, exit "
+                         "(use with `ncu --profile-from-start off`; prints no bench line)")
+    args = ap.parse_args()
+    cfg = MODELS[args.model]
+    if args.impl == "reference":
+        return run_reference(args, cfg)
+
+    import torch
+    import torch.distributed as dist
+
+    from a3vlm_b200 import ops
+    from a3vlm_b200.model import MetaModel
+    from a3vlm_b200.train import AdamW, NativeScalerWithGradNormCount
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    args.warmup = max(args.warmup, 3)
+    B, T, S = args.batch, args.text_len, args.image_size
+    fl = flops_per_sample(cfg, S, T)
+    pk = peaks()
+
+    model = MetaModel("llama_b200", {**cfg, "image_size": S}, None, with_visual=True, max_seq_len=2048)
+    model.llma.reset_parameters(seed=2 + 0)  # identical replicas on every rank
+    eng = model.llma.engine
+    if world > 1:
+        model.llma.enable_data_parallel()
+    opt = AdamW(model, lr=2e-5, betas=(0.9, 0.95), weight_decay=0.0)  # M/scripts/a3vlm_train.sh: lr 2e-5, wd 0
+    scaler = NativeScalerWithGradNormCount()
+    clip = 8.0  # --clip_grad 8
+
+    g = torch.Generator().manual_seed(100 + rank)
+    tok_h = torch.randint(3, cfg["vocab_size"], (B, T), generator=g)
+    tok_h[:, 0] = 1
+    lab_h = tok_h.clone()
+    lab_h[:, : T // 2] = 0
+    img_h = torch.randn(B, 3, S, S, generator=g)
+    tok_h, lab_h, img_h = tok_h.pin_memory(), lab_h.pin_memory(), img_h.pin_memory()
+    tok_d, lab_d, img_d = tok_h.to(dev), lab_h.to(dev), img_h.to(dev)
+
+    hook = finish = None
+    grad_scale = 1.0 / world
+
+    def step_device():
+        nonlocal hook, finish
+        ws, _ = eng.forward_train(tok_d, img_d, lab_d)
+        if world > 1:
+            hook, finish = eng.allreduce_hook(model.llma.dp_group)
+        eng.backward(ws, tok_d, ws.logits, accumulate=False, on_bucket=hook, scale=grad_scale)
+        if finish:
+            finish()
+        eng.optimizer_step(2e-5, 0.0, clip)
+        return ws.loss
+
+    def step_e2e():
+        tok, lab, img = tok_h.to(dev, non_blocking=True), lab_h.to(dev, non_blocking=True), img_h.to(dev, non_blocking=True)
+        model.zero_grad(set_to_none=True)
+        loss, _ = model(tok, lab, images=img)
+        lv = loss.item()  # D2H read of the step's result (M/engine_finetune.py:54)
+        scaler(loss, opt, model, clip_grad=clip, update_grad=True)
+        return lv
+
+    def timed(fn, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, out
+
+    for _ in range(args.warmup):
+        step_device()
+    torch.cuda.synchronize()
+    if args.ncu:
+        torch.cuda.profiler.start()
+        step_device()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
+    clocks = ClockSampler(local)
+    clocks.start()
+    ops.reset_launch_count()
+    ms, loss_t = timed(step_device, args.steps)
+    launches = ops.launch_count()
+    clk = clocks.stop()
+    ms_step = ms / args.steps
+    value = B * world / (ms_step / 1e3)
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e, last_loss = timed(step_e2e, args.steps)
+    ms_e2e /= args.steps
+    e2e = B * world / (ms_e2e / 1e3)
+    h2d = tok_h.numel() * 8 + lab_h.numel() * 8 + img_h.numel() * 4
+
+    # forward-only (the north star's "% of tensor roofline on the fused ViT+LLM forward at batch 8")
+    def fwd_only():
+        eng.forward_train(tok_d, img_d, lab_d, want_grad=False)
+    ms_fwd, _ = timed(fwd_only, args.steps)
+    ms_fwd /= args.steps
+    fwd_tflops = B * fl["fwd"] / (ms_fwd / 1e3) / 1e12
+
+    # dominant kernel: every tcgen05 GEMM launch of one instrumented step, CUDA events around each
+    roof = None
+    if rank == 0:
+        recs = []
+        orig = ops.gemm
+
+        def timed_gemm(a, b, out=None, **kw):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = orig(a, b, out, **kw)
+            e1.record()
+            a_mn, b_mn = kw.get("a_mn", False), kw.get("b_mn", False)
+            M = kw.get("M") or (a.shape[1] if a_mn else a.shape[0])
+            K = kw.get("K") or (a.shape[0] if a_mn else a.shape[1])
+            N = kw.get("N") or (b.shape[1] if b_mn else b.shape[0])
+            recs.append((e0, e1, 2.0 * M * N * K))
+            return r
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        import a3vlm_b200.engine as E
+
+        E.ops.gemm = timed_gemm
+        try:
+            ws, _ = eng.forward_train(tok_d, img_d, lab_d)
+            eng.backward(ws, tok_d, ws.logits, accumulate=False, on_bucket=None, scale=grad_scale)
+        finally:
+            E.ops.gemm = orig
+        torch.cuda.synchronize()
+        tot_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in recs)
+        tot_fl = sum(f for _, _, f in recs)
+        ach = tot_fl / (tot_ms / 1e3) / 1e12
+        roof = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05/TMEM/TMA)", "achieved": ach, "peak": pk["bf16"],
+                "unit": "TFLOP/s", "frac": ach / pk["bf16"], "peak_source": pk["src"] + " (burst; sustained %s)" % pk["bf16_sustained"],
+                "launches_per_step": len(recs), "avg_launch_ms": tot_ms / len(recs), "gemm_ms_per_step": tot_ms,
+                "gemm_share_of_step": tot_ms / ms_step, "flops_per_launch": tot_fl / len(recs), "traffic": None}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        sec, cores, sample = cpu_reference_sample(cfg, S, T)
+        cpu = {"value": 1.0 / sec, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}
+    step_tflops = B * fl["total"] / (ms_step / 1e3) / 1e12
+    line = {"metric": "images/sec (336x336 + 256-tok prompt) fwd+bwd", "value": value, "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, cfg, fl, world),
+            "clocks": clk,
+            "e2e": {"value": e2e, "unit": "images/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "api": "MetaModel.forward -> loss.item() -> NativeScalerWithGradNormCount(loss, AdamW, clip_grad=8)"},
+            "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+            "step_tflops_per_gpu": step_tflops, "step_frac_of_bf16_peak": step_tflops / pk["bf16"],
+            "forward": {"ms": ms_fwd, "tflops": fwd_tflops, "frac_of_bf16_peak": fwd_tflops / pk["bf16"],
+                        "what": "ViT + projector + LLM forward + LM head + CE at batch %d" % B},
+            "loss": float(loss_t.item()), "e2e_last_loss": last_loss}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
