@@ -18,6 +18,7 @@
 #include "ptx.cuh"
 #include "a3vlm_b200.h"
 #include "common.cuh"
+#include <cstdlib>
 
 namespace a3 {
 
@@ -69,6 +70,125 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == 1) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
   if (act == 2) return v / (1.0f + __expf(-1.702f * v));
   return v;
+}
+
+
+// Epilogue of one accumulator tile for the 32 rows a warp owns: TMEM -> registers -> fused
+// alpha / bias / activation / RoPE / residual / accumulate -> global (bf16 or fp32).
+template <int BN>
+__device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t t_row, int row, int n0) {
+  const bool row_ok = row < p.M;
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    uint32_t r[32];
+    tmem_ld_32x32(t_row + c * 32, r);
+    tmem_ld_wait();
+    const int col0 = n0 + c * 32;
+    if (row_ok && col0 < p.N) {
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+      const int ncols = min(32, p.N - col0);  // N % 8 == 0 is enforced on the host
+      if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          if (j < ncols) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(p.bias + col0 + j));
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 f = unpack_bf16x2(w[t]);
+              v[j + 2 * t] += f.x;
+              v[j + 2 * t + 1] += f.y;
+            }
+          }
+        }
+      }
+      if (!p.out_fp32) {
+        // bf16 path mirrors the reference's rounding points: Linear output rounds to bf16,
+        // the activation rounds, the residual add rounds.
+        if (p.act) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = apply_act(bf16_round(v[j]), p.act);
+        }
+        if (col0 < p.rope_cols) {
+          // apply_rotary_emb on the bf16-rounded projection, fp32 math, one rounding at the
+          // store.  Heads are 128 wide, so pair index = (col % 128) / 2.
+          const int pos = p.rope_pos0 + row % p.rope_period;
+          const float2* tp = p.rope + static_cast<long long>(pos) * 64 + ((col0 & 127) >> 1);
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float2 cs = __ldg(tp + (j >> 1));
+            const float a = bf16_round(v[j]), b = bf16_round(v[j + 1]);
+            v[j] = a * cs.x - b * cs.y;
+            v[j + 1] = a * cs.y + b * cs.x;
+          }
+        }
+        if (p.residual) {
+          const __nv_bfloat16* rp = p.residual + static_cast<long long>(row) * p.ldr + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (j < ncols) {
+              const uint4 q = *reinterpret_cast<const uint4*>(rp + j);
+              const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float2 f = unpack_bf16x2(w[t]);
+                v[j + 2 * t] = bf16_round(v[j + 2 * t]) + f.x;
+                v[j + 2 * t + 1] = bf16_round(v[j + 2 * t + 1]) + f.y;
+              }
+            }
+          }
+        }
+        __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) +
+                            static_cast<long long>(row) * p.ldc + col0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          if (j < ncols) {
+            if (p.accumulate) {
+              const uint4 q = *reinterpret_cast<const uint4*>(cp + j);
+              const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float2 f = unpack_bf16x2(w[t]);
+                v[j + 2 * t] += f.x;
+                v[j + 2 * t + 1] += f.y;
+              }
+            }
+            uint4 o;
+            o.x = pack_bf16x2(v[j], v[j + 1]);
+            o.y = pack_bf16x2(v[j + 2], v[j + 3]);
+            o.z = pack_bf16x2(v[j + 4], v[j + 5]);
+            o.w = pack_bf16x2(v[j + 6], v[j + 7]);
+            *reinterpret_cast<uint4*>(cp + j) = o;
+          }
+        }
+      } else {
+        if (p.act) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+        }
+        if (p.residual) {
+          const __nv_bfloat16* rp = p.residual + static_cast<long long>(row) * p.ldr + col0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < ncols) v[j] += __bfloat162float(rp[j]);
+        }
+        float* cp = reinterpret_cast<float*>(p.C) + static_cast<long long>(row) * p.ldc + col0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (j < ncols) {
+            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (p.accumulate) {
+              const float4 q = *reinterpret_cast<const float4*>(cp + j);
+              o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
+            }
+            *reinterpret_cast<float4*>(cp + j) = o;
+          }
+        }
+      }
+    }
+  }
 }
 
 template <int BN>
@@ -199,118 +319,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&tmem_full[acc_stage], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc_stage * BN;
-      const bool row_ok = row < p.M;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(t_row + c * 32, r);
-        tmem_ld_wait();
-        const int col0 = n0 + c * 32;
-        if (row_ok && col0 < p.N) {
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-          const int ncols = min(32, p.N - col0);  // N % 8 == 0 is enforced on the host
-          if (p.bias) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (j < ncols) {
-                const uint4 q = __ldg(reinterpret_cast<const uint4*>(p.bias + col0 + j));
-                const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                  const float2 f = unpack_bf16x2(w[t]);
-                  v[j + 2 * t] += f.x;
-                  v[j + 2 * t + 1] += f.y;
-                }
-              }
-            }
-          }
-          if (!p.out_fp32) {
-            // bf16 path mirrors the reference's rounding points: Linear output rounds to bf16,
-            // the activation rounds, the residual add rounds.
-            if (p.act) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = apply_act(bf16_round(v[j]), p.act);
-            }
-            if (col0 < p.rope_cols) {
-              // apply_rotary_emb on the bf16-rounded projection, fp32 math, one rounding at the
-              // store.  Heads are 128 wide, so pair index = (col % 128) / 2.
-              const int pos = p.rope_pos0 + row % p.rope_period;
-              const float2* tp = p.rope + static_cast<long long>(pos) * 64 + ((col0 & 127) >> 1);
-#pragma unroll
-              for (int j = 0; j < 32; j += 2) {
-                const float2 cs = __ldg(tp + (j >> 1));
-                const float a = bf16_round(v[j]), b = bf16_round(v[j + 1]);
-                v[j] = a * cs.x - b * cs.y;
-                v[j + 1] = a * cs.y + b * cs.x;
-              }
-            }
-            if (p.residual) {
-              const __nv_bfloat16* rp = p.residual + static_cast<long long>(row) * p.ldr + col0;
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                if (j < ncols) {
-                  const uint4 q = *reinterpret_cast<const uint4*>(rp + j);
-                  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                  for (int t = 0; t < 4; ++t) {
-                    const float2 f = unpack_bf16x2(w[t]);
-                    v[j + 2 * t] = bf16_round(v[j + 2 * t]) + f.x;
-                    v[j + 2 * t + 1] = bf16_round(v[j + 2 * t + 1]) + f.y;
-                  }
-                }
-              }
-            }
-            __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) +
-                                static_cast<long long>(row) * p.ldc + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (j < ncols) {
-                if (p.accumulate) {
-                  const uint4 q = *reinterpret_cast<const uint4*>(cp + j);
-                  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                  for (int t = 0; t < 4; ++t) {
-                    const float2 f = unpack_bf16x2(w[t]);
-                    v[j + 2 * t] += f.x;
-                    v[j + 2 * t + 1] += f.y;
-                  }
-                }
-                uint4 o;
-                o.x = pack_bf16x2(v[j], v[j + 1]);
-                o.y = pack_bf16x2(v[j + 2], v[j + 3]);
-                o.z = pack_bf16x2(v[j + 4], v[j + 5]);
-                o.w = pack_bf16x2(v[j + 6], v[j + 7]);
-                *reinterpret_cast<uint4*>(cp + j) = o;
-              }
-            }
-          } else {
-            if (p.act) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
-            }
-            if (p.residual) {
-              const __nv_bfloat16* rp = p.residual + static_cast<long long>(row) * p.ldr + col0;
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < ncols) v[j] += __bfloat162float(rp[j]);
-            }
-            float* cp = reinterpret_cast<float*>(p.C) + static_cast<long long>(row) * p.ldc + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (j < ncols) {
-                float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                if (p.accumulate) {
-                  const float4 q = *reinterpret_cast<const float4*>(cp + j);
-                  o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
-                }
-                *reinterpret_cast<float4*>(cp + j) = o;
-              }
-            }
-          }
-        }
-      }
+      epilogue_rows<BN>(p, t_row, row, n0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc_stage]);
@@ -323,6 +332,176 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x 256 tile.  Each
+// CTA stages its own 128 rows of A and its own 128 of the 256 B rows, so a k-block costs 32 KB of
+// shared memory per CTA instead of 48 KB -- six pipeline stages instead of four and half the B
+// traffic per SM.  The leader CTA's single thread issues tcgen05.mma.cta_group::2 (M = 256); the
+// accumulator rows of each CTA land in that CTA's own TMEM, so both CTAs run the same epilogue.
+// Barriers: full[] lives in the leader (both CTAs' TMA bytes are signalled there); empty[] and
+// tmem_full[] are arrived on in both CTAs by a multicast tcgen05.commit; tmem_empty[] lives in the
+// leader and counts the 8 epilogue warps of the pair.
+// ------------------------------------------------------------------------------------------------
+struct Gemm2Smem {
+  static constexpr int BN = 256;
+  static constexpr int BNH = 128;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BNH * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = 6;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const GemmParams p) {
+  using S = Gemm2Smem;
+  constexpr int BN = S::BN, BNH = S::BNH;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + S::STAGES;
+  uint64_t* tmem_full = bars + 2 * S::STAGES;
+  uint64_t* tmem_empty = bars + 2 * S::STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  const int m_blocks = (p.M + 2 * BM - 1) / (2 * BM);
+  const int n_blocks = (p.N + BN - 1) / BN;
+  const int k_blocks = (p.K + BK - 1) / BK;
+  const int num_tiles = m_blocks * n_blocks;
+  const int first_tile = blockIdx.x >> 1, tile_step = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < S::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 8);
+    }
+    fence_mbar_init();
+  }
+  cluster_sync_all();  // peer barriers are initialised before anyone signals them
+  if (warp == 2) {
+    tmem_alloc_2sm(tmem_slot, 2 * BN);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+        int mb, nb;
+        tile_coords(tile, m_blocks, n_blocks, p.group_m, mb, nb);
+        const int m0 = mb * (2 * BM) + rank * BM, n0 = nb * BN + rank * BNH;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * S::STAGE_BYTES;
+          uint8_t* sb = sa + S::A_BYTES;
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);
+          const uint32_t fb = mapa_u32(&full_bar[stage], 0);
+          const int k0 = kb * BK;
+          if (!p.a_mn) {
+            tma_load_2d_2sm(sa, &tmA, fb, k0, m0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c)
+              tma_load_2d_2sm(sa + c * (BK * 128), &tmA, fb, m0 + c * 64, k0);
+          }
+          if (!p.b_mn) {
+            tma_load_2d_2sm(sb, &tmB, fb, k0, n0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BNH / 64; ++c)
+              tma_load_2d_2sm(sb + c * (BK * 128), &tmB, fb, n0 + c * 64, k0);
+          }
+          if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA, single thread) =====================
+    if (leader && lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(2 * BM, BN, p.a_mn, p.b_mn);
+      const uint32_t a_lbo = p.a_mn ? BK * 128 : 16, b_lbo = p.b_mn ? BK * 128 : 16;
+      const uint32_t a_kstep = p.a_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+      const uint32_t b_kstep = p.b_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc_stage = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+        mbar_wait(&tmem_empty[acc_stage], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc_stage * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint32_t sb = sa + S::A_BYTES;
+          const uint64_t adesc = make_smem_desc_sw128(sa, a_lbo, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(sb, b_lbo, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            umma_bf16_2sm(d_tmem, adesc + k * a_kstep, bdesc + k * b_kstep, idesc,
+                          (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty_bar[stage], 3);  // frees this stage in both CTAs
+          if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(&tmem_full[acc_stage], 3);
+        if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs): own 128 rows of the 256-row tile =====================
+    const int ew = warp - 4;
+    int acc_stage = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+      int mb, nb;
+      tile_coords(tile, m_blocks, n_blocks, p.group_m, mb, nb);
+      const int row = mb * (2 * BM) + rank * BM + ew * 32 + lane;
+      const int n0 = nb * BN;
+      mbar_wait(&tmem_full[acc_stage], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc_stage * BN;
+      epilogue_rows<BN>(p, t_row, row, n0);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(&tmem_empty[acc_stage], 0));
+      if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // the peer may still be signalling this CTA's barriers / reading its smem
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 2 * BN);
   }
 }
 
@@ -355,6 +534,24 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   return check_launch("a3_gemm_bf16");
 }
 
+static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
+                        cudaStream_t stream) {
+  using S = Gemm2Smem;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         S::TOTAL);
+    if (e != cudaSuccess) return set_error(A3_ERR_CUDA, cudaGetErrorString(e));
+    configured = true;
+  }
+  const int m_blocks = (p.M + 2 * BM - 1) / (2 * BM), n_blocks = (p.N + S::BN - 1) / S::BN;
+  const int tiles = m_blocks * n_blocks;
+  const int pairs = num_sms() / 2;
+  const int grid = 2 * (tiles < pairs ? tiles : pairs);
+  gemm2_bf16_kernel<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(tmA, tmB, p);
+  return check_launch("a3_gemm_bf16(2cta)");
+}
+
 }  // namespace a3
 
 extern "C" int a3_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K,
@@ -380,11 +577,29 @@ extern "C" int a3_gemm_bf16(const void* A, const void* B, void* C, int M, int N,
   if (rope_table && rope_cols > 0 && ((rope_cols & 127) || out_fp32))
     return set_error(A3_ERR_ARG, "a3_gemm_bf16: rope needs rope_cols % 128 == 0 and bf16 output");
 
-  const int bn = (N <= 128 || (N % 256 != 0 && N % 128 == 0 && N < 2048)) ? 128 : 256;
+  // Kernel choice by wave quantisation: both kernels retire one 128 x 256 output block per SM per
+  // "tile time"; the CTA-pair kernel (256 x 256 per SM pair) runs ~8 % faster per tile (six smem
+  // stages, half the B traffic) but has half as many scheduling slots, so narrow / short problems
+  // (ViT at batch 8) stay on the single-CTA kernel when that needs fewer waves.
+  static const int force = getenv("A3_GEMM_KERNEL") ? atoi(getenv("A3_GEMM_KERNEL")) : 0;  // 1 / 2: testing
+  bool pair;
+  if (force) {
+    pair = force == 2;
+  } else if (N < 256 || M < 256) {
+    pair = false;
+  } else {
+    const long long sms = num_sms();
+    const long long tp = (long long)((M + 255) / 256) * ((N + 255) / 256);
+    const long long ts = (long long)((M + 127) / 128) * ((N + 255) / 256);
+    const double t_pair = (double)((tp + sms / 2 - 1) / (sms / 2)) / 1.08;
+    const double t_single = (double)((ts + sms - 1) / sms);
+    pair = t_pair < t_single;
+  }
+  const int bn = pair ? 128 : ((N <= 128 || (N % 256 != 0 && N % 128 == 0 && N < 2048)) ? 128 : 256);
   CUtensorMap tmA, tmB;
   int rc = encode_operand_map(&tmA, A, M, K, lda, a_mn_major, BM);
   if (rc != A3_OK) return rc;
-  rc = encode_operand_map(&tmB, B, N, K, ldb, b_mn_major, bn);
+  rc = encode_operand_map(&tmB, B, N, K, ldb, b_mn_major, bn);  // pair: each CTA loads 128 B rows
   if (rc != A3_OK) return rc;
 
   GemmParams p;
@@ -406,5 +621,6 @@ extern "C" int a3_gemm_bf16(const void* A, const void* B, void* C, int M, int N,
   p.alpha = alpha;
   p.group_m = 16;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (pair) return launch_gemm2(tmA, tmB, p, s);
   return bn == 128 ? launch_gemm<128>(tmA, tmB, p, s) : launch_gemm<256>(tmA, tmB, p, s);
 }
