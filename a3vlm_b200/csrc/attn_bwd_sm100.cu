@@ -8,9 +8,12 @@
 //     dV  += P^T  dO          A = P^T (K-major)  B = dO  (MN-major)   -> TMEM [256,384)
 //     dK  += dS^T Q           A = dS^T (K-major) B = Q   (MN-major)   -> TMEM [384,512)
 //     dQ^T = K^T dS           A = K  (MN-major)  B = dS^T (MN-major)  -> TMEM [128,192)
-// dQ^T has head-dim on lanes and queries on columns, so each warp's red.global.add.f32 on the fp32
-// dQ accumulator is a coalesced 128-byte line.  Q/dO tiles are double-buffered by TMA and the S/dP
-// MMAs of the next tile are issued behind the dV/dK/dQ MMAs of the current one.
+// dQ^T has head-dim on lanes and queries on columns; each thread transposes its row into a
+// [64 queries][128 dims] fp32 staging tile in shared memory (conflict-free: a warp writes 32
+// consecutive floats per query) and ONE bulk-tensor reduce-add (cp.reduce.async.bulk.tensor, fp32
+// add in L2) per tile accumulates it into the global dQ accumulator -- 8192 scalar atomics per tile
+// were the bottleneck of the first version (ncu r01: 779 us / layer).  Q/dO tiles are double-buffered
+// by TMA and the S/dP MMAs of the next tile are issued behind the dV/dK/dQ MMAs of the current one.
 //
 // Replaces the autograd backward of flash_attn_func / SDPA (reference
 // model/accessory/model/LLM/llama_ens5.py:142-167) on the fine-tune path
@@ -34,7 +37,8 @@ struct BwdSmem {
   static constexpr int OFF_DO = OFF_Q + 2 * QT_BYTES;  // [2]
   static constexpr int OFF_P = OFF_DO + 2 * QT_BYTES;
   static constexpr int OFF_DS = OFF_P + PT_BYTES;
-  static constexpr int OFF_STAT = OFF_DS + PT_BYTES;  // lse[2][64], delta[2][64] fp32
+  static constexpr int OFF_DQ = OFF_DS + PT_BYTES;    // fp32 [64 q][128 d] staging for the reduce
+  static constexpr int OFF_STAT = OFF_DQ + BW_Q * BW_HD * 4;  // lse[2][64], delta[2][64] fp32
   static constexpr int OFF_BAR = OFF_STAT + 4 * BW_Q * 4;
   static constexpr int TOTAL = OFF_BAR + 128;
 };
@@ -58,7 +62,7 @@ __device__ __forceinline__ void red_add_f32(float* addr, float v) {
 __global__ void __launch_bounds__(128)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
-                const BwdParams p) {
+                const __grid_constant__ CUtensorMap tmDQ, const BwdParams p) {
   using S = BwdSmem;
   extern __shared__ __align__(1024) uint8_t smem[];
   if (smem_u32(smem) & 1023u) __trap();
@@ -83,6 +87,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     prefetch_tmap(&tmK);
     prefetch_tmap(&tmV);
     prefetch_tmap(&tmDO);
+    prefetch_tmap(&tmDQ);
     mbar_init(kv_full, 1);
     mbar_init(&q_full[0], 1);
     mbar_init(&q_full[1], 1);
@@ -234,6 +239,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         *reinterpret_cast<uint4*>(ds_row + ((unit ^ sw) << 4)) = make_uint4(dw[0], dw[1], dw[2], dw[3]);
       }
     }
+    if (tid == 0) bulk_wait_group_read0();  // the previous tile's reduce has drained the dQ staging
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -255,23 +261,26 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     if (tid == 0 && it + 2 < n_iter) load_q(i + 2);  // stage st is free: its MMAs have retired
     __syncwarp();
     {
-      float* dq_col = p.dq_acc + (static_cast<long long>(b) * T + qbase) * (p.H * BW_HD) + h * BW_HD +
-                      warp * 32 + lane;
+      float* stage = reinterpret_cast<float*>(smem + S::OFF_DQ) + warp * 32 + lane;  // column d
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t dq[32];
         tmem_ld_32x32(t_lane + C_DQ + half * 32, dq);
         tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const int qc = half * 32 + c;
-          if (qbase + qc < T) red_add_f32(dq_col + static_cast<long long>(qc) * (p.H * BW_HD), __uint_as_float(dq[c]));
-        }
+        for (int c = 0; c < 32; ++c) stage[(half * 32 + c) * BW_HD] = __uint_as_float(dq[c]);
       }
     }
     // The next iteration's issue_grads overwrites dQ^T; order the reads above before it.
     tc_fence_before();
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tma_reduce_add_3d(&tmDQ, smem + S::OFF_DQ, h * BW_HD, qbase, b);  // rows >= T are clipped
+      bulk_commit_group();
+    }
   }
+  if (tid == 0) bulk_wait_group0();
 
   // ---- epilogue: dV, dK -> bf16
   if (n_iter > 0) {
@@ -385,7 +394,7 @@ extern "C" int a3_attn_bwd(const void* q, const void* k, const void* v, const vo
   cudaError_t e = cudaMemsetAsync(dq_acc, 0, (size_t)B * T * width * sizeof(float), s);
   if (e != cudaSuccess) return set_error(A3_ERR_CUDA, cudaGetErrorString(e));
 
-  CUtensorMap tmQ, tmK, tmV, tmDO;
+  CUtensorMap tmQ, tmK, tmV, tmDO, tmDQ;
   int rc = make_tmap_3d_bf16(&tmQ, q, (uint64_t)width, (uint64_t)T, (uint64_t)B, (uint64_t)ldqkv * 2,
                              (uint64_t)T * ldqkv * 2, 64, BW_Q, 1);
   if (rc) return rc;
@@ -397,6 +406,10 @@ extern "C" int a3_attn_bwd(const void* q, const void* k, const void* v, const vo
   if (rc) return rc;
   rc = make_tmap_3d_bf16(&tmDO, dout, (uint64_t)width, (uint64_t)T, (uint64_t)B, (uint64_t)ldo * 2,
                          (uint64_t)T * ldo * 2, 64, BW_Q, 1);
+  if (rc) return rc;
+
+  rc = make_tmap_3d_f32_linear(&tmDQ, dq_acc, (uint64_t)width, (uint64_t)T, (uint64_t)B,
+                               (uint64_t)width * 4, (uint64_t)T * width * 4, BW_HD, BW_Q, 1);
   if (rc) return rc;
 
   static bool configured = false;
@@ -417,7 +430,7 @@ extern "C" int a3_attn_bwd(const void* q, const void* k, const void* v, const vo
   p.scale = scale;
   p.causal = causal ? 1 : 0;
   dim3 grid((T + BW_KEYS - 1) / BW_KEYS, H, B);
-  attn_bwd_kernel<<<grid, 128, BwdSmem::TOTAL, s>>>(tmQ, tmK, tmV, tmDO, p);
+  attn_bwd_kernel<<<grid, 128, BwdSmem::TOTAL, s>>>(tmQ, tmK, tmV, tmDO, tmDQ, p);
   rc = check_launch("a3_attn_bwd");
   if (rc) return rc;
   const long long rows = (long long)B * T;

@@ -59,13 +59,15 @@ static EncodeTiledFn encode_fn() {
 }
 
 static int encode(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims,
-                  const cuuint64_t* strides, const cuuint32_t* box) {
+                  const cuuint64_t* strides, const cuuint32_t* box,
+                  CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                  CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return set_error(A3_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr),
+  CUresult r = fn(tm, dtype, (cuuint32_t)rank, const_cast<void*>(ptr),
                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[256];
@@ -95,6 +97,16 @@ int make_tmap_3d_bf16(CUtensorMap* tm, const void* ptr, uint64_t dim0, uint64_t 
   cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
   cuuint32_t box[3] = {box0, box1, box2};
   return encode(tm, ptr, 3, dims, strides, box);
+}
+
+int make_tmap_3d_f32_linear(CUtensorMap* tm, const void* ptr, uint64_t dim0, uint64_t dim1,
+                            uint64_t dim2, uint64_t stride1_bytes, uint64_t stride2_bytes,
+                            uint32_t box0, uint32_t box1, uint32_t box2) {
+  cuuint64_t dims[3] = {dim0, dim1, dim2};
+  cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+  cuuint32_t box[3] = {box0, box1, box2};
+  return encode(tm, ptr, 3, dims, strides, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 
 }  // namespace a3

@@ -21,4 +21,9 @@ int make_tmap_3d_bf16(CUtensorMap* tm, const void* ptr, uint64_t dim0, uint64_t 
                       uint64_t dim2, uint64_t stride1_bytes, uint64_t stride2_bytes,
                       uint32_t box0, uint32_t box1, uint32_t box2);
 
+// 3-D fp32 tensor map without swizzle (row-major smem box), used for TMA reduce-add stores.
+int make_tmap_3d_f32_linear(CUtensorMap* tm, const void* ptr, uint64_t dim0, uint64_t dim1,
+                            uint64_t dim2, uint64_t stride1_bytes, uint64_t stride2_bytes,
+                            uint32_t box0, uint32_t box1, uint32_t box2);
+
 }  // namespace a3

@@ -90,17 +90,18 @@ rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
 // y = n * w, n = bf16(x * rstd).  dn = dy * w; dx = rstd * (dn - xhat * mean(dn * xhat));
 // dw += dy * n.  Each CTA walks rows blockIdx.x, +gridDim.x, ... and keeps its dw slice in
 // registers; the [nparts][D] partials are summed by colsum_partials.
-__global__ void __launch_bounds__(ROW_THREADS)
+template <int NCH>
+__global__ void __launch_bounds__(ROW_THREADS, NCH <= 2 ? 2 : 1)
 rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                    const __nv_bfloat16* __restrict__ w, const float* __restrict__ rstd_in,
                    __nv_bfloat16* __restrict__ dx, float* __restrict__ dw_partial, int rows, int D,
                    int add_to_dx) {
   __shared__ float red[32];
   const int nchunks = D >> 3;
-  float dw[MAX_CHUNKS][8];
-  float wv[MAX_CHUNKS][8];
+  float dw[NCH][8];
+  float wv[NCH][8];
 #pragma unroll
-  for (int i = 0; i < MAX_CHUNKS; ++i) {
+  for (int i = 0; i < NCH; ++i) {
     const int c = threadIdx.x + i * ROW_THREADS;
 #pragma unroll
     for (int j = 0; j < 8; ++j) dw[i][j] = 0.f;
@@ -110,10 +111,10 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __
     const float rstd = rstd_in[row];
     const __nv_bfloat16* xr = x + (long long)row * D;
     const __nv_bfloat16* gr = dy + (long long)row * D;
-    float xh[MAX_CHUNKS][8], dn[MAX_CHUNKS][8];
+    float xh[NCH][8], dn[NCH][8];
     float dot = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAX_CHUNKS; ++i) {
+    for (int i = 0; i < NCH; ++i) {
       const int c = threadIdx.x + i * ROW_THREADS;
       if (c < nchunks) {
         float g[8];
@@ -131,7 +132,7 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __
     dot = block_sum(dot, red) / (float)D;
     __nv_bfloat16* dr = dx + (long long)row * D;
 #pragma unroll
-    for (int i = 0; i < MAX_CHUNKS; ++i) {
+    for (int i = 0; i < NCH; ++i) {
       const int c = threadIdx.x + i * ROW_THREADS;
       if (c < nchunks) {
         float o[8];
@@ -149,7 +150,7 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __
   }
   float* out = dw_partial + (long long)blockIdx.x * D;
 #pragma unroll
-  for (int i = 0; i < MAX_CHUNKS; ++i) {
+  for (int i = 0; i < NCH; ++i) {
     const int c = threadIdx.x + i * ROW_THREADS;
     if (c < nchunks) {
       *reinterpret_cast<float4*>(out + c * 8) = make_float4(dw[i][0], dw[i][1], dw[i][2], dw[i][3]);
@@ -426,8 +427,16 @@ extern "C" int a3_rmsnorm_bwd(const void* dy, const void* x, const void* w, cons
                               int add_to_dx, void* stream) {
   if (check_rowshape("a3_rmsnorm_bwd: D must be a multiple of 8 and <= 8192", rows, D)) return A3_ERR_ARG;
   if (nparts <= 0) return set_error(A3_ERR_ARG, "a3_rmsnorm_bwd: nparts <= 0");
-  rmsnorm_bwd_kernel<<<nparts, ROW_THREADS, 0, ST(stream)>>>(BF(dy), BF(x), BF(w), rstd, BFM(dx),
-                                                             dw_partial, rows, D, add_to_dx);
+  const int nch = (D / 8 + ROW_THREADS - 1) / ROW_THREADS;
+  if (nch <= 1)
+    rmsnorm_bwd_kernel<1><<<nparts, ROW_THREADS, 0, ST(stream)>>>(BF(dy), BF(x), BF(w), rstd, BFM(dx),
+                                                                  dw_partial, rows, D, add_to_dx);
+  else if (nch == 2)
+    rmsnorm_bwd_kernel<2><<<nparts, ROW_THREADS, 0, ST(stream)>>>(BF(dy), BF(x), BF(w), rstd, BFM(dx),
+                                                                  dw_partial, rows, D, add_to_dx);
+  else
+    rmsnorm_bwd_kernel<4><<<nparts, ROW_THREADS, 0, ST(stream)>>>(BF(dy), BF(x), BF(w), rstd, BFM(dx),
+                                                                  dw_partial, rows, D, add_to_dx);
   return check_launch("a3_rmsnorm_bwd");
 }
 

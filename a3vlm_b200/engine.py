@@ -69,7 +69,9 @@ class Workspace:
         self.h = [e(M, D) for _ in range(keep)]
         self.hn = [e(M, D) for _ in range(keep)]
         self.gu = [e(M, 2 * F) for _ in range(keep)]
-        self.y = e(M, F)
+        # swiglu output: kept per layer when training (the w2 wgrad needs it; recomputing costs a
+        # 441 MB pass per layer), one scratch buffer otherwise
+        self.y = [e(M, F) for _ in range(keep)]
         self.lse = [e(B, a.n_heads, L, dt=torch.float32) for _ in range(keep)]
         self.rstd1 = [e(M, dt=torch.float32) for _ in range(keep)]
         self.rstd2 = [e(M, dt=torch.float32) for _ in range(keep)]
@@ -90,7 +92,7 @@ class Workspace:
             self.dqkv = e(M, 3 * D)
             self.dq_acc = e(M, D, dt=torch.float32)
             self.delta = e(B, a.n_heads, L, dt=torch.float32)
-            self.nparts = 2 * eng.n_sms
+            self.nparts = 4 * eng.n_sms
             self.part = e(max(B, 1) * self.nparts, D, dt=torch.float32)
             self.part2 = e(self.nparts, D, dt=torch.float32)
             self.tag_grad = e(2, D, dt=torch.float32)
@@ -337,7 +339,7 @@ class Engine:
         ops.embed_splice(examples, w["tok_embeddings.weight"], img, w["start_img"] if W else None,
                          w["end_img"] if W else None, ws.x[0], B, T, self.vis.tokens if W else 0, D)
         for i in range(a.n_layers):
-            self._layer_fwd(i, ws.x[i], ws.xn[i], ws.qkv[i], ws.o[i], ws.h[i], ws.hn[i], ws.gu[i], ws.y,
+            self._layer_fwd(i, ws.x[i], ws.xn[i], ws.qkv[i], ws.o[i], ws.h[i], ws.hn[i], ws.gu[i], ws.y[i],
                             ws.x[i + 1], ws.lse[i], ws.rstd1[i], ws.rstd2[i], B, L)
         xf = ws.x[a.n_layers].view(B, L, D)
         for b in range(B):  # final norm on the text rows only (llama_ens5.py:485-486)
@@ -378,8 +380,7 @@ class Engine:
         d, t = ws.d, ws.dtmp
         for i in reversed(range(NL)):
             p = f"layers.{i}."
-            ops.swiglu_fwd(ws.gu[i], ws.y)                                   # recompute y
-            wg(d, ws.y, g[p + "feed_forward.w2.weight"])
+            wg(d, ws.y[i], g[p + "feed_forward.w2.weight"])
             dg(d, w[p + "feed_forward.w2.weight"], ws.dy)
             ops.swiglu_bwd(ws.gu[i], ws.dy, ws.dgu)
             wg(ws.dgu, ws.hn[i], g[p + "w13"])
@@ -525,7 +526,7 @@ class Engine:
                          w["end_img"] if W else None, ws.x[0], B, l, self.vis.tokens if W else 0, D)
         xa, xb = ws.x[0], ws.x[1]
         for i in range(a.n_layers):
-            self._layer_fwd(i, xa, ws.xn[0], ws.qkv[0], ws.o[0], ws.h[0], ws.hn[0], ws.gu[0], ws.y, xb,
+            self._layer_fwd(i, xa, ws.xn[0], ws.qkv[0], ws.o[0], ws.h[0], ws.hn[0], ws.gu[0], ws.y[0], xb,
                             None, None, None, B, L, pos0=start_pos, kv=True)
             xa, xb = xb, xa
         last = xa.view(B, L, D)[:, L - 1]  # (B, D) strided view: last position of every sample
