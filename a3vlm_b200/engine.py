@@ -32,17 +32,87 @@ def _no_decay(name: str) -> bool:
     return name.endswith(".bias") or name.endswith("norm.weight")
 
 
+def ffn_hidden_dim(dim: int, multiple_of: int, ffn_dim_multiplier) -> int:
+    """LLM/llama_ens5.py:196-200 with hidden_dim = 4 * dim (:228)."""
+    hidden = int(2 * (4 * dim) / 3)
+    if ffn_dim_multiplier is not None:
+        hidden = int(ffn_dim_multiplier * hidden)
+    return multiple_of * ((hidden + multiple_of - 1) // multiple_of)
+
+
+def build_layout(args, vis):
+    """Pure function (no device): the ordered (name, shape) lists of the flat buffers.
+    Returns (decay, nodecay, frozen, kpad).  Trainable order = decay + nodecay:
+      tok_embeddings | per layer: wqkv, wo, w13, w2 | output | visual_proj.{0,1}.weight, start/end_img ||
+      per layer: attention_norm, ffn_norm | norm | visual_proj.{0,1}.bias
+    wq|wk|wv and w1|w3 are adjacent rows of one matrix, so the reference-named parameters are views."""
+    D, V = args.dim, args.vocab_size
+    F = ffn_hidden_dim(D, args.multiple_of, args.ffn_dim_multiplier)
+    decay: List[Tuple[str, Tuple[int, ...]]] = [("tok_embeddings.weight", (V, D))]
+    nodecay: List[Tuple[str, Tuple[int, ...]]] = []
+    for i in range(args.n_layers):
+        p = f"layers.{i}."
+        decay += [(p + "wqkv", (3 * D, D)), (p + "attention.wo.weight", (D, D)),
+                  (p + "w13", (2 * F, D)), (p + "feed_forward.w2.weight", (D, F))]
+        nodecay += [(p + "attention_norm.weight", (D,)), (p + "ffn_norm.weight", (D,))]
+    decay.append(("output.weight", (V, D)))
+    nodecay.append(("norm.weight", (D,)))
+    frozen: List[Tuple[str, Tuple[int, ...]]] = []
+    kpad = 0
+    if vis is not None:
+        v, c = vis, "clip.visual."
+        Wv = v.width
+        kpad = (3 * v.patch * v.patch + 7) // 8 * 8
+        # visual_proj.1 is a LayerNorm, but its weight's NAME does not end in "norm.weight", so the
+        # reference's add_weight_decay (M/util/misc.py:591) puts it in the decay group -- kept faithfully
+        decay += [("visual_proj.0.weight", (D, Wv)), ("visual_proj.1.weight", (D,)), ("start_img", (1, 1, D)),
+                  ("end_img", (1, 1, D))]
+        nodecay += [("visual_proj.0.bias", (D,)), ("visual_proj.1.bias", (D,))]
+        frozen += [(c + "conv1.weight", (Wv, 3, v.patch, v.patch)), (c + "conv1_padded", (Wv, kpad)),
+                   (c + "class_embedding", (Wv,)), (c + "positional_embedding", (v.tokens, Wv)),
+                   (c + "ln_pre.weight", (Wv,)), (c + "ln_pre.bias", (Wv,)),
+                   (c + "ln_post.weight", (Wv,)), (c + "ln_post.bias", (Wv,))]
+        for i in range(v.layers):
+            r = f"{c}transformer.resblocks.{i}."
+            frozen += [(r + "ln_1.weight", (Wv,)), (r + "ln_1.bias", (Wv,)),
+                       (r + "attn.in_proj_weight", (3 * Wv, Wv)), (r + "attn.in_proj_bias", (3 * Wv,)),
+                       (r + "attn.out_proj.weight", (Wv, Wv)), (r + "attn.out_proj.bias", (Wv,)),
+                       (r + "ln_2.weight", (Wv,)), (r + "ln_2.bias", (Wv,)),
+                       (r + "mlp.c_fc.weight", (v.mlp, Wv)), (r + "mlp.c_fc.bias", (v.mlp,)),
+                       (r + "mlp.c_proj.weight", (Wv, v.mlp)), (r + "mlp.c_proj.bias", (Wv,))]
+    return decay, nodecay, frozen, kpad
+
+
+def flat_offsets(layout, align: int = 64):
+    """name -> (offset, numel, shape) with every tensor starting on a 128-byte boundary; total."""
+    offsets: Dict[str, Tuple[int, int, Tuple[int, ...]]] = {}
+    off = 0
+    for name, shape in layout:
+        n = int(math.prod(shape))
+        offsets[name] = (off, n, tuple(shape))
+        off += (n + align - 1) // align * align
+    return offsets, off
+
+
+def bucket_plan(offsets, numel: int, n_layers: int):
+    """Flat element ranges in the order the backward completes them (the all-reduce buckets):
+    LM head, decoder layers last to first, embedding, then everything after the LM head
+    (projector, tags, all norm weights).  Together they tile [0, numel) exactly once."""
+    rng = lambda n: (offsets[n][0], offsets[n][0] + offsets[n][1])
+    plan = [rng("output.weight")]
+    for i in reversed(range(n_layers)):
+        plan.append((rng(f"layers.{i}.wqkv")[0], rng(f"layers.{i}.feed_forward.w2.weight")[1]))
+    plan.append((0, rng("tok_embeddings.weight")[1]))
+    plan.append((rng("output.weight")[1], numel))
+    return plan
+
+
 class FlatParams:
     """Flat bf16 storage for a set of named parameters.  `layout` is an ordered list of
     (name, shape); views[name] aliases the flat buffer."""
 
     def __init__(self, layout: List[Tuple[str, Tuple[int, ...]]], device, align: int = 64):
-        self.offsets: Dict[str, Tuple[int, int, Tuple[int, ...]]] = {}
-        off = 0
-        for name, shape in layout:
-            n = int(math.prod(shape))
-            self.offsets[name] = (off, n, tuple(shape))
-            off += (n + align - 1) // align * align
+        self.offsets, off = flat_offsets(layout, align)
         self.numel = off
         self.flat = torch.zeros(max(off, align), device=device, dtype=bf16)
         self.views = {n: self.flat[o:o + k].view(s) for n, (o, k, s) in self.offsets.items()}
@@ -118,10 +188,7 @@ class Engine:
         self.head_dim = a.dim // a.n_heads
         if self.head_dim != 128:
             raise NotImplementedError("decoder head_dim must be 128 (7B / 13B)")
-        hidden = int(2 * (4 * a.dim) / 3)  # LLM/llama_ens5.py:196-200
-        if a.ffn_dim_multiplier is not None:
-            hidden = int(a.ffn_dim_multiplier * hidden)
-        self.ffn_dim = a.multiple_of * ((hidden + a.multiple_of - 1) // a.multiple_of)
+        self.ffn_dim = ffn_hidden_dim(a.dim, a.multiple_of, a.ffn_dim_multiplier)
         self.n_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         self.rope = ops.rope_table(self.head_dim, a.max_seq_len * 2, a.rope_theta, device=self.device)
         self.image_words = (vis.tokens + 2) if vis is not None else 0
@@ -140,41 +207,13 @@ class Engine:
 
     # ------------------------------------------------------------------------------------ layouts
     def _build_layouts(self):
-        a, D, F, V = self.args, self.args.dim, self.ffn_dim, self.args.vocab_size
-        decay: List[Tuple[str, Tuple[int, ...]]] = [("tok_embeddings.weight", (V, D))]
-        nodecay: List[Tuple[str, Tuple[int, ...]]] = []
-        for i in range(a.n_layers):
-            p = f"layers.{i}."
-            decay += [(p + "wqkv", (3 * D, D)), (p + "attention.wo.weight", (D, D)),
-                      (p + "w13", (2 * F, D)), (p + "feed_forward.w2.weight", (D, F))]
-            nodecay += [(p + "attention_norm.weight", (D,)), (p + "ffn_norm.weight", (D,))]
-        decay.append(("output.weight", (V, D)))
-        nodecay.append(("norm.weight", (D,)))
-        frozen: List[Tuple[str, Tuple[int, ...]]] = []
-        if self.vis is not None:
-            v, c = self.vis, "clip.visual."
-            Wv = v.width
-            self.kpad = (3 * v.patch * v.patch + 7) // 8 * 8
-            decay += [("visual_proj.0.weight", (D, Wv)), ("start_img", (1, 1, D)), ("end_img", (1, 1, D))]
-            nodecay += [("visual_proj.0.bias", (D,)), ("visual_proj.1.weight", (D,)), ("visual_proj.1.bias", (D,))]
-            frozen += [(c + "conv1.weight", (Wv, 3, v.patch, v.patch)), (c + "conv1_padded", (Wv, self.kpad)),
-                       (c + "class_embedding", (Wv,)), (c + "positional_embedding", (v.tokens, Wv)),
-                       (c + "ln_pre.weight", (Wv,)), (c + "ln_pre.bias", (Wv,)),
-                       (c + "ln_post.weight", (Wv,)), (c + "ln_post.bias", (Wv,))]
-            for i in range(v.layers):
-                r = f"{c}transformer.resblocks.{i}."
-                frozen += [(r + "ln_1.weight", (Wv,)), (r + "ln_1.bias", (Wv,)),
-                           (r + "attn.in_proj_weight", (3 * Wv, Wv)), (r + "attn.in_proj_bias", (3 * Wv,)),
-                           (r + "attn.out_proj.weight", (Wv, Wv)), (r + "attn.out_proj.bias", (Wv,)),
-                           (r + "ln_2.weight", (Wv,)), (r + "ln_2.bias", (Wv,)),
-                           (r + "mlp.c_fc.weight", (v.mlp, Wv)), (r + "mlp.c_fc.bias", (v.mlp,)),
-                           (r + "mlp.c_proj.weight", (Wv, v.mlp)), (r + "mlp.c_proj.bias", (Wv,))]
-        self.n_decay_names = len(decay)
+        decay, nodecay, frozen, self.kpad = build_layout(self.args, self.vis)
         self.w = FlatParams(decay + nodecay, self.device)
         self.decay_numel = self.w.offsets[nodecay[0][0]][0]  # no-decay region starts here
         self.fz = FlatParams(frozen, self.device) if frozen else None
         self.g: Optional[FlatParams] = None  # gradients: allocated on first training use
         self._layout = decay + nodecay
+        self._buckets = bucket_plan(self.w.offsets, self.w.numel, self.args.n_layers)
 
     def param_views(self) -> Dict[str, torch.Tensor]:
         """Reference-named views (SURVEY 8b state-dict names) into the flat buffers."""
@@ -369,8 +408,9 @@ class Engine:
         # LM head + final norm
         ops.gemm(dlogits, ws.fn, g["output.weight"], a_mn=True, b_mn=True, accumulate=acc, alpha=scale)
         ops.gemm(dlogits, w["output.weight"], ws.dfn, b_mn=True, alpha=scale)
+        bk = iter(self._buckets)
         if on_bucket:
-            on_bucket(*self._range("output.weight"))
+            on_bucket(*next(bk))
         ws.d.zero_()
         xf, dv = ws.x[NL].view(B, L, D), ws.d.view(B, L, D)
         for b in range(B):
@@ -399,9 +439,7 @@ class Engine:
             ops.rmsnorm_bwd(t, ws.x[i], w[p + "attention_norm.weight"], ws.rstd1[i], d, ws.part2, add_to_dx=True)
             ops.colsum_partials(ws.part2, g[p + "attention_norm.weight"], accumulate=acc)
             if on_bucket:
-                lo, _ = self._range(p + "wqkv")
-                _, hi = self._range(p + "feed_forward.w2.weight")
-                on_bucket(lo, hi)
+                on_bucket(*next(bk))
         # embedding scatter-add, tags, projector
         if not acc:
             g["tok_embeddings.weight"].zero_()
@@ -423,8 +461,8 @@ class Engine:
                       "visual_proj.1.weight", "visual_proj.1.bias"):
                 g[n].zero_()
         if on_bucket:
-            on_bucket(0, self._range("tok_embeddings.weight")[1])
-            on_bucket(self._range("output.weight")[1], self.g.numel)
+            for lo_hi in bk:
+                on_bucket(*lo_hi)
 
     def _range(self, name: str) -> Tuple[int, int]:
         o, n, _ = self.w.offsets[name]
@@ -456,29 +494,14 @@ class Engine:
 
     # ------------------------------------------------------------------------------------ data-parallel
     def allreduce_hook(self, group=None):
-        """Returns (on_bucket, finish): on_bucket enqueues an NCCL all-reduce (sum) of a finished flat
-        gradient range on a side stream behind an event, so it overlaps the rest of the backward;
-        finish() makes the compute stream wait for all of them.  The 1/world factor is folded into
-        grad_scale by the caller."""
-        import torch.distributed as dist
+        """(on_bucket, finish) for the backward: see dp.BucketAllReduce."""
+        from .dp import BucketAllReduce
 
+        self._ensure_grads()
         if self.comm_stream is None:
             self.comm_stream = torch.cuda.Stream(device=self.device)
-        cs = self.comm_stream
-
-        def on_bucket(lo, hi):
-            if hi <= lo:
-                return
-            ev = torch.cuda.Event()
-            ev.record()
-            cs.wait_event(ev)
-            with torch.cuda.stream(cs):
-                dist.all_reduce(self.g.flat[lo:hi], op=dist.ReduceOp.SUM, group=group)
-
-        def finish():
-            torch.cuda.current_stream().wait_stream(cs)
-
-        return on_bucket, finish
+        r = BucketAllReduce(self.g.flat, group, self.comm_stream)
+        return r.on_bucket, r.finish
 
     # ------------------------------------------------------------------------------------ inference
     def allocate_kv_cache(self, B: int) -> None:

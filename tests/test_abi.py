@@ -1,0 +1,65 @@
+"""CPU checks of the drop-in boundary: the C-ABI library loads and exports every symbol that
+include/a3vlm_b200.h declares; no compute call is made (no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from a3vlm_b200 import _lib
+
+    assert os.path.exists(_lib.LIB_PATH), "build with python -c 'import __graft_entry__ as g; g.build()'"
+    lib = _lib.load(strict=True)
+    assert not _lib.MISSING
+    text = open(_lib.HEADER).read()
+    declared = set(re.findall(r"\b(a3_\w+)\s*\(", re.sub(r"/\*.*?\*/", "", text, flags=re.S)))
+    assert declared == set(_lib.PROTOS), declared ^ set(_lib.PROTOS)
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.a3_version() >= 100
+    assert isinstance(lib.a3_launch_count(), int)
+
+
+def test_signatures_have_no_torch_types():
+    from a3vlm_b200 import _lib
+
+    allowed = {"int", "float", "long long", "void", "const void*", "void*", "const float*", "float*",
+               "const long long*", "long long*", "const int*", "int*", "const char*"}
+    for name, (ret, args) in _lib.PROTOS.items():
+        assert ret.replace(" ", "") in {a.replace(" ", "") for a in allowed}, (name, ret)
+        for t, _ in args:
+            assert t.replace(" ", "") in {a.replace(" ", "") for a in allowed}, (name, t)
+
+
+def test_ops_refuse_cpu_tensors_and_model_refuses_cpu_only_hosts():
+    from a3vlm_b200 import ops
+    from a3vlm_b200._lib import A3Error
+
+    with pytest.raises(A3Error):
+        ops.rmsnorm_fwd(torch.zeros(2, 8, dtype=torch.bfloat16), torch.ones(8, dtype=torch.bfloat16), 1e-5)
+    if not torch.cuda.is_available():
+        from a3vlm_b200.model import MetaModel
+
+        with pytest.raises(A3Error):
+            MetaModel("llama_b200", dict(dim=256, n_layers=1, n_heads=2, vocab_size=64, multiple_of=64), None)
+
+
+def test_sass_is_blackwell_native():
+    """The shipped binary carries tcgen05 MMAs (UTC*MMA), TMEM loads (LDTM) and TMA (UTMALDG) and no
+    legacy HMMA tensor path -- checked from the cubin, no GPU needed."""
+    import shutil
+    import subprocess
+
+    from a3vlm_b200 import _lib
+
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass and "LDTM" in sass and "UTMALDG" in sass and "UTMAREDG" in sass
+    assert " HMMA" not in sass
