@@ -1,7 +1,9 @@
 // FlashAttention-style backward on tcgen05 / TMEM, fed by TMA (sm_100a), head_dim 128.
 //
-// One CTA = 128 keys of one (batch, head); thread t owns key row t (TMEM lane t).  For each tile of
-// 64 queries (all five contractions on tcgen05, transposes are free through the UMMA majorness):
+// One CTA = 128 keys of one (batch, head), 8 warps: threads t and t+128 share key row t (TMEM lane
+// t) and split the 64 query columns of a tile between them (two warps per SM sub-partition hide the
+// MUFU / TMEM / smem latencies of the element-wise phase -- ncu r01: it, not the MMAs, bounds the
+// kernel).  For each tile of 64 queries (all five contractions on tcgen05, transposes are free through the UMMA majorness):
 //     S^T  = K Q^T            A = K  (K-major)   B = Q   (K-major)    -> TMEM [  0, 64)
 //     dP^T = V dO^T           A = V  (K-major)   B = dO  (K-major)    -> TMEM [ 64,128)
 //     P^T = exp2(S^T c - lse), dS^T = P^T (dP^T - delta) scale        -> smem (bf16, SW128)
@@ -59,7 +61,7 @@ __device__ __forceinline__ void red_add_f32(float* addr, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                 const __grid_constant__ CUtensorMap tmDQ, const BwdParams p) {
@@ -75,7 +77,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   float* s_lse = reinterpret_cast<float*>(smem + S::OFF_STAT);   // [2][64]
   float* s_delta = s_lse + 2 * BW_Q;                             // [2][64]
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  const int warp = (threadIdx.x >> 5) & 3, lane = threadIdx.x & 31, tid = threadIdx.x;
+  const int half = threadIdx.x >> 7;  // which 32 of the 64 query columns this thread handles
   const int key0 = blockIdx.x * BW_KEYS, h = blockIdx.y, b = blockIdx.z;
   const int T = p.T;
   const int n_q_tiles = (T + BW_Q - 1) / BW_Q;
@@ -95,7 +98,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_init(grad_bar, 1);
     fence_mbar_init();
   }
-  if (warp == 0) {
+  if (tid < 32) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -117,8 +120,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   auto load_stats = [&](int i) {  // lse / delta of query tile i -> smem stage i&1
     const int st = i & 1;
     const int qi = i * BW_Q + (tid & 63);
-    if (tid < 64) s_lse[st * BW_Q + tid] = qi < T ? p.lse[stat_base + qi] : INFINITY;
-    else s_delta[st * BW_Q + (tid - 64)] = qi < T ? p.delta[stat_base + qi] : 0.f;
+    // lse is stored pre-multiplied by log2(e): P = exp2(S * scale * log2e - lse * log2e)
+    if (tid < 64) s_lse[st * BW_Q + tid] = qi < T ? p.lse[stat_base + qi] * 1.4426950408889634f : INFINITY;
+    else if (tid < 128) s_delta[st * BW_Q + (tid - 64)] = qi < T ? p.delta[stat_base + qi] : 0.f;
   };
   auto load_q = [&](int i) {  // TMA: Q_i and dO_i -> stage i&1
     const int st = i & 1;
@@ -195,7 +199,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int key = key0 + warp * 32 + lane;
   const bool key_ok = key < T;
   const float c2 = p.scale * 1.4426950408889634f;
-  const float LOG2E = 1.4426950408889634f;
   uint8_t* p_row = smem + S::OFF_P + (warp * 32 + lane) * 128;
   uint8_t* ds_row = smem + S::OFF_DS + (warp * 32 + lane) * 128;
   const int sw = lane & 7;
@@ -208,35 +211,35 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_wait(sdp_bar, it & 1);
     tc_fence_after();
     const int qbase = i * BW_Q;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
+    {
       uint32_t s[32], dp[32];
       tmem_ld_32x32(t_lane + C_S + half * 32, s);
       tmem_ld_32x32(t_lane + C_DP + half * 32, dp);
+      const float4* l4 = reinterpret_cast<const float4*>(s_lse + st * BW_Q + half * 32);
+      const float4* d4 = reinterpret_cast<const float4*>(s_delta + st * BW_Q + half * 32);
       tmem_ld_wait();
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        uint32_t pw[4], dw[4];
+        const float4 la = l4[2 * u], lb = l4[2 * u + 1], da = d4[2 * u], db = d4[2 * u + 1];
+        const float l2[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
+        const float dl[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+        float pv[8], dv[8];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          float pv[2], dv[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int idx = u * 8 + t * 2 + e;
-            const int qc = half * 32 + idx;
-            const int qi = qbase + qc;
-            const bool vis = key_ok && (!p.causal || key <= qi);
-            const float l2 = s_lse[st * BW_Q + qc] * LOG2E;
-            const float pr = vis ? exp2f(__uint_as_float(s[idx]) * c2 - l2) : 0.f;
-            pv[e] = pr;
-            dv[e] = pr * (__uint_as_float(dp[idx]) - s_delta[st * BW_Q + qc]) * p.scale;
-          }
-          pw[t] = pack_bf16x2(pv[0], pv[1]);
-          dw[t] = pack_bf16x2(dv[0], dv[1]);
+        for (int e = 0; e < 8; ++e) {
+          const int idx = u * 8 + e;
+          const int qi = qbase + half * 32 + idx;
+          const bool vis = key_ok && (!p.causal || key <= qi);
+          const float pr = vis ? exp2f(__uint_as_float(s[idx]) * c2 - l2[e]) : 0.f;
+          pv[e] = pr;
+          dv[e] = pr * (__uint_as_float(dp[idx]) - dl[e]) * p.scale;
         }
         const int unit = half * 4 + u;
-        *reinterpret_cast<uint4*>(p_row + ((unit ^ sw) << 4)) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
-        *reinterpret_cast<uint4*>(ds_row + ((unit ^ sw) << 4)) = make_uint4(dw[0], dw[1], dw[2], dw[3]);
+        *reinterpret_cast<uint4*>(p_row + ((unit ^ sw) << 4)) =
+            make_uint4(pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]), pack_bf16x2(pv[4], pv[5]),
+                       pack_bf16x2(pv[6], pv[7]));
+        *reinterpret_cast<uint4*>(ds_row + ((unit ^ sw) << 4)) =
+            make_uint4(pack_bf16x2(dv[0], dv[1]), pack_bf16x2(dv[2], dv[3]), pack_bf16x2(dv[4], dv[5]),
+                       pack_bf16x2(dv[6], dv[7]));
       }
     }
     if (tid == 0) bulk_wait_group_read0();  // the previous tile's reduce has drained the dQ staging
@@ -262,14 +265,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     __syncwarp();
     {
       float* stage = reinterpret_cast<float*>(smem + S::OFF_DQ) + warp * 32 + lane;  // column d
+      uint32_t dq[32];
+      tmem_ld_32x32(t_lane + C_DQ + half * 32, dq);
+      tmem_ld_wait();
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t dq[32];
-        tmem_ld_32x32(t_lane + C_DQ + half * 32, dq);
-        tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 32; ++c) stage[(half * 32 + c) * BW_HD] = __uint_as_float(dq[c]);
-      }
+      for (int c = 0; c < 32; ++c) stage[(half * 32 + c) * BW_HD] = __uint_as_float(dq[c]);
     }
     // The next iteration's issue_grads overwrites dQ^T; order the reads above before it.
     tc_fence_before();
@@ -288,7 +288,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     __nv_bfloat16* dvr = p.dv + (static_cast<long long>(b) * T + key) * p.lddkv + h * BW_HD;
     __nv_bfloat16* dkr = p.dk + (static_cast<long long>(b) * T + key) * p.lddkv + h * BW_HD;
 #pragma unroll
-    for (int c = 0; c < BW_HD / 32; ++c) {
+    for (int cc = 0; cc < BW_HD / 64; ++cc) {
+      const int c = half * (BW_HD / 64) + cc;
       uint32_t a[32], d[32];
       tmem_ld_32x32(t_lane + C_DV + c * 32, a);
       tmem_ld_32x32(t_lane + C_DK + c * 32, d);
@@ -310,7 +311,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
     }
-  } else if (key_ok) {
+  } else if (key_ok && half == 0) {
     // keys no query can see (cannot happen for causal Tq == Tk, kept for safety): zero gradient
     __nv_bfloat16* dvr = p.dv + (static_cast<long long>(b) * T + key) * p.lddkv + h * BW_HD;
     __nv_bfloat16* dkr = p.dk + (static_cast<long long>(b) * T + key) * p.lddkv + h * BW_HD;
@@ -321,7 +322,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (tid < 32) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -430,7 +431,7 @@ extern "C" int a3_attn_bwd(const void* q, const void* k, const void* v, const vo
   p.scale = scale;
   p.causal = causal ? 1 : 0;
   dim3 grid((T + BW_KEYS - 1) / BW_KEYS, H, B);
-  attn_bwd_kernel<<<grid, 128, BwdSmem::TOTAL, s>>>(tmQ, tmK, tmV, tmDO, tmDQ, p);
+  attn_bwd_kernel<<<grid, 256, BwdSmem::TOTAL, s>>>(tmQ, tmK, tmV, tmDO, tmDQ, p);
   rc = check_launch("a3_attn_bwd");
   if (rc) return rc;
   const long long rows = (long long)B * T;

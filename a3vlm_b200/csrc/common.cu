@@ -27,7 +27,15 @@ int check_launch(const char* what) {
   return A3_OK;
 }
 
+static std::atomic<int> g_sm_limit{0};
+
 int num_sms() {
+  const int lim = g_sm_limit.load(std::memory_order_relaxed);
+  if (lim > 0) return lim;
+  return device_sms();
+}
+
+int device_sms() {
   static int n = 0;
   if (n == 0) {
     int dev = 0;
@@ -110,6 +118,12 @@ int make_tmap_3d_f32_linear(CUtensorMap* tm, const void* ptr, uint64_t dim0, uin
 }
 
 }  // namespace a3
+
+extern "C" int a3_set_sm_limit(int n) {
+  if (n < 0 || n > a3::device_sms()) return a3::set_error(A3_ERR_ARG, "a3_set_sm_limit: 0 <= n <= SM count");
+  a3::g_sm_limit.store(n & ~1);  // even: CTA pairs
+  return A3_OK;
+}
 
 extern "C" const char* a3_last_error(void) { return a3::g_err; }
 extern "C" int a3_version(void) { return 100; }

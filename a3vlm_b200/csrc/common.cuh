@@ -11,7 +11,8 @@ namespace a3 {
 
 int set_error(int code, const char* msg);
 int check_launch(const char* what);
-int num_sms();
+int num_sms();     // SMs the persistent kernels size their grids for (a3_set_sm_limit)
+int device_sms();  // physical SM count
 
 // 2-D bf16 tensor map with 128-byte swizzle.  dim0 is the contiguous dimension.
 int make_tmap_2d_bf16(CUtensorMap* tm, const void* ptr, uint64_t dim0, uint64_t dim1,

@@ -162,7 +162,7 @@ class Workspace:
             self.dqkv = e(M, 3 * D)
             self.dq_acc = e(M, D, dt=torch.float32)
             self.delta = e(B, a.n_heads, L, dt=torch.float32)
-            self.nparts = 4 * eng.n_sms
+            self.nparts = 2 * eng.n_sms  # rmsnorm_bwd runs 2 CTAs/SM: one resident wave
             self.part = e(max(B, 1) * self.nparts, D, dt=torch.float32)
             self.part2 = e(self.nparts, D, dt=torch.float32)
             self.tag_grad = e(2, D, dt=torch.float32)

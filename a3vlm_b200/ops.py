@@ -32,6 +32,10 @@ def _st():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def set_sm_limit(n: int) -> None:
+    _lib.check(_L().a3_set_sm_limit(int(n)), "a3_set_sm_limit")
+
+
 def launch_count() -> int:
     return int(_L().a3_launch_count())
 

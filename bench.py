@@ -207,7 +207,14 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # leave SMs for the overlapped all-reduce: NCCL capped at 8 CTAs, our persistent GEMMs sized to
+        # the rest, so no GEMM CTA queues behind a collective CTA
+        nccl_ctas = int(os.environ.get("A3_NCCL_CTAS", "8"))
+        if nccl_ctas > 0:
+            os.environ.setdefault("NCCL_MAX_CTAS", str(nccl_ctas))
         dist.init_process_group("nccl", device_id=dev)
+        if nccl_ctas > 0:
+            ops.set_sm_limit(torch.cuda.get_device_properties(dev).multi_processor_count - nccl_ctas)
     args.warmup = max(args.warmup, 3)
     B, T, S = args.batch, args.text_len, args.image_size
     fl = flops_per_sample(cfg, S, T)

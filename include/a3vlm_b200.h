@@ -36,6 +36,10 @@ const char* a3_last_error(void);
 int a3_version(void);
 /* Number of kernels this library has launched since load / since the last reset (bench.py's
  * `gpu_launches`). */
+/* Persistent kernels (GEMM) size their grids to at most n SMs (0 = all).  Used by the data-parallel
+ * fine-tune step to leave SMs for the concurrent NCCL all-reduce kernels, so that no GEMM CTA has
+ * to wait for a collective CTA to retire. */
+int a3_set_sm_limit(int n);
 long long a3_launch_count(void);
 void a3_reset_launch_count(void);
 
