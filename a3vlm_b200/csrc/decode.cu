@@ -98,8 +98,10 @@ constexpr int DEC_MAX_SPLIT = 32;
 __global__ void __launch_bounds__(DEC_WARPS * 32)
 attn_decode_partial_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kc,
                            const __nv_bfloat16* __restrict__ vc, float* __restrict__ scratch, int H,
-                           int ctx, int max_seq, long long ldq, float scale_log2) {
+                           int ctx, int max_seq, long long ldq, float scale_log2,
+                           const int* __restrict__ pos_dev) {
   constexpr int HD = 128;
+  if (pos_dev) ctx = *pos_dev + 1;  // CUDA-graph replay: the context length lives in device memory
   __shared__ float s_acc[DEC_WARPS][HD];
   __shared__ float s_m[DEC_WARPS], s_l[DEC_WARPS];
   const int bh = blockIdx.x, b = bh / H, h = bh % H;
@@ -171,6 +173,34 @@ attn_decode_combine_kernel(const float* __restrict__ scratch, __nv_bfloat16* __r
   o[b * ldo + h * HD + d] = __float2bfloat16_rn(A / L);
 }
 
+// Fused RoPE (q, k) + KV-cache append for one new token per sequence (LLM/llama_ens5.py:118-127 with
+// seqlen 1).  grid = B*H CTAs of 64 threads; thread j rotates pair j of q and k of head h in place,
+// writes the rotated k and the v pair into cache[b, pos, h].  pos comes from device memory when
+// pos_dev != null so the whole decode step can be replayed as one CUDA graph.
+__global__ void __launch_bounds__(64)
+decode_rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, long long ld, __nv_bfloat16* __restrict__ kc,
+                      __nv_bfloat16* __restrict__ vc, int H, const float2* __restrict__ table,
+                      const int* __restrict__ pos_dev, int pos_host, int max_seq) {
+  constexpr int HD = 128;
+  const int pos = pos_dev ? *pos_dev : pos_host;
+  const int b = blockIdx.x / H, h = blockIdx.x % H, j = threadIdx.x;
+  const long long D = (long long)H * HD;
+  __nv_bfloat16* row = qkv + b * ld + h * HD + 2 * j;
+  const float2 cs = table[(long long)pos * (HD / 2) + j];
+  const long long ci = (((long long)b * max_seq + pos) * H + h) * HD + 2 * j;
+  {
+    const float2 x = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(row));
+    *reinterpret_cast<uint32_t*>(row) = pack_bf16x2(x.x * cs.x - x.y * cs.y, x.x * cs.y + x.y * cs.x);
+  }
+  {
+    const float2 x = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(row + D));
+    const uint32_t r = pack_bf16x2(x.x * cs.x - x.y * cs.y, x.x * cs.y + x.y * cs.x);
+    *reinterpret_cast<uint32_t*>(row + D) = r;
+    *reinterpret_cast<uint32_t*>(kc + ci) = r;
+  }
+  *reinterpret_cast<uint32_t*>(vc + ci) = *reinterpret_cast<const uint32_t*>(row + 2 * D);
+}
+
 }  // namespace a3
 
 using namespace a3;
@@ -207,19 +237,33 @@ extern "C" int a3_linear_small_m(const void* X, const void* W, void* Y, int M, i
   return A3_ERR_ARG;
 }
 
+extern "C" int a3_decode_rope_kv(void* qkv, long long ld, void* kcache, void* vcache, int B, int H,
+                                 int head_dim, const float* table, int pos, const int* pos_dev,
+                                 int max_seq, void* stream) {
+  if (head_dim != 128) return set_error(A3_ERR_UNSUPPORTED, "a3_decode_rope_kv: head_dim must be 128");
+  if ((ld & 1) || (!pos_dev && (pos < 0 || pos >= max_seq)))
+    return set_error(A3_ERR_ARG, "a3_decode_rope_kv: 0 <= pos < max_seq");
+  if (B * H <= 0) return A3_OK;
+  decode_rope_kv_kernel<<<B * H, 64, 0, ST(stream)>>>(BFM(qkv), ld, BFM(kcache), BFM(vcache), H,
+                                                     reinterpret_cast<const float2*>(table), pos_dev, pos,
+                                                     max_seq);
+  return check_launch("a3_decode_rope_kv");
+}
+
 extern "C" int a3_attn_decode(const void* q, const void* kcache, const void* vcache, void* o,
                               float* scratch, int B, int H, int head_dim, int ctx, int max_seq,
-                              long long ldq, long long ldo, float scale, void* stream) {
+                              long long ldq, long long ldo, float scale, const int* pos_dev,
+                              void* stream) {
   if (head_dim != 128) return set_error(A3_ERR_UNSUPPORTED, "a3_attn_decode: head_dim must be 128");
   if (ctx <= 0 || ctx > max_seq) return set_error(A3_ERR_ARG, "a3_attn_decode: 0 < ctx <= max_seq");
   if (B * H <= 0) return A3_OK;
   int nsplit = (2 * num_sms() + B * H - 1) / (B * H);
   const int max_useful = (ctx + 4 * DEC_WARPS - 1) / (4 * DEC_WARPS);
-  if (nsplit > max_useful) nsplit = max_useful;
+  if (!pos_dev && nsplit > max_useful) nsplit = max_useful;  // graph mode: split count must not depend on ctx
   if (nsplit > DEC_MAX_SPLIT) nsplit = DEC_MAX_SPLIT;
   if (nsplit < 1) nsplit = 1;
   attn_decode_partial_kernel<<<dim3(B * H, nsplit), DEC_WARPS * 32, 0, ST(stream)>>>(
-      BF(q), BF(kcache), BF(vcache), scratch, H, ctx, max_seq, ldq, scale * 1.4426950408889634f);
+      BF(q), BF(kcache), BF(vcache), scratch, H, ctx, max_seq, ldq, scale * 1.4426950408889634f, pos_dev);
   int rc = check_launch("a3_attn_decode(partial)");
   if (rc != A3_OK) return rc;
   attn_decode_combine_kernel<<<B * H, 128, 0, ST(stream)>>>(scratch, BFM(o), H, nsplit, ldo);

@@ -203,6 +203,7 @@ class Engine:
         self.cache_B = 0
         self.cache_image_words = 0
         self.dec = None
+        self.use_decode_graph = True
         self.comm_stream = None
 
     # ------------------------------------------------------------------------------------ layouts
@@ -563,8 +564,11 @@ class Engine:
         return ops.gemm(fn, w["output.weight"]).float()
 
     def _decode_step(self, tokens: torch.Tensor, pos: int) -> torch.Tensor:
-        """One-token step (q_len = 1): weight-streaming linears + split-KV attention over the cache."""
-        a, w = self.args, self.w.views
+        """One-token step (q_len = 1): weight-streaming linears + fused RoPE/KV-append + split-KV
+        attention over the cache.  The kernel sequence takes the position and the token ids from
+        device memory, so after one eager step it is captured once per batch size and replayed as a
+        single CUDA graph (~330 launches per token would otherwise be launch-bound)."""
+        a = self.args
         B, D, F = tokens.shape[0], a.dim, self.ffn_dim
         if pos + 1 > a.max_seq_len:
             raise ValueError("KV cache overflow")
@@ -572,22 +576,46 @@ class Engine:
             e = lambda *s, dt=bf16: torch.empty(*s, device=self.device, dtype=dt)
             self.dec = {"B": B, "x": e(B, D), "x2": e(B, D), "xn": e(B, D), "qkv": e(B, 3 * D), "o": e(B, D),
                         "h": e(B, D), "gu": e(B, 2 * F), "y": e(B, F),
-                        "scratch": e(B * a.n_heads * 32 * (self.head_dim + 2), dt=torch.float32)}
+                        "scratch": e(B * a.n_heads * 32 * (self.head_dim + 2), dt=torch.float32),
+                        "tok": torch.zeros(B, 1, device=self.device, dtype=torch.int64),
+                        "pos": torch.zeros(1, device=self.device, dtype=torch.int32),
+                        "logits": e(B, a.vocab_size, dt=torch.float32), "graph": None, "eager_steps": 0}
+            if B > 16:
+                self.dec["logits_bf"] = e(B, a.vocab_size)
         d = self.dec
+        d["tok"].copy_(tokens.reshape(B, 1))
+        d["pos"].fill_(pos)
+        if d["graph"] is not None:
+            d["graph"].replay()
+            return d["logits"]
+        if self.use_decode_graph and d["eager_steps"] >= 1:
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._decode_kernels(d)
+            d["graph"] = g
+            g.replay()
+            return d["logits"]
+        d["eager_steps"] += 1
+        self._decode_kernels(d)
+        return d["logits"]
+
+    def _decode_kernels(self, d) -> None:
+        a, w = self.args, self.w.views
+        B, D = d["B"], a.dim
         small = B <= 16
         lin = (lambda x, wt, out, residual=None: ops.linear_small_m(x, wt, out=out, residual=residual)) if small \
             else (lambda x, wt, out, residual=None: ops.gemm(x, wt, out, residual=residual))
-        ops.embed_splice(tokens.contiguous(), w["tok_embeddings.weight"], None, None, None, d["x"], B, 1, 0, D)
+        ops.embed_splice(d["tok"], w["tok_embeddings.weight"], None, None, None, d["x"], B, 1, 0, D)
         x, x2 = d["x"], d["x2"]
         for i in range(a.n_layers):
             p = f"layers.{i}."
             ops.rmsnorm_fwd(x, w[p + "attention_norm.weight"], a.norm_eps, out=d["xn"])
             lin(d["xn"], w[p + "wqkv"], d["qkv"])
-            ops.rope_apply(d["qkv"][:, :2 * D], 2 * a.n_heads, self.head_dim, self.rope, 1, pos)
-            ops.kv_append(d["qkv"][:, D:2 * D], d["qkv"][:, 2 * D:], self.kcache[i], self.vcache[i], B, 1,
-                          a.n_heads, self.head_dim, pos, a.max_seq_len)
+            ops.decode_rope_kv(d["qkv"], self.kcache[i], self.vcache[i], B, a.n_heads, self.head_dim, self.rope,
+                               0, a.max_seq_len, pos_dev=d["pos"])
             ops.attn_decode(d["qkv"][:, :D], self.kcache[i], self.vcache[i], d["o"], d["scratch"], B,
-                            a.n_heads, self.head_dim, pos + 1, a.max_seq_len, self.scale)
+                            a.n_heads, self.head_dim, a.max_seq_len, a.max_seq_len, self.scale, pos_dev=d["pos"])
             lin(d["o"], w[p + "attention.wo.weight"], d["h"], residual=x)
             ops.rmsnorm_fwd(d["h"], w[p + "ffn_norm.weight"], a.norm_eps, out=d["xn"])
             lin(d["xn"], w[p + "w13"], d["gu"])
@@ -595,4 +623,10 @@ class Engine:
             lin(d["y"], w[p + "feed_forward.w2.weight"], x2, residual=d["h"])
             x, x2 = x2, x
         fn = ops.rmsnorm_fwd(x, w["norm.weight"], a.norm_eps, out=d["xn"])
-        return self._lm_head(fn)
+        if small:
+            ops.linear_small_m(fn, w["output.weight"], out=d["logits"], out_fp32=True)
+        else:
+            if "logits_bf" not in d:
+                d["logits_bf"] = torch.empty(B, a.vocab_size, device=self.device, dtype=bf16)
+            ops.gemm(fn, w["output.weight"], d["logits_bf"])
+            d["logits"].copy_(d["logits_bf"])  # .float() of the bf16 result (llama_ens5.py:530-531)

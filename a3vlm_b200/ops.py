@@ -184,11 +184,17 @@ def attn_bwd(q, k, v, o, dout, lse, delta, dq_acc, dq, dk, dv, B, H, T, head_dim
     _lib.check(rc, "a3_attn_bwd")
 
 
-def attn_decode(q, kcache, vcache, out, scratch, B, H, head_dim, ctx, max_seq, scale):
+def attn_decode(q, kcache, vcache, out, scratch, B, H, head_dim, ctx, max_seq, scale, pos_dev=None):
     rc = _L().a3_attn_decode(_p(q), _p(kcache), _p(vcache), _p(out), _p(scratch), B, H, head_dim, ctx,
-                             max_seq, q.stride(0), out.stride(0), float(scale), _st())
+                             max_seq, q.stride(0), out.stride(0), float(scale), _p(pos_dev), _st())
     _lib.check(rc, "a3_attn_decode")
     return out
+
+
+def decode_rope_kv(qkv, kcache, vcache, B, H, head_dim, table, pos, max_seq, pos_dev=None):
+    rc = _L().a3_decode_rope_kv(_p(qkv), qkv.stride(0), _p(kcache), _p(vcache), B, H, head_dim, _p(table),
+                                int(pos), _p(pos_dev), max_seq, _st())
+    _lib.check(rc, "a3_decode_rope_kv")
 
 
 def kv_append(k, v, kcache, vcache, B, T, H, head_dim, start, max_seq):

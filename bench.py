@@ -119,6 +119,9 @@ def cpu_reference_sample(cfg, S, T, sample_layers=2, repeats=1):
     img = torch.randn(1, 3, S, S, generator=g)
     train = [k for k in sd if not k.startswith("clip.")]
 
+    master = {k: sd[k].detach().float() for k in train}  # fp32 masters + AdamW state (M/util/tensor_type.py:60-66)
+    state = {k: (torch.zeros_like(master[k]), torch.zeros_like(master[k])) for k in train}
+
     def run(args):
         for k in train:
             sd[k].requires_grad_(True)
@@ -127,14 +130,17 @@ def cpu_reference_sample(cfg, S, T, sample_layers=2, repeats=1):
         t0 = time.perf_counter()
         loss = O.meta_forward_loss(m, tok, lab, img)
         loss.backward()
+        live = [k for k in train if sd[k].grad is not None]
+        grads = {k: sd[k].grad for k in live}
+        O.adamw_step({k: master[k] for k in live}, grads, state, 1, 2e-5, 0.0, 8.0)  # clip 8 + AdamW, as our step
         return time.perf_counter() - t0
 
     t_small = min(run(a_small) for _ in range(repeats))
     t_zero = min(run(a_zero) for _ in range(repeats))
     per_layer = max(t_small - t_zero, 0.0) / sample_layers
     full = t_zero + per_layer * cfg["n_layers"]
-    sample = (f"oracle (torch eager, bf16 linears) batch 1, {S}px + {T} tok: ViT fwd + head/loss fwd+bwd = {t_zero:.2f}s, "
-              f"{sample_layers} decoder layers fwd+bwd = {t_small - t_zero:.2f}s, extrapolated x{cfg['n_layers']}/{sample_layers}")
+    sample = (f"oracle (torch eager, bf16 linears) batch 1, {S}px + {T} tok: ViT fwd + head/loss fwd+bwd + their clip/AdamW = {t_zero:.2f}s, "
+              f"{sample_layers} decoder layers fwd+bwd+AdamW = {t_small - t_zero:.2f}s, extrapolated x{cfg['n_layers']}/{sample_layers}")
     return full, cores, sample
 
 
@@ -207,9 +213,10 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # leave SMs for the overlapped all-reduce: NCCL capped at 8 CTAs, our persistent GEMMs sized to
+        # optional (A3_NCCL_CTAS=n, default off: measured 312 ms vs 307 ms per step at N=2 with the cap):
+        # NCCL capped at n CTAs, our persistent GEMMs sized to
         # the rest, so no GEMM CTA queues behind a collective CTA
-        nccl_ctas = int(os.environ.get("A3_NCCL_CTAS", "8"))
+        nccl_ctas = int(os.environ.get("A3_NCCL_CTAS", "0"))
         if nccl_ctas > 0:
             os.environ.setdefault("NCCL_MAX_CTAS", str(nccl_ctas))
         dist.init_process_group("nccl", device_id=dev)

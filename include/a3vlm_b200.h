@@ -127,9 +127,16 @@ int a3_attn_bwd(const void* q, const void* k, const void* v, const void* o, cons
                 float scale, int causal, void* stream);
 /* Single-query decode attention over the KV cache (llama_ens5.py:121-129,142-167 with seqlen 1):
  * cache layout [B][max_seq][H][128] bf16; q [B][H*128]; ctx = number of valid positions. */
+/* pos_dev != NULL (CUDA-graph replay): ctx = *pos_dev + 1 is read on the device and `ctx` is only an
+ * upper bound used to size the split. */
 int a3_attn_decode(const void* q, const void* kcache, const void* vcache, void* o, float* scratch,
                    int B, int H, int head_dim, int ctx, int max_seq, long long ldq, long long ldo,
-                   float scale, void* stream);
+                   float scale, const int* pos_dev, void* stream);
+/* Decode-step fusion of apply_rotary_emb + cache write (llama_ens5.py:118-127, seqlen 1): rotates q
+ * and k of qkv [B][3*H*128] in place at position pos (or *pos_dev) and writes k, v into
+ * cache[b, pos]. */
+int a3_decode_rope_kv(void* qkv, long long ld, void* kcache, void* vcache, int B, int H, int head_dim,
+                      const float* table, int pos, const int* pos_dev, int max_seq, void* stream);
 /* KV-cache append (llama_ens5.py:121-127): copy rows [B][T] of k and v (strided, ld) into
  * cache[:, start:start+T]. */
 int a3_kv_append(const void* k, const void* v, long long ld, void* kcache, void* vcache, int B,

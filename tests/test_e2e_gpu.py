@@ -106,9 +106,19 @@ def test_inference_prefill_decode_match_golden(tiny, gold):
     check("decode_vs_prefill", dl, pl7, rel=1e-2)
 
 
-def test_greedy_generate_token_exact(tiny, gold):
+@pytest.mark.parametrize("graph", [True, False])
+def test_greedy_generate_token_exact(tiny, gold, graph):
+    """Greedy decode ids are exact against the oracle, both with the decode step replayed as a CUDA
+    graph (default) and launched eagerly."""
     m, _ = tiny
-    out, toks, _ = m.generate_tokens(gold["prompts"], gold["image"], max_gen_len=gold["max_gen_len"], eos_id=2)
+    eng = m.llma.engine
+    eng.use_decode_graph = graph
+    eng.destroy_kv_cache()
+    try:
+        out, toks, _ = m.generate_tokens(gold["prompts"], gold["image"], max_gen_len=gold["max_gen_len"], eos_id=2)
+        assert (eng.dec["graph"] is not None) == graph
+    finally:
+        eng.use_decode_graph = True
     assert out == gold["generated"], (out, gold["generated"])
     assert torch.equal(toks.cpu(), gold["gen_tokens"])
 

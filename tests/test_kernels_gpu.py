@@ -268,6 +268,33 @@ def test_attn_decode_and_kv_append(ops, B, H, ctx):
     close_bf16(o2.reshape(B, 1, H, hd), ref, rtol=2 ** -6, atol=6e-3)
 
 
+def test_decode_rope_kv_and_device_pos(ops):
+    torch.manual_seed(12)
+    B, H, hd, max_seq, pos = 3, 4, 128, 64, 17
+    W = H * hd
+    qkv = rnd(B, 3 * W)
+    table = ops.rope_table(128, 128, device=dev())
+    kc, vc = torch.zeros(B, max_seq, H, hd, device=dev(), dtype=bf16), torch.zeros(B, max_seq, H, hd, device=dev(), dtype=bf16)
+    ref = qkv.clone()
+    ops.rope_apply(ref[:, :2 * W], 2 * H, hd, table, 1, pos)
+    got = qkv.clone()
+    pos_dev = torch.tensor([pos], device=dev(), dtype=torch.int32)
+    ops.decode_rope_kv(got, kc, vc, B, H, hd, table, 0, max_seq, pos_dev=pos_dev)
+    assert torch.equal(got, ref)
+    assert torch.equal(kc[:, pos].reshape(B, W), ref[:, W:2 * W]) and torch.equal(vc[:, pos].reshape(B, W), ref[:, 2 * W:])
+    assert (kc[:, :pos] == 0).all() and (kc[:, pos + 1:] == 0).all()
+    got2 = qkv.clone()
+    ops.decode_rope_kv(got2, kc, vc, B, H, hd, table, pos, max_seq)  # host-side position gives the same
+    assert torch.equal(got2, ref)
+    # attention with the context length read from device memory == host-side ctx
+    kc.copy_(rnd(B, max_seq, H, hd)); vc.copy_(rnd(B, max_seq, H, hd))
+    o1, o2 = torch.empty(B, W, device=dev(), dtype=bf16), torch.empty(B, W, device=dev(), dtype=bf16)
+    scratch = torch.empty(B * H * 32 * 130, device=dev())
+    ops.attn_decode(got[:, :W], kc, vc, o1, scratch, B, H, hd, pos + 1, max_seq, 0.088)
+    ops.attn_decode(got[:, :W], kc, vc, o2, scratch, B, H, hd, max_seq, max_seq, 0.088, pos_dev=pos_dev)
+    close_bf16(o2, o1, atol=2e-3)
+
+
 # ------------------------------------------------------------------------------------------- embed / ViT front
 def test_embed_splice_and_bwd(ops):
     torch.manual_seed(7)
