@@ -88,6 +88,201 @@ linear_small_m_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* 
   }
 }
 
+
+// ------------------------------------------------------------------ fused decode linear
+// Y[m][n] = sum_k Xeff[m][k] W[n][k] for M <= 8 rows (decode, q_len = 1), one launch per projection:
+//   prologue (once per CTA, into shared memory):  Xeff = X                       (plain)
+//                                                 Xeff = RMSNorm(X) * norm_w     (components.py:39-53)
+//                                                 Xeff = bf16(silu(g)) * u       (llama_ens5.py:213-214)
+//   main loop: a warp owns two consecutive output columns and streams their weight rows once
+//              (ld.global.nc, 16-byte, L1 no-allocate); HBM-bound
+//   epilogue:  + residual | fp32 logits | RoPE on the (2j, 2j+1) pair the warp owns + KV-cache append
+//              (llama_ens5.py:118-127) for the QKV projection.
+// Programmatic dependent launch: the first weight chunks are fetched BEFORE griddepcontrol.wait, so the
+// weight stream of projection i+1 starts while projection i drains; everything that depends on the
+// previous kernel (X, the position) is read after the wait.
+struct DecLinParams {
+  const __nv_bfloat16* X; const __nv_bfloat16* W; void* Y;
+  const __nv_bfloat16* norm_w; const __nv_bfloat16* residual;
+  const float2* rope; __nv_bfloat16* kc; __nv_bfloat16* vc; const int* pos_dev;
+  long long ldx, ldw, ldy, ldr;
+  int N, K, mode /*0 plain, 1 rmsnorm, 2 swiglu*/, out_fp32, n_heads, pos, max_seq;
+  float eps;
+};
+constexpr int DL_PF = 8;  // prefetched 16-byte chunks per lane per weight row (issued before the PDL wait)
+
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <int M>
+__global__ void __launch_bounds__(LIN_WARPS * 32)
+decode_linear_kernel(const DecLinParams p) {
+  extern __shared__ __align__(16) uint8_t dl_smem[];
+  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(dl_smem);  // [M][K]
+  __shared__ float s_red[LIN_WARPS][M];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = (blockIdx.x * LIN_WARPS + warp) * LIN_COLS_PER_WARP;
+  const bool active = n0 < p.N;
+  const int K = p.K, nchunks = K >> 3;
+  const __nv_bfloat16* w0 = p.W + (long long)(active ? n0 : 0) * p.ldw;
+  const __nv_bfloat16* w1 = (n0 + 1 < p.N) ? w0 + p.ldw : w0;
+  uint4 pa[DL_PF], pb[DL_PF];
+#pragma unroll
+  for (int i = 0; i < DL_PF; ++i) {
+    const int ch = lane + i * 32;
+    if (ch < nchunks) { pa[i] = ldg_stream(w0 + ch * 8); pb[i] = ldg_stream(w1 + ch * 8); }
+  }
+  griddep_launch();
+  griddep_wait();
+
+  // ---- stage the (transformed) activations
+  if (p.mode == 1) {
+    // one global pass: raw rows -> smem while accumulating sum(x^2); the transform re-reads smem
+    float ss[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) ss[m] = 0.f;
+    for (int ch = threadIdx.x; ch < nchunks; ch += LIN_WARPS * 32) {
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        const uint4 q = *reinterpret_cast<const uint4*>(p.X + m * p.ldx + ch * 8);
+        *reinterpret_cast<uint4*>(xs + m * K + ch * 8) = q;
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { const float2 f = unpack_bf16x2(w[t]); ss[m] += f.x * f.x + f.y * f.y; }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ss[m] += __shfl_xor_sync(0xffffffffu, ss[m], o);
+      if (lane == 0) s_red[warp][m] = ss[m];
+    }
+    __syncthreads();
+    float rstd[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < LIN_WARPS; ++w) t += s_red[w][m];
+      rstd[m] = rsqrtf(t / (float)K + p.eps);
+    }
+    for (int ch = threadIdx.x; ch < nchunks; ch += LIN_WARPS * 32) {  // same chunks this thread staged
+      const uint4 nq = __ldg(reinterpret_cast<const uint4*>(p.norm_w + ch * 8));
+      const uint32_t nw[4] = {nq.x, nq.y, nq.z, nq.w};
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        const uint4 q = *reinterpret_cast<const uint4*>(xs + m * K + ch * 8);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 f = unpack_bf16x2(w[t]), g = unpack_bf16x2(nw[t]);
+          o[t] = pack_bf16x2(bf16_round(f.x * rstd[m]) * g.x, bf16_round(f.y * rstd[m]) * g.y);
+        }
+        *reinterpret_cast<uint4*>(xs + m * K + ch * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  } else if (p.mode == 2) {
+    for (int ch = threadIdx.x; ch < nchunks; ch += LIN_WARPS * 32) {
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        const uint4 gq = *reinterpret_cast<const uint4*>(p.X + m * p.ldx + ch * 8);
+        const uint4 uq = *reinterpret_cast<const uint4*>(p.X + m * p.ldx + K + ch * 8);
+        const uint32_t gw[4] = {gq.x, gq.y, gq.z, gq.w}, uw[4] = {uq.x, uq.y, uq.z, uq.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 g = unpack_bf16x2(gw[t]), u = unpack_bf16x2(uw[t]);
+          o[t] = pack_bf16x2(bf16_round(g.x / (1.f + __expf(-g.x))) * u.x,
+                             bf16_round(g.y / (1.f + __expf(-g.y))) * u.y);
+        }
+        *reinterpret_cast<uint4*>(xs + m * K + ch * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  } else {
+    for (int ch = threadIdx.x; ch < nchunks; ch += LIN_WARPS * 32)
+#pragma unroll
+      for (int m = 0; m < M; ++m)
+        *reinterpret_cast<uint4*>(xs + m * K + ch * 8) = *reinterpret_cast<const uint4*>(p.X + m * p.ldx + ch * 8);
+  }
+  __syncthreads();
+  if (!active) return;
+
+  // ---- stream the two weight rows
+  float acc[LIN_COLS_PER_WARP][M];
+#pragma unroll
+  for (int c = 0; c < LIN_COLS_PER_WARP; ++c)
+#pragma unroll
+    for (int m = 0; m < M; ++m) acc[c][m] = 0.f;
+#pragma unroll
+  for (int i = 0; i < DL_PF; ++i) {
+    const int ch = lane + i * 32;
+    if (ch < nchunks) {
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        const uint4 x = *reinterpret_cast<const uint4*>(xs + m * K + ch * 8);
+        acc[0][m] += dot8(pa[i], x);
+        acc[1][m] += dot8(pb[i], x);
+      }
+    }
+  }
+#pragma unroll 4
+  for (int ch = lane + DL_PF * 32; ch < nchunks; ch += 32) {
+    const uint4 a = ldg_stream(w0 + ch * 8);
+    const uint4 b = ldg_stream(w1 + ch * 8);
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      const uint4 x = *reinterpret_cast<const uint4*>(xs + m * K + ch * 8);
+      acc[0][m] += dot8(a, x);
+      acc[1][m] += dot8(b, x);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < LIN_COLS_PER_WARP; ++c)
+#pragma unroll
+    for (int m = 0; m < M; ++m)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[c][m] += __shfl_xor_sync(0xffffffffu, acc[c][m], o);
+  if (lane != 0) return;
+
+  if (p.rope) {
+    // QKV projection: n0 is even, so this warp owns one RoPE pair (or a v pair)
+    const int D = p.n_heads * 128;
+    const int pos = p.pos_dev ? *p.pos_dev : p.pos;
+    const int sect = n0 / D, within = n0 - sect * D;  // 0 q, 1 k, 2 v
+    const float2 cs = p.rope[(long long)pos * 64 + ((within & 127) >> 1)];
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      float a = bf16_round(acc[0][m]), b = bf16_round(acc[1][m]);
+      if (sect < 2) { const float ra = a * cs.x - b * cs.y, rb = a * cs.y + b * cs.x; a = ra; b = rb; }
+      const uint32_t r = pack_bf16x2(a, b);
+      *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(p.Y) + m * p.ldy + n0) = r;
+      if (sect >= 1) {
+        __nv_bfloat16* cache = sect == 1 ? p.kc : p.vc;
+        *reinterpret_cast<uint32_t*>(cache + ((long long)m * p.max_seq + pos) * D + within) = r;
+      }
+    }
+    return;
+  }
+#pragma unroll
+  for (int c = 0; c < LIN_COLS_PER_WARP; ++c) {
+    const int n = n0 + c;
+    if (n >= p.N) break;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      float v = acc[c][m];
+      if (p.out_fp32) {
+        v = bf16_round(v);  // logits: .float() of a bf16 GEMM result (llama_ens5.py:530-531)
+        if (p.residual) v += __bfloat162float(p.residual[m * p.ldr + n]);
+        reinterpret_cast<float*>(p.Y)[m * p.ldy + n] = v;
+      } else {
+        if (p.residual) v = bf16_round(v) + __bfloat162float(p.residual[m * p.ldr + n]);
+        reinterpret_cast<__nv_bfloat16*>(p.Y)[m * p.ldy + n] = __float2bfloat16_rn(v);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ single-query attention
 // grid (B*H, nsplit).  Each CTA (4 warps) scans its slice of the context: a warp takes one key at
 // a time, lanes hold 4 consecutive dims (head_dim 128).  Partial (m, l, acc[128]) per CTA goes to
@@ -99,8 +294,10 @@ __global__ void __launch_bounds__(DEC_WARPS * 32)
 attn_decode_partial_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kc,
                            const __nv_bfloat16* __restrict__ vc, float* __restrict__ scratch, int H,
                            int ctx, int max_seq, long long ldq, float scale_log2,
-                           const int* __restrict__ pos_dev) {
+                           const int* __restrict__ pos_dev, int* __restrict__ counters,
+                           __nv_bfloat16* __restrict__ o, long long ldo) {
   constexpr int HD = 128;
+  __shared__ bool s_last;
   if (pos_dev) ctx = *pos_dev + 1;  // CUDA-graph replay: the context length lives in device memory
   __shared__ float s_acc[DEC_WARPS][HD];
   __shared__ float s_m[DEC_WARPS], s_l[DEC_WARPS];
@@ -113,24 +310,45 @@ attn_decode_partial_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloa
   const float2 q01 = unpack_bf16x2(qraw.x), q23 = unpack_bf16x2(qraw.y);
   float m = -INFINITY, l = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f, a3v = 0.f;
   const long long base = ((long long)b * max_seq) * H * HD + h * HD + lane * 4;
-  for (int t = k_begin + warp; t < k_end; t += DEC_WARPS) {
-    const long long off = base + (long long)t * H * HD;
-    const uint2 kr = *reinterpret_cast<const uint2*>(kc + off);
-    const uint2 vr = *reinterpret_cast<const uint2*>(vc + off);
-    const float2 k01 = unpack_bf16x2(kr.x), k23 = unpack_bf16x2(kr.y);
-    float s = q01.x * k01.x + q01.y * k01.y + q23.x * k23.x + q23.y * k23.y;
+  // 8 keys per warp in flight: all K / V loads of a group are issued before the dependent
+  // online-softmax chain (one L2 round trip per group instead of per key)
+  constexpr int KU = 8;
+  for (int t0 = k_begin + warp; t0 < k_end; t0 += DEC_WARPS * KU) {
+    uint2 kr[KU], vr[KU];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    s *= scale_log2;
-    const float mn = fmaxf(m, s);
-    const float corr = exp2f(m - mn), p = exp2f(s - mn);
-    const float2 v01 = unpack_bf16x2(vr.x), v23 = unpack_bf16x2(vr.y);
-    l = l * corr + p;
-    a0 = a0 * corr + p * v01.x;
-    a1 = a1 * corr + p * v01.y;
-    a2 = a2 * corr + p * v23.x;
-    a3v = a3v * corr + p * v23.y;
-    m = mn;
+    for (int u = 0; u < KU; ++u) {
+      const int t = t0 + u * DEC_WARPS;
+      if (t < k_end) {
+        const long long off = base + (long long)t * H * HD;
+        kr[u] = *reinterpret_cast<const uint2*>(kc + off);
+        vr[u] = *reinterpret_cast<const uint2*>(vc + off);
+      }
+    }
+    float sc[KU];
+#pragma unroll
+    for (int u = 0; u < KU; ++u) {
+      const float2 k01 = unpack_bf16x2(kr[u].x), k23 = unpack_bf16x2(kr[u].y);
+      sc[u] = q01.x * k01.x + q01.y * k01.y + q23.x * k23.x + q23.y * k23.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < KU; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], o);
+#pragma unroll
+    for (int u = 0; u < KU; ++u) {
+      if (t0 + u * DEC_WARPS < k_end) {
+        const float s = sc[u] * scale_log2;
+        const float mn = fmaxf(m, s);
+        const float corr = exp2f(m - mn), p = exp2f(s - mn);
+        const float2 v01 = unpack_bf16x2(vr[u].x), v23 = unpack_bf16x2(vr[u].y);
+        l = l * corr + p;
+        a0 = a0 * corr + p * v01.x;
+        a1 = a1 * corr + p * v01.y;
+        a2 = a2 * corr + p * v23.x;
+        a3v = a3v * corr + p * v23.y;
+        m = mn;
+      }
+    }
   }
   s_acc[warp][lane * 4 + 0] = a0;
   s_acc[warp][lane * 4 + 1] = a1;
@@ -153,6 +371,29 @@ attn_decode_partial_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloa
   float* out = scratch + ((long long)bh * nsplit + split) * (HD + 2);
   out[d] = A;
   if (d == 0) { out[HD] = M; out[HD + 1] = L; }
+  // The last split of this (b, h) to finish merges all of them (no second launch).  The counter
+  // resets itself for the next step.
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int done = atomicAdd(&counters[bh], 1);
+    s_last = done == nsplit - 1;
+    if (s_last) counters[bh] = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const volatile float* in = scratch + (long long)bh * nsplit * (HD + 2);
+  float Mx = -INFINITY;
+  for (int s = 0; s < nsplit; ++s) Mx = fmaxf(Mx, in[s * (HD + 2) + HD]);
+  float Lx = 0.f, Ax = 0.f;
+  for (int s = 0; s < nsplit; ++s) {
+    const float ms = in[s * (HD + 2) + HD];
+    const float c = ms == -INFINITY ? 0.f : exp2f(ms - Mx);
+    Lx += in[s * (HD + 2) + HD + 1] * c;
+    Ax += in[s * (HD + 2) + d] * c;
+  }
+  o[b * ldo + h * HD + d] = __float2bfloat16_rn(Ax / Lx);
 }
 
 __global__ void __launch_bounds__(128)
@@ -237,6 +478,61 @@ extern "C" int a3_linear_small_m(const void* X, const void* W, void* Y, int M, i
   return A3_ERR_ARG;
 }
 
+
+template <int M>
+static int launch_decode_linear(const DecLinParams& p, cudaStream_t s) {
+  const size_t smem = (size_t)M * p.K * 2;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(decode_linear_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(smem > 48 * 1024 ? smem : 48 * 1024));
+    if (e != cudaSuccess) return set_error(A3_ERR_CUDA, cudaGetErrorString(e));
+    configured = smem;
+  }
+  const int cols_per_block = LIN_WARPS * LIN_COLS_PER_WARP;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((p.N + cols_per_block - 1) / cols_per_block);
+  cfg.blockDim = dim3(LIN_WARPS * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, decode_linear_kernel<M>, p);
+  if (e != cudaSuccess) return set_error(A3_ERR_CUDA, cudaGetErrorString(e));
+  return check_launch("a3_decode_linear");
+}
+
+extern "C" int a3_decode_linear(const void* X, const void* W, void* Y, int M, int N, int K,
+                                long long ldx, long long ldw, long long ldy, const void* norm_w,
+                                float eps, int swiglu, const void* residual, long long ldr,
+                                int out_fp32, const float* rope_table, int n_heads, void* kcache,
+                                void* vcache, const int* pos_dev, int pos, int max_seq,
+                                void* stream) {
+  if (M <= 0 || N <= 0) return A3_OK;
+  if (M > 8) return set_error(A3_ERR_ARG, "a3_decode_linear: M <= 8 (use a3_linear_small_m / a3_gemm_bf16)");
+  if ((K & 7) || (ldx & 7) || (ldw & 7) || (reinterpret_cast<uintptr_t>(X) & 15) ||
+      (reinterpret_cast<uintptr_t>(W) & 15))
+    return set_error(A3_ERR_ARG, "a3_decode_linear: K, ldx, ldw % 8 == 0 and 16-byte alignment");
+  if ((size_t)M * K * 2 > 200 * 1024) return set_error(A3_ERR_ARG, "a3_decode_linear: M*K too large for smem staging");
+  if (norm_w && swiglu) return set_error(A3_ERR_ARG, "a3_decode_linear: norm and swiglu prologues are exclusive");
+  if (rope_table && (N != 3 * n_heads * 128 || out_fp32 || residual || !kcache || !vcache || (ldy & 1)))
+    return set_error(A3_ERR_ARG, "a3_decode_linear: rope epilogue needs N == 3*H*128, bf16 out, caches");
+  DecLinParams p;
+  p.X = BF(X); p.W = BF(W); p.Y = Y; p.norm_w = BF(norm_w); p.residual = BF(residual);
+  p.rope = reinterpret_cast<const float2*>(rope_table); p.kc = BFM(kcache); p.vc = BFM(vcache);
+  p.pos_dev = pos_dev; p.ldx = ldx; p.ldw = ldw; p.ldy = ldy; p.ldr = ldr;
+  p.N = N; p.K = K; p.mode = norm_w ? 1 : (swiglu ? 2 : 0); p.out_fp32 = out_fp32;
+  p.n_heads = n_heads; p.pos = pos; p.max_seq = max_seq; p.eps = eps;
+  cudaStream_t s = ST(stream);
+#define CASE(m) case m: return launch_decode_linear<m>(p, s);
+  switch (M) { CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) }
+#undef CASE
+  return A3_ERR_ARG;
+}
+
 extern "C" int a3_decode_rope_kv(void* qkv, long long ld, void* kcache, void* vcache, int B, int H,
                                  int head_dim, const float* table, int pos, const int* pos_dev,
                                  int max_seq, void* stream) {
@@ -263,9 +559,7 @@ extern "C" int a3_attn_decode(const void* q, const void* kcache, const void* vca
   if (nsplit > DEC_MAX_SPLIT) nsplit = DEC_MAX_SPLIT;
   if (nsplit < 1) nsplit = 1;
   attn_decode_partial_kernel<<<dim3(B * H, nsplit), DEC_WARPS * 32, 0, ST(stream)>>>(
-      BF(q), BF(kcache), BF(vcache), scratch, H, ctx, max_seq, ldq, scale * 1.4426950408889634f, pos_dev);
-  int rc = check_launch("a3_attn_decode(partial)");
-  if (rc != A3_OK) return rc;
-  attn_decode_combine_kernel<<<B * H, 128, 0, ST(stream)>>>(scratch, BFM(o), H, nsplit, ldo);
-  return check_launch("a3_attn_decode(combine)");
+      BF(q), BF(kcache), BF(vcache), scratch, H, ctx, max_seq, ldq, scale * 1.4426950408889634f, pos_dev,
+      reinterpret_cast<int*>(scratch + (long long)B * H * DEC_MAX_SPLIT * (128 + 2)), BFM(o), ldo);
+  return check_launch("a3_attn_decode");
 }

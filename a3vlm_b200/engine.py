@@ -576,7 +576,8 @@ class Engine:
             e = lambda *s, dt=bf16: torch.empty(*s, device=self.device, dtype=dt)
             self.dec = {"B": B, "x": e(B, D), "x2": e(B, D), "xn": e(B, D), "qkv": e(B, 3 * D), "o": e(B, D),
                         "h": e(B, D), "gu": e(B, 2 * F), "y": e(B, F),
-                        "scratch": e(B * a.n_heads * 32 * (self.head_dim + 2), dt=torch.float32),
+                        "scratch": torch.zeros(B * a.n_heads * (32 * (self.head_dim + 2) + 1), device=self.device,
+                                               dtype=torch.float32),
                         "tok": torch.zeros(B, 1, device=self.device, dtype=torch.int64),
                         "pos": torch.zeros(1, device=self.device, dtype=torch.int32),
                         "logits": e(B, a.vocab_size, dt=torch.float32), "graph": None, "eager_steps": 0}
@@ -602,12 +603,28 @@ class Engine:
 
     def _decode_kernels(self, d) -> None:
         a, w = self.args, self.w.views
-        B, D = d["B"], a.dim
+        B, D, F = d["B"], a.dim, self.ffn_dim
+        ops.embed_splice(d["tok"], w["tok_embeddings.weight"], None, None, None, d["x"], B, 1, 0, D)
+        x, x2 = d["x"], d["x2"]
+        if B <= 8:
+            # five launches per layer: every norm / activation / RoPE / cache write is a prologue or
+            # epilogue of the weight-streaming projection that consumes or produces it
+            for i in range(a.n_layers):
+                p = f"layers.{i}."
+                ops.decode_linear(x, w[p + "wqkv"], d["qkv"], norm_w=w[p + "attention_norm.weight"], eps=a.norm_eps,
+                                  rope=self.rope, n_heads=a.n_heads, kcache=self.kcache[i], vcache=self.vcache[i],
+                                  pos_dev=d["pos"], max_seq=a.max_seq_len)
+                ops.attn_decode(d["qkv"][:, :D], self.kcache[i], self.vcache[i], d["o"], d["scratch"], B,
+                                a.n_heads, self.head_dim, a.max_seq_len, a.max_seq_len, self.scale, pos_dev=d["pos"])
+                ops.decode_linear(d["o"], w[p + "attention.wo.weight"], d["h"], residual=x)
+                ops.decode_linear(d["h"], w[p + "w13"], d["gu"], norm_w=w[p + "ffn_norm.weight"], eps=a.norm_eps)
+                ops.decode_linear(d["gu"], w[p + "feed_forward.w2.weight"], x2, K=F, swiglu=True, residual=d["h"])
+                x, x2 = x2, x
+            ops.decode_linear(x, w["output.weight"], d["logits"], norm_w=w["norm.weight"], eps=a.norm_eps, out_fp32=True)
+            return
         small = B <= 16
         lin = (lambda x, wt, out, residual=None: ops.linear_small_m(x, wt, out=out, residual=residual)) if small \
             else (lambda x, wt, out, residual=None: ops.gemm(x, wt, out, residual=residual))
-        ops.embed_splice(d["tok"], w["tok_embeddings.weight"], None, None, None, d["x"], B, 1, 0, D)
-        x, x2 = d["x"], d["x2"]
         for i in range(a.n_layers):
             p = f"layers.{i}."
             ops.rmsnorm_fwd(x, w[p + "attention_norm.weight"], a.norm_eps, out=d["xn"])
@@ -626,7 +643,5 @@ class Engine:
         if small:
             ops.linear_small_m(fn, w["output.weight"], out=d["logits"], out_fp32=True)
         else:
-            if "logits_bf" not in d:
-                d["logits_bf"] = torch.empty(B, a.vocab_size, device=self.device, dtype=bf16)
             ops.gemm(fn, w["output.weight"], d["logits_bf"])
             d["logits"].copy_(d["logits_bf"])  # .float() of the bf16 result (llama_ens5.py:530-531)

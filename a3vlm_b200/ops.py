@@ -84,6 +84,20 @@ def linear_small_m(x, w, out=None, residual=None, out_fp32=False):
     return out
 
 
+def decode_linear(x, w, out, *, K=None, norm_w=None, eps=1e-5, swiglu=False, residual=None, out_fp32=False,
+                  rope=None, n_heads=0, kcache=None, vcache=None, pos_dev=None, pos=0, max_seq=0):
+    M = x.shape[0]
+    N = w.shape[0]
+    if K is None:
+        K = w.shape[1]
+    rc = _L().a3_decode_linear(_p(x), _p(w), _p(out), M, N, K, x.stride(0), w.stride(0), out.stride(0),
+                               _p(norm_w), float(eps), int(swiglu), _p(residual),
+                               residual.stride(0) if residual is not None else 0, int(out_fp32), _p(rope),
+                               n_heads, _p(kcache), _p(vcache), _p(pos_dev), int(pos), max_seq, _st())
+    _lib.check(rc, "a3_decode_linear")
+    return out
+
+
 # ----------------------------------------------------------------------------------------- norms
 def rmsnorm_fwd(x, w, eps, out=None, rstd=None):
     rows, D = x.shape

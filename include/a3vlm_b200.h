@@ -70,6 +70,19 @@ int a3_linear_small_m(const void* X, const void* W, void* Y, int M, int N, int K
                       long long ldw, long long ldy, const void* residual, long long ldr,
                       int out_fp32, void* stream);
 
+/* Fused decode projection for M <= 8 rows (one launch per projection of a decode step):
+ *   prologue  norm_w != NULL: X <- RMSNorm(X) * norm_w (components.py:39-53)
+ *             swiglu != 0:    X is gu [M][2K], X <- bf16(silu(g)) * u (llama_ens5.py:213-214)
+ *   epilogue  residual | fp32 logits | rope_table != NULL (QKV projection, N = 3*H*128): RoPE of q, k
+ *             at position pos (or *pos_dev) and k, v written into cache[m, pos] (llama_ens5.py:118-127).
+ * Launched with programmatic dependent launch: weights are prefetched while the previous kernel of
+ * the stream drains. */
+int a3_decode_linear(const void* X, const void* W, void* Y, int M, int N, int K, long long ldx,
+                     long long ldw, long long ldy, const void* norm_w, float eps, int swiglu,
+                     const void* residual, long long ldr, int out_fp32, const float* rope_table,
+                     int n_heads, void* kcache, void* vcache, const int* pos_dev, int pos, int max_seq,
+                     void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Norms.  x,y bf16 [rows][D]; weights bf16; statistics fp32.
  * RMSNorm: reference model/accessory/model/components.py:39-53 -- y = bf16(x*rsqrt(mean(x^2)+eps)) * w
@@ -127,7 +140,9 @@ int a3_attn_bwd(const void* q, const void* k, const void* v, const void* o, cons
                 float scale, int causal, void* stream);
 /* Single-query decode attention over the KV cache (llama_ens5.py:121-129,142-167 with seqlen 1):
  * cache layout [B][max_seq][H][128] bf16; q [B][H*128]; ctx = number of valid positions. */
-/* pos_dev != NULL (CUDA-graph replay): ctx = *pos_dev + 1 is read on the device and `ctx` is only an
+/* scratch: B*H*(32*130 + 1) floats, ZERO-INITIALISED once by the caller (the tail holds per-(b,h)
+ * arrival counters that reset themselves; the last split to finish merges the partial results).
+ * pos_dev != NULL (CUDA-graph replay): ctx = *pos_dev + 1 is read on the device and `ctx` is only an
  * upper bound used to size the split. */
 int a3_attn_decode(const void* q, const void* kcache, const void* vcache, void* o, float* scratch,
                    int B, int H, int head_dim, int ctx, int max_seq, long long ldq, long long ldo,

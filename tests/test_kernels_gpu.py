@@ -257,7 +257,7 @@ def test_attn_decode_and_kv_append(ops, B, H, ctx):
     assert torch.equal(vc[:, :ctx].reshape(B * ctx, W), kv[:, 2 * W:])
     q = rnd(B, W)
     out = torch.empty(B, W, device=dev(), dtype=bf16)
-    scratch = torch.empty(B * H * 32 * 130, device=dev())
+    scratch = torch.zeros(B * H * (32 * 130 + 1), device=dev())
     scale = 1 / math.sqrt(hd)
     ops.attn_decode(q, kc, vc, out, scratch, B, H, hd, ctx, max_seq, scale)
     ref, _ = attn_ref(q.float().reshape(B, 1, H, hd), kc[:, :ctx].float(), vc[:, :ctx].float(), 0, scale)
@@ -289,10 +289,48 @@ def test_decode_rope_kv_and_device_pos(ops):
     # attention with the context length read from device memory == host-side ctx
     kc.copy_(rnd(B, max_seq, H, hd)); vc.copy_(rnd(B, max_seq, H, hd))
     o1, o2 = torch.empty(B, W, device=dev(), dtype=bf16), torch.empty(B, W, device=dev(), dtype=bf16)
-    scratch = torch.empty(B * H * 32 * 130, device=dev())
+    scratch = torch.zeros(B * H * (32 * 130 + 1), device=dev())
     ops.attn_decode(got[:, :W], kc, vc, o1, scratch, B, H, hd, pos + 1, max_seq, 0.088)
     ops.attn_decode(got[:, :W], kc, vc, o2, scratch, B, H, hd, max_seq, max_seq, 0.088, pos_dev=pos_dev)
     close_bf16(o2, o1, atol=2e-3)
+
+
+@pytest.mark.parametrize("M", [1, 3, 8])
+def test_decode_linear_fused(ops, M):
+    """One-launch decode projections: RMSNorm prologue, SwiGLU prologue, residual / fp32 epilogues and the
+    RoPE + KV-append epilogue, against the unfused kernels they replace."""
+    torch.manual_seed(40 + M)
+    H, hd, K, F, max_seq, pos = 2, 128, 256, 704, 32, 9
+    D = H * hd
+    x, nw = rnd(M, K), (1 + 0.1 * torch.randn(K, device=dev())).to(bf16)
+    wqkv, w2, res = rnd(3 * D, K, scale=0.06), rnd(K, F, scale=0.05), rnd(M, K)
+    table = ops.rope_table(128, 64, device=dev())
+    pos_dev = torch.tensor([pos], device=dev(), dtype=torch.int32)
+    # norm prologue + rope/append epilogue == rmsnorm -> linear -> decode_rope_kv
+    kc, vc = (torch.zeros(M, max_seq, H, hd, device=dev(), dtype=bf16) for _ in range(2))
+    kc2, vc2 = torch.zeros_like(kc), torch.zeros_like(vc)
+    ref = ops.linear_small_m(ops.rmsnorm_fwd(x, nw, 1e-5), wqkv)
+    ops.decode_rope_kv(ref, kc2, vc2, M, H, hd, table, pos, max_seq)
+    got = torch.empty_like(ref)
+    ops.decode_linear(x, wqkv, got, norm_w=nw, eps=1e-5, rope=table, n_heads=H, kcache=kc, vcache=vc,
+                      pos_dev=pos_dev, max_seq=max_seq)
+    close_bf16(got, ref, atol=4e-3)
+    close_bf16(kc, kc2, atol=4e-3)
+    close_bf16(vc, vc2, atol=4e-3)
+    assert torch.equal(kc[:, pos].reshape(M, D), got[:, D:2 * D]) and torch.equal(vc[:, pos].reshape(M, D), got[:, 2 * D:])
+    # swiglu prologue + residual == swiglu -> linear(+residual)
+    gu = rnd(M, 2 * F)
+    ref = ops.linear_small_m(ops.swiglu_fwd(gu), w2, residual=res)
+    got = torch.empty_like(ref)
+    ops.decode_linear(gu, w2, got, K=F, swiglu=True, residual=res)
+    close_bf16(got, ref, atol=4e-3)
+    # norm prologue + fp32 logits
+    wo = rnd(1000, K, scale=0.05)
+    ref = ops.linear_small_m(ops.rmsnorm_fwd(x, nw, 1e-5), wo, out_fp32=True)
+    got = torch.empty_like(ref)
+    ops.decode_linear(x, wo, got, norm_w=nw, eps=1e-5, out_fp32=True)
+    close_bf16(got, ref, atol=2e-3)
+    assert torch.equal(got, got.to(bf16).float())
 
 
 # ------------------------------------------------------------------------------------------- embed / ViT front
