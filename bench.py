@@ -331,7 +331,7 @@ def main():
             M = kw.get("M") or (a.shape[1] if a_mn else a.shape[0])
             K = kw.get("K") or (a.shape[0] if a_mn else a.shape[1])
             N = kw.get("N") or (b.shape[1] if b_mn else b.shape[0])
-            recs.append((e0, e1, 2.0 * M * N * K))
+            recs.append((e0, e1, 2.0 * M * N * K, (M, N, K, int(a_mn), int(b_mn))))
             return r
     if world > 1:
         dist.barrier()
@@ -345,8 +345,16 @@ def main():
         finally:
             E.ops.gemm = orig
         torch.cuda.synchronize()
-        tot_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in recs)
-        tot_fl = sum(f for _, _, f in recs)
+        tot_ms = sum(e0.elapsed_time(e1) for e0, e1, _, _ in recs)
+        tot_fl = sum(f for _, _, f, _ in recs)
+        if os.environ.get("A3_BENCH_GEMM_DETAIL"):
+            by = {}
+            for e0, e1, f, key in recs:
+                t = by.setdefault(key, [0, 0.0, 0.0])
+                t[0] += 1; t[1] += e0.elapsed_time(e1); t[2] += f
+            for key, (n, ms_, f) in sorted(by.items(), key=lambda kv: -kv[1][1]):
+                print(f"gemm M{key[0]} N{key[1]} K{key[2]} a_mn{key[3]} b_mn{key[4]}: n={n} total {ms_:.2f} ms, "
+                      f"{f / ms_ / 1e9:.0f} TFLOP/s", file=sys.stderr)
         ach = tot_fl / (tot_ms / 1e3) / 1e12
         roof = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05/TMEM/TMA)", "achieved": ach, "peak": pk["bf16"],
                 "unit": "TFLOP/s", "frac": ach / pk["bf16"], "peak_source": pk["src"] + " (burst; sustained %s)" % pk["bf16_sustained"],
