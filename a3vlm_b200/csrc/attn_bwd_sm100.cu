@@ -51,6 +51,7 @@ struct BwdParams {
   float* dq_acc;       // [B*T][H*128] fp32
   __nv_bfloat16* dk;
   __nv_bfloat16* dv;
+  const float2* rope;  // [T][64] (cos, sin) or null: fold the backward of apply_rotary_emb into dq / dk
   long long lddkv;
   int B, H, T;
   float scale;
@@ -295,6 +296,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tmem_ld_32x32(t_lane + C_DK + c * 32, d);
       tmem_ld_wait();
       if (key_ok) {
+        if (p.rope) {  // dK was taken w.r.t. the rotated keys: rotate back by -angle(key position)
+          const float2* tp = p.rope + (long long)key * (BW_HD / 2) + c * 16;
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float2 cs = __ldg(tp + (i >> 1));
+            const float x = __uint_as_float(d[i]), y = __uint_as_float(d[i + 1]);
+            d[i] = __float_as_uint(x * cs.x + y * cs.y);
+            d[i + 1] = __float_as_uint(y * cs.x - x * cs.y);
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
           uint4 q;
@@ -353,14 +364,24 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o,
 
 // dq (bf16, strided) = dq_acc (fp32, dense [B*T][H*128])
 __global__ void attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq,
-                                       long long rows, int width, long long lddq) {
+                                       long long rows, int width, long long lddq,
+                                       const float2* __restrict__ rope, int T) {
   const int cpr = width / 8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < rows * cpr;
        i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / cpr;
     const int c = (int)(i - r * cpr);
-    const float4 a = *reinterpret_cast<const float4*>(acc + r * width + c * 8);
-    const float4 b = *reinterpret_cast<const float4*>(acc + r * width + c * 8 + 4);
+    float4 a = *reinterpret_cast<const float4*>(acc + r * width + c * 8);
+    float4 b = *reinterpret_cast<const float4*>(acc + r * width + c * 8 + 4);
+    if (rope) {  // inverse rotation at position r % T, pairs ((c*8) % 128) / 2 ...
+      const float2* tp = rope + (r % T) * (BW_HD / 2) + (((c * 8) & (BW_HD - 1)) >> 1);
+      const float2 c0 = __ldg(tp), c1 = __ldg(tp + 1), c2 = __ldg(tp + 2), c3 = __ldg(tp + 3);
+      float t;
+      t = a.x * c0.x + a.y * c0.y; a.y = a.y * c0.x - a.x * c0.y; a.x = t;
+      t = a.z * c1.x + a.w * c1.y; a.w = a.w * c1.x - a.z * c1.y; a.z = t;
+      t = b.x * c2.x + b.y * c2.y; b.y = b.y * c2.x - b.x * c2.y; b.x = t;
+      t = b.z * c3.x + b.w * c3.y; b.w = b.w * c3.x - b.z * c3.y; b.z = t;
+    }
     uint4 q;
     q.x = pack_bf16x2(a.x, a.y);
     q.y = pack_bf16x2(a.z, a.w);
@@ -375,7 +396,8 @@ __global__ void attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloa
 extern "C" int a3_attn_bwd(const void* q, const void* k, const void* v, const void* o,
                            const void* dout, const float* lse, float* delta, float* dq_acc, void* dq,
                            void* dk, void* dv, int B, int H, int T, int head_dim, long long ldqkv,
-                           long long ldo, long long lddqkv, float scale, int causal, void* stream) {
+                           long long ldo, long long lddqkv, float scale, int causal,
+                           const float* rope_table, void* stream) {
   using namespace a3;
   if (B <= 0 || H <= 0 || T <= 0) return A3_OK;
   if (head_dim != BW_HD) return set_error(A3_ERR_UNSUPPORTED, "a3_attn_bwd: head_dim must be 128");
@@ -427,6 +449,7 @@ extern "C" int a3_attn_bwd(const void* q, const void* k, const void* v, const vo
   p.dk = reinterpret_cast<__nv_bfloat16*>(dk);
   p.dv = reinterpret_cast<__nv_bfloat16*>(dv);
   p.lddkv = lddqkv;
+  p.rope = reinterpret_cast<const float2*>(rope_table);
   p.B = B; p.H = H; p.T = T;
   p.scale = scale;
   p.causal = causal ? 1 : 0;
@@ -438,6 +461,7 @@ extern "C" int a3_attn_bwd(const void* q, const void* k, const void* v, const vo
   long long blocks = (rows * (width / 8) + 255) / 256;
   if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
   attn_dq_convert_kernel<<<(unsigned)blocks, 256, 0, s>>>(dq_acc, reinterpret_cast<__nv_bfloat16*>(dq),
-                                                          rows, width, lddqkv);
+                                                          rows, width, lddqkv,
+                                                          reinterpret_cast<const float2*>(rope_table), T);
   return check_launch("a3_attn_bwd(dq)");
 }

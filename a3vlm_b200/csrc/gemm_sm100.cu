@@ -41,6 +41,17 @@ struct GemmParams {
   int accumulate;
   float alpha;
   int group_m;  // M-blocks per rasterisation group
+  // fused gated-SiLU modes (llama_ens5.py:213-217):
+  //   swiglu_F > 0 (CTA-pair kernel only): B = [w1; w3] ([2F][K]); CTA 0 of the pair loads 128 rows of
+  //     w1, CTA 1 the same 128 rows of w3, so one accumulator tile holds g | u of 128 features; the
+  //     epilogue writes gu (C, [M][2F]) and y = bf16(bf16(silu(g)) * u) (C2, [M][F]).
+  //   dswiglu_gu != null: the GEMM computes dy = d W2 (N = F); the epilogue turns it into
+  //     dgu = (dg | du) ([M][2F], C) from the saved gu -- dy never touches HBM.
+  int swiglu_F;
+  __nv_bfloat16* C2;
+  long long ldc2;
+  const __nv_bfloat16* dswiglu_gu;
+  long long ldgu;
 };
 
 template <int BN>
@@ -75,8 +86,98 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 
 // Epilogue of one accumulator tile for the 32 rows a warp owns: TMEM -> registers -> fused
 // alpha / bias / activation / RoPE / residual / accumulate -> global (bf16 or fp32).
+__device__ __forceinline__ void load8f(const __nv_bfloat16* ptr, float (&f)[8]) {
+  const uint4 q = *reinterpret_cast<const uint4*>(ptr);
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float2 v = unpack_bf16x2(w[t]);
+    f[2 * t] = v.x;
+    f[2 * t + 1] = v.y;
+  }
+}
+__device__ __forceinline__ void store8f(__nv_bfloat16* ptr, const float* f) {
+  uint4 o;
+  o.x = pack_bf16x2(f[0], f[1]);
+  o.y = pack_bf16x2(f[2], f[3]);
+  o.z = pack_bf16x2(f[4], f[5]);
+  o.w = pack_bf16x2(f[6], f[7]);
+  *reinterpret_cast<uint4*>(ptr) = o;
+}
+
+// Backward of the gated SiLU fused behind the w2 dgrad: acc = dy tile; dg = bf16(dy*u) * silu'(g),
+// du = dy * bf16(silu(g))  (same rounding points as the stand-alone a3_swiglu_bwd).
+template <int BN>
+__device__ __forceinline__ void epilogue_dswiglu_rows(const GemmParams& p, uint32_t t_row, int row, int n0) {
+  const bool row_ok = row < p.M;
+  const int F = p.N;
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    uint32_t r[32];
+    tmem_ld_32x32(t_row + c * 32, r);
+    tmem_ld_wait();
+    const int col0 = n0 + c * 32;
+    if (row_ok && col0 < F) {
+      const __nv_bfloat16* gp = p.dswiglu_gu + static_cast<long long>(row) * p.ldgu + col0;
+      __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<long long>(row) * p.ldc + col0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        if (col0 + j < F) {
+          float g[8], u[8], dg[8], du[8];
+          load8f(gp + j, g);
+          load8f(gp + F + j, u);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float dy = bf16_round(__uint_as_float(r[j + e]) * p.alpha);
+            const float sig = 1.f / (1.f + __expf(-g[e]));
+            dg[e] = bf16_round(dy * u[e]) * sig * (1.f + g[e] * (1.f - sig));
+            du[e] = dy * bf16_round(g[e] * sig);
+          }
+          store8f(op + j, dg);
+          store8f(op + F + j, du);
+        }
+      }
+    }
+  }
+}
+
+// Forward gated SiLU fused behind the w1 | w3 projection (CTA-pair kernel, swiglu_F mode): columns
+// [0,128) of the accumulator tile are g, [128,256) are u of features f0 .. f0+127.
+__device__ __forceinline__ void epilogue_swiglu_rows(const GemmParams& p, uint32_t t_row, int row, int f0) {
+  const bool row_ok = row < p.M;
+  const int F = p.swiglu_F;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t rg[32], ru[32];
+    tmem_ld_32x32(t_row + c * 32, rg);
+    tmem_ld_32x32(t_row + 128 + c * 32, ru);
+    tmem_ld_wait();
+    if (row_ok) {
+      __nv_bfloat16* gp = reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<long long>(row) * p.ldc + f0 + c * 32;
+      __nv_bfloat16* yp = p.C2 + static_cast<long long>(row) * p.ldc2 + f0 + c * 32;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        float g[8], u[8], y[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          g[e] = bf16_round(__uint_as_float(rg[j + e]));
+          u[e] = bf16_round(__uint_as_float(ru[j + e]));
+          y[e] = bf16_round(g[e] / (1.f + __expf(-g[e]))) * u[e];
+        }
+        store8f(gp + j, g);
+        store8f(gp + F + j, u);
+        store8f(yp + j, y);
+      }
+    }
+  }
+}
+
 template <int BN>
 __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t t_row, int row, int n0) {
+  if (p.dswiglu_gu) {
+    epilogue_dswiglu_rows<BN>(p, t_row, row, n0);
+    return;
+  }
   const bool row_ok = row < p.M;
 #pragma unroll 1
   for (int c = 0; c < BN / 32; ++c) {
@@ -378,7 +479,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const bool leader = rank == 0;
 
   const int m_blocks = (p.M + 2 * BM - 1) / (2 * BM);
-  const int n_blocks = (p.N + BN - 1) / BN;
+  const int n_blocks = p.swiglu_F ? p.swiglu_F / BNH : (p.N + BN - 1) / BN;
   const int k_blocks = (p.K + BK - 1) / BK;
   const int num_tiles = m_blocks * n_blocks;
   const int first_tile = blockIdx.x >> 1, tile_step = gridDim.x >> 1;
@@ -416,7 +517,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         int mb, nb;
         tile_coords(tile, m_blocks, n_blocks, p.group_m, mb, nb);
-        const int m0 = mb * (2 * BM) + rank * BM, n0 = nb * BN + rank * BNH;
+        const int m0 = mb * (2 * BM) + rank * BM;
+        // B rows of this CTA: its half of the 256-wide tile, or (gated-SiLU mode) 128 rows of w1 / w3
+        const int n0 = p.swiglu_F ? nb * BNH + rank * p.swiglu_F : nb * BN + rank * BNH;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S::STAGE_BYTES;
@@ -489,7 +592,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(&tmem_full[acc_stage], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc_stage * BN;
-      epilogue_rows<BN>(p, t_row, row, n0);
+      if (p.swiglu_F) epilogue_swiglu_rows(p, t_row, row, nb * BNH);
+      else epilogue_rows<BN>(p, t_row, row, n0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(&tmem_empty[acc_stage], 0));
@@ -544,7 +648,8 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ge
     if (e != cudaSuccess) return set_error(A3_ERR_CUDA, cudaGetErrorString(e));
     configured = true;
   }
-  const int m_blocks = (p.M + 2 * BM - 1) / (2 * BM), n_blocks = (p.N + S::BN - 1) / S::BN;
+  const int m_blocks = (p.M + 2 * BM - 1) / (2 * BM);
+  const int n_blocks = p.swiglu_F ? p.swiglu_F / S::BNH : (p.N + S::BN - 1) / S::BN;
   const int tiles = m_blocks * n_blocks;
   const int pairs = num_sms() / 2;
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
@@ -620,7 +725,61 @@ extern "C" int a3_gemm_bf16(const void* A, const void* B, void* C, int M, int N,
   p.accumulate = accumulate ? 1 : 0;
   p.alpha = alpha;
   p.group_m = 16;
+  p.swiglu_F = 0; p.C2 = nullptr; p.ldc2 = 0; p.dswiglu_gu = nullptr; p.ldgu = 0;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (pair) return launch_gemm2(tmA, tmB, p, s);
   return bn == 128 ? launch_gemm<128>(tmA, tmB, p, s) : launch_gemm<256>(tmA, tmB, p, s);
+}
+
+static void init_params(a3::GemmParams& p, int M, int N, int K) {
+  p.C = nullptr; p.bias = nullptr; p.residual = nullptr; p.rope = nullptr; p.ldc = 0; p.ldr = 0;
+  p.rope_cols = 0; p.rope_period = 1; p.rope_pos0 = 0; p.M = M; p.N = N; p.K = K; p.a_mn = 0; p.b_mn = 0;
+  p.act = 0; p.out_fp32 = 0; p.accumulate = 0; p.alpha = 1.f; p.group_m = 16; p.swiglu_F = 0; p.C2 = nullptr;
+  p.ldc2 = 0; p.dswiglu_gu = nullptr; p.ldgu = 0;
+}
+
+extern "C" int a3_gemm_swiglu_bf16(const void* X, const void* W13, void* GU, void* Y, int M, int F, int K,
+                                   long long ldx, long long ldw, long long ldgu, long long ldy,
+                                   void* stream) {
+  using namespace a3;
+  if (M <= 0 || F <= 0 || K <= 0) return A3_OK;
+  if (!X || !W13 || !GU || !Y) return set_error(A3_ERR_ARG, "a3_gemm_swiglu_bf16: null operand");
+  if ((F & 127) || (ldx & 7) || (ldw & 7) || (ldgu & 7) || (ldy & 7) ||
+      ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(W13) | reinterpret_cast<uintptr_t>(GU) |
+        reinterpret_cast<uintptr_t>(Y)) & 15))
+    return set_error(A3_ERR_ARG, "a3_gemm_swiglu_bf16: F % 128 == 0, strides % 8 == 0, 16-byte aligned pointers");
+  CUtensorMap tmA, tmB;
+  int rc = encode_operand_map(&tmA, X, M, K, ldx, 0, BM);
+  if (rc != A3_OK) return rc;
+  rc = encode_operand_map(&tmB, W13, 2 * F, K, ldw, 0, 128);
+  if (rc != A3_OK) return rc;
+  GemmParams p;
+  init_params(p, M, 2 * F, K);
+  p.C = GU; p.ldc = ldgu; p.C2 = reinterpret_cast<__nv_bfloat16*>(Y); p.ldc2 = ldy; p.swiglu_F = F;
+  return launch_gemm2(tmA, tmB, p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int a3_gemm_dswiglu_bf16(const void* D, const void* W2, const void* GU, void* DGU, int M, int F,
+                                    int Dm, long long ldd, long long ldw, long long ldgu, long long lddgu,
+                                    void* stream) {
+  using namespace a3;
+  if (M <= 0 || F <= 0 || Dm <= 0) return A3_OK;
+  if (!D || !W2 || !GU || !DGU) return set_error(A3_ERR_ARG, "a3_gemm_dswiglu_bf16: null operand");
+  if ((F & 7) || (ldd & 7) || (ldw & 7) || (ldgu & 7) || (lddgu & 7) ||
+      ((reinterpret_cast<uintptr_t>(D) | reinterpret_cast<uintptr_t>(W2) | reinterpret_cast<uintptr_t>(GU) |
+        reinterpret_cast<uintptr_t>(DGU)) & 15))
+    return set_error(A3_ERR_ARG, "a3_gemm_dswiglu_bf16: F % 8 == 0, strides % 8 == 0, 16-byte aligned pointers");
+  // dy[M][F] = D[M][Dm] * W2[Dm][F]: A K-major, B MN-major (W2 is stored [K = Dm][N = F])
+  const bool pair = M >= 256 && F >= 256;
+  CUtensorMap tmA, tmB;
+  int rc = encode_operand_map(&tmA, D, M, Dm, ldd, 0, BM);
+  if (rc != A3_OK) return rc;
+  rc = encode_operand_map(&tmB, W2, F, Dm, ldw, 1, pair ? 128 : 256);
+  if (rc != A3_OK) return rc;
+  GemmParams p;
+  init_params(p, M, F, Dm);
+  p.b_mn = 1; p.C = DGU; p.ldc = lddgu;
+  p.dswiglu_gu = reinterpret_cast<const __nv_bfloat16*>(GU); p.ldgu = ldgu;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  return pair ? launch_gemm2(tmA, tmB, p, s) : launch_gemm<256>(tmA, tmB, p, s);
 }

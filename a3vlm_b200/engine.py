@@ -189,6 +189,7 @@ class Engine:
         if self.head_dim != 128:
             raise NotImplementedError("decoder head_dim must be 128 (7B / 13B)")
         self.ffn_dim = ffn_hidden_dim(a.dim, a.multiple_of, a.ffn_dim_multiplier)
+        self.fuse_swiglu = self.ffn_dim % 128 == 0
         self.n_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         self.rope = ops.rope_table(self.head_dim, a.max_seq_len * 2, a.rope_theta, device=self.device)
         self.image_words = (vis.tokens + 2) if vis is not None else 0
@@ -357,8 +358,11 @@ class Engine:
             ops.attn_fwd(q, k, v, B, a.n_heads, L, L, self.head_dim, self.scale, True, out=o, lse=lse)
         ops.gemm(o, w[p + "attention.wo.weight"], h, residual=x)
         ops.rmsnorm_fwd(h, w[p + "ffn_norm.weight"], a.norm_eps, out=hn, rstd=rstd2)
-        ops.gemm(hn, w[p + "w13"], gu)
-        ops.swiglu_fwd(gu, y)
+        if self.fuse_swiglu:  # gate fused into the w1|w3 projection's epilogue (one launch, y never re-read)
+            ops.gemm_swiglu(hn, w[p + "w13"], gu, y)
+        else:
+            ops.gemm(hn, w[p + "w13"], gu)
+            ops.swiglu_fwd(gu, y)
         ops.gemm(y, w[p + "feed_forward.w2.weight"], out, residual=h)
 
     # ------------------------------------------------------------------------------------ training forward
@@ -422,8 +426,11 @@ class Engine:
         for i in reversed(range(NL)):
             p = f"layers.{i}."
             wg(d, ws.y[i], g[p + "feed_forward.w2.weight"])
-            dg(d, w[p + "feed_forward.w2.weight"], ws.dy)
-            ops.swiglu_bwd(ws.gu[i], ws.dy, ws.dgu)
+            if self.fuse_swiglu:  # gate backward fused behind the w2 dgrad: dy stays in TMEM / registers
+                ops.gemm_dswiglu(d, w[p + "feed_forward.w2.weight"], ws.gu[i], ws.dgu)
+            else:
+                dg(d, w[p + "feed_forward.w2.weight"], ws.dy)
+                ops.swiglu_bwd(ws.gu[i], ws.dy, ws.dgu)
             wg(ws.dgu, ws.hn[i], g[p + "w13"])
             dg(ws.dgu, w[p + "w13"], t)
             ops.rmsnorm_bwd(t, ws.h[i], w[p + "ffn_norm.weight"], ws.rstd2[i], d, ws.part2, add_to_dx=True)
@@ -433,8 +440,7 @@ class Engine:
             qkv, dqkv = ws.qkv[i], ws.dqkv
             ops.attn_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], ws.o[i], t, ws.lse[i], ws.delta, ws.dq_acc,
                          dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], B, a.n_heads, L, self.head_dim,
-                         self.scale, True)
-            ops.rope_apply(dqkv[:, :2 * D], 2 * a.n_heads, self.head_dim, self.rope, L, 0, inverse=True)
+                         self.scale, True, rope=self.rope)  # backward of RoPE fused into the dq / dk stores
             wg(dqkv, ws.xn[i], g[p + "wqkv"])
             dg(dqkv, w[p + "wqkv"], t)
             ops.rmsnorm_bwd(t, ws.x[i], w[p + "attention_norm.weight"], ws.rstd1[i], d, ws.part2, add_to_dx=True)

@@ -72,6 +72,26 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
     return out
 
 
+def gemm_swiglu(x, w13, gu, y):
+    """gu = x @ w13^T ([M][2F], g | u) and y = bf16(silu(g)) * u in one tcgen05 launch."""
+    M, K = x.shape
+    F = w13.shape[0] // 2
+    rc = _L().a3_gemm_swiglu_bf16(_p(x), _p(w13), _p(gu), _p(y), M, F, K, x.stride(0), w13.stride(0),
+                                  gu.stride(0), y.stride(0), _st())
+    _lib.check(rc, "a3_gemm_swiglu_bf16")
+    return gu, y
+
+
+def gemm_dswiglu(d, w2, gu, dgu):
+    """dgu = swiglu_bwd(gu, d @ w2) with w2 stored [Dm][F]; dy stays on chip."""
+    M, Dm = d.shape
+    F = w2.shape[1]
+    rc = _L().a3_gemm_dswiglu_bf16(_p(d), _p(w2), _p(gu), _p(dgu), M, F, Dm, d.stride(0), w2.stride(0),
+                                   gu.stride(0), dgu.stride(0), _st())
+    _lib.check(rc, "a3_gemm_dswiglu_bf16")
+    return dgu
+
+
 def linear_small_m(x, w, out=None, residual=None, out_fp32=False):
     M, K = x.shape
     N = w.shape[0]
@@ -189,12 +209,12 @@ def attn_fwd(q, k, v, B, H, Tq, Tk, head_dim, scale, causal, out=None, lse=None,
     return out
 
 
-def attn_bwd(q, k, v, o, dout, lse, delta, dq_acc, dq, dk, dv, B, H, T, head_dim, scale, causal):
+def attn_bwd(q, k, v, o, dout, lse, delta, dq_acc, dq, dk, dv, B, H, T, head_dim, scale, causal, rope=None):
     assert q.stride(0) == k.stride(0) == v.stride(0)
     assert dq.stride(0) == dk.stride(0) == dv.stride(0)
     rc = _L().a3_attn_bwd(_p(q), _p(k), _p(v), _p(o), _p(dout), _p(lse), _p(delta), _p(dq_acc), _p(dq),
                           _p(dk), _p(dv), B, H, T, head_dim, q.stride(0), o.stride(0), dq.stride(0),
-                          float(scale), int(causal), _st())
+                          float(scale), int(causal), _p(rope), _st())
     _lib.check(rc, "a3_attn_bwd")
 
 

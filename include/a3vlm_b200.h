@@ -64,6 +64,17 @@ int a3_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, lon
                  float alpha, const void* rope_table, int rope_cols, int rope_period, int rope_pos0,
                  void* stream);
 
+/* Gated-SiLU MLP with the activation fused into the tensor-core kernels (llama_ens5.py:213-217):
+ *   a3_gemm_swiglu_bf16:  gu[M][2F] = X[M][K] W13[2F][K]^T (W13 = w1 rows then w3 rows) AND
+ *                         y[M][F] = bf16(bf16(silu(g)) * u) in one launch (the CTA pair loads 128 rows of
+ *                         w1 and the matching 128 rows of w3, so g and u of a feature share a tile).
+ *   a3_gemm_dswiglu_bf16: dgu[M][2F] = swiglu'(gu) applied to dy = D[M][Dm] W2[Dm][F] -- the backward
+ *                         of the gate fused behind the w2 dgrad; dy is never written to HBM. */
+int a3_gemm_swiglu_bf16(const void* X, const void* W13, void* GU, void* Y, int M, int F, int K,
+                        long long ldx, long long ldw, long long ldgu, long long ldy, void* stream);
+int a3_gemm_dswiglu_bf16(const void* D, const void* W2, const void* GU, void* DGU, int M, int F, int Dm,
+                         long long ldd, long long ldw, long long ldgu, long long lddgu, void* stream);
+
 /* Weight-streaming GEMV-shaped linear for decode: Y[M,N] = X[M,K] W[N,K]^T (+residual), M <= 16.
  * HBM-bound (reads W once).  out_fp32 for the LM head (llama_ens5.py:530-531). */
 int a3_linear_small_m(const void* X, const void* W, void* Y, int M, int N, int K, long long ldx,
@@ -133,11 +144,13 @@ int a3_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse
                 long long ldo, long long q_bstride, long long kv_bstride, float scale, int causal,
                 void* stream);
 /* Backward of the above for Tq == Tk, head_dim 128 (fine-tune path).  delta [B][H][T] fp32 scratch,
- * dq_acc [B*T][H*128] fp32 scratch (zeroed by the call); dq/dk/dv share the q/k/v layout. */
+ * dq_acc [B*T][H*128] fp32 scratch (zeroed by the call); dq/dk/dv share the q/k/v layout.
+ * rope_table != NULL: q and k were rotated by apply_rotary_emb at positions 0..T-1 (llama_ens5.py:118);
+ * dq and dk are returned w.r.t. the UN-rotated projections (rotation by -angle fused into the stores). */
 int a3_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout,
                 const float* lse, float* delta, float* dq_acc, void* dq, void* dk, void* dv, int B,
                 int H, int T, int head_dim, long long ldqkv, long long ldo, long long lddqkv,
-                float scale, int causal, void* stream);
+                float scale, int causal, const float* rope_table, void* stream);
 /* Single-query decode attention over the KV cache (llama_ens5.py:121-129,142-167 with seqlen 1):
  * cache layout [B][max_seq][H][128] bf16; q [B][H*128]; ctx = number of valid positions. */
 /* scratch: B*H*(32*130 + 1) floats, ZERO-INITIALISED once by the caller (the tail holds per-(b,h)

@@ -186,6 +186,26 @@ def test_swiglu(ops):
     close_bf16(dgu[:, F:], uf.grad, rtol=2 ** -6, atol=2e-2)
 
 
+@pytest.mark.parametrize("M", [200, 835])
+def test_gemm_fused_swiglu_fwd_bwd(ops, M):
+    """The gate fused into the tcgen05 epilogues == the unfused kernel sequences it replaces."""
+    torch.manual_seed(M)
+    K, F = 256, 640
+    x, w13, w2, d = rnd(M, K), rnd(2 * F, K, scale=0.06), rnd(K, F, scale=0.05), rnd(M, K)
+    gu_ref = ops.gemm(x, w13)
+    y_ref = ops.swiglu_fwd(gu_ref)
+    gu, y = torch.empty_like(gu_ref), torch.empty_like(y_ref)
+    ops.gemm_swiglu(x, w13, gu, y)
+    close_bf16(gu, gu_ref, atol=2e-3)  # same MMAs, different tile shape -> same values up to accumulation order
+    close_bf16(y, ops.swiglu_fwd(gu), rtol=0, atol=0)  # y is exactly the gate of the gu it wrote
+    dy = ops.gemm(d, w2, b_mn=True)
+    dgu_ref = torch.empty_like(gu)
+    ops.swiglu_bwd(gu, dy, dgu_ref)
+    dgu = torch.empty_like(gu)
+    ops.gemm_dswiglu(d, w2, gu, dgu)
+    close_bf16(dgu, dgu_ref, rtol=2 ** -6, atol=4e-3)
+
+
 # ------------------------------------------------------------------------------------------- attention
 def attn_ref(q, k, v, causal, scale):
     # q [B,Tq,H,d], k/v [B,Tk,H,d] fp32; right-aligned causal (llama_ens5.py:181-185)
@@ -238,12 +258,23 @@ def test_attn_bwd(ops, B, H, T, causal):
     dq_acc = torch.empty(B * T, W, device=dev())
     ops.attn_bwd(q, k, v, o, dout, lse, delta, dq_acc, dqkv[:, :W], dqkv[:, W:2 * W], dqkv[:, 2 * W:], B, H, T,
                  hd, scale, causal)
-    for name, got, g in [("dq", dqkv[:, :W], qf.grad), ("dk", dqkv[:, W:2 * W], kf.grad), ("dv", dqkv[:, 2 * W:], vf.grad)]:
-        got, g = got.float().reshape(B, T, H, hd), g
-        err = (got - g).abs().max().item()
-        assert err <= 2e-2 * max(1.0, g.abs().max().item()), (name, err, g.abs().max().item())
-        rel = ((got - g).norm() / g.norm()).item()
-        assert rel < 1e-2, (name, rel)
+    def cmp(dqkv, refs):
+        for name, got, g in zip(("dq", "dk", "dv"), (dqkv[:, :W], dqkv[:, W:2 * W], dqkv[:, 2 * W:]), refs):
+            got = got.float().reshape(B, T, H, hd)
+            err = (got - g).abs().max().item()
+            assert err <= 2e-2 * max(1.0, g.abs().max().item()), (name, err, g.abs().max().item())
+            rel = ((got - g).norm() / g.norm()).item()
+            assert rel < 1e-2, (name, rel)
+
+    cmp(dqkv, (qf.grad, kf.grad, vf.grad))
+    # fused backward of apply_rotary_emb: dq, dk rotated by -angle(position) == a3_rope_apply(inverse)
+    table = ops.rope_table(128, 1024, device=dev())
+    d2 = torch.full_like(qkv, float("nan"))
+    ops.attn_bwd(q, k, v, o, dout, lse, delta, dq_acc, d2[:, :W], d2[:, W:2 * W], d2[:, 2 * W:], B, H, T, hd, scale,
+                 causal, rope=table)
+    ref = dqkv.clone()
+    ops.rope_apply(ref[:, :2 * W], 2 * H, hd, table, T, 0, inverse=True)
+    close_bf16(d2, ref, rtol=2 ** -6, atol=2e-2 * max(1.0, ref.float().abs().max().item()) * 0.25)
 
 
 @pytest.mark.parametrize("B,H,ctx", [(1, 32, 836), (4, 4, 17), (2, 2, 1)])
