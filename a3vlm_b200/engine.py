@@ -43,13 +43,21 @@ def ffn_hidden_dim(dim: int, multiple_of: int, ffn_dim_multiplier) -> int:
 def build_layout(args, vis):
     """Pure function (no device): the ordered (name, shape) lists of the flat buffers.
     Returns (decay, nodecay, frozen, kpad).  Trainable order = decay + nodecay:
-      tok_embeddings | per layer: wqkv, wo, w13, w2 | output | visual_proj.{0,1}.weight, start/end_img ||
+      visual_proj.{0,1}.weight, start/end_img | tok_embeddings | per layer: wqkv, wo, w13, w2 | output ||
       per layer: attention_norm, ffn_norm | norm | visual_proj.{0,1}.bias
-    wq|wk|wv and w1|w3 are adjacent rows of one matrix, so the reference-named parameters are views."""
+    i.e. in the order the forward consumes them (the sharded optimiser broadcasts updated shards in that
+    order while the next forward is already running).  wq|wk|wv and w1|w3 are adjacent rows of one
+    matrix, so the reference-named parameters are views.  `||` = decay / no-decay boundary."""
     D, V = args.dim, args.vocab_size
     F = ffn_hidden_dim(D, args.multiple_of, args.ffn_dim_multiplier)
-    decay: List[Tuple[str, Tuple[int, ...]]] = [("tok_embeddings.weight", (V, D))]
+    decay: List[Tuple[str, Tuple[int, ...]]] = []
     nodecay: List[Tuple[str, Tuple[int, ...]]] = []
+    if vis is not None:
+        # visual_proj.1 is a LayerNorm, but its weight's NAME does not end in "norm.weight", so the
+        # reference's add_weight_decay (M/util/misc.py:591) puts it in the decay group -- kept faithfully
+        decay += [("visual_proj.0.weight", (D, vis.width)), ("visual_proj.1.weight", (D,)),
+                  ("start_img", (1, 1, D)), ("end_img", (1, 1, D))]
+    decay.append(("tok_embeddings.weight", (V, D)))
     for i in range(args.n_layers):
         p = f"layers.{i}."
         decay += [(p + "wqkv", (3 * D, D)), (p + "attention.wo.weight", (D, D)),
@@ -63,10 +71,6 @@ def build_layout(args, vis):
         v, c = vis, "clip.visual."
         Wv = v.width
         kpad = (3 * v.patch * v.patch + 7) // 8 * 8
-        # visual_proj.1 is a LayerNorm, but its weight's NAME does not end in "norm.weight", so the
-        # reference's add_weight_decay (M/util/misc.py:591) puts it in the decay group -- kept faithfully
-        decay += [("visual_proj.0.weight", (D, Wv)), ("visual_proj.1.weight", (D,)), ("start_img", (1, 1, D)),
-                  ("end_img", (1, 1, D))]
         nodecay += [("visual_proj.0.bias", (D,)), ("visual_proj.1.bias", (D,))]
         frozen += [(c + "conv1.weight", (Wv, 3, v.patch, v.patch)), (c + "conv1_padded", (Wv, kpad)),
                    (c + "class_embedding", (Wv,)), (c + "positional_embedding", (v.tokens, Wv)),
@@ -83,26 +87,37 @@ def build_layout(args, vis):
     return decay, nodecay, frozen, kpad
 
 
-def flat_offsets(layout, align: int = 64):
-    """name -> (offset, numel, shape) with every tensor starting on a 128-byte boundary; total."""
+SHARD_ALIGN = 512  # 8 ranks x 64 elements: the decay region splits evenly over 1 / 2 / 4 / 8 ranks
+
+
+def flat_offsets(layout, align: int = 64, segment_after: Optional[str] = None):
+    """name -> (offset, numel, shape) with every tensor starting on a 128-byte boundary; total.
+    After `segment_after` (the last decay parameter) the offset is rounded up to SHARD_ALIGN so the
+    decay region can be sharded evenly across data-parallel ranks."""
     offsets: Dict[str, Tuple[int, int, Tuple[int, ...]]] = {}
     off = 0
     for name, shape in layout:
         n = int(math.prod(shape))
         offsets[name] = (off, n, tuple(shape))
         off += (n + align - 1) // align * align
+        if name == segment_after:
+            off = (off + SHARD_ALIGN - 1) // SHARD_ALIGN * SHARD_ALIGN
     return offsets, off
 
 
 def bucket_plan(offsets, numel: int, n_layers: int):
     """Flat element ranges in the order the backward completes them (the all-reduce buckets):
-    LM head, decoder layers last to first, embedding, then everything after the LM head
-    (projector, tags, all norm weights).  Together they tile [0, numel) exactly once."""
+    LM head, decoder layers last to first, then projector + tags + embedding (the head of the buffer),
+    then everything after the LM head (all norm weights, projector biases).  Together they tile
+    [0, numel) exactly once."""
     rng = lambda n: (offsets[n][0], offsets[n][0] + offsets[n][1])
     plan = [rng("output.weight")]
+    prev_lo = rng("output.weight")[0]
     for i in reversed(range(n_layers)):
-        plan.append((rng(f"layers.{i}.wqkv")[0], rng(f"layers.{i}.feed_forward.w2.weight")[1]))
-    plan.append((0, rng("tok_embeddings.weight")[1]))
+        lo = rng(f"layers.{i}.wqkv")[0]
+        plan.append((lo, prev_lo))  # up to the next bucket's start: alignment padding is covered once
+        prev_lo = lo
+    plan.append((0, prev_lo))
     plan.append((rng("output.weight")[1], numel))
     return plan
 
@@ -111,8 +126,9 @@ class FlatParams:
     """Flat bf16 storage for a set of named parameters.  `layout` is an ordered list of
     (name, shape); views[name] aliases the flat buffer."""
 
-    def __init__(self, layout: List[Tuple[str, Tuple[int, ...]]], device, align: int = 64):
-        self.offsets, off = flat_offsets(layout, align)
+    def __init__(self, layout: List[Tuple[str, Tuple[int, ...]]], device, align: int = 64,
+                 segment_after: Optional[str] = None):
+        self.offsets, off = flat_offsets(layout, align, segment_after)
         self.numel = off
         self.flat = torch.zeros(max(off, align), device=device, dtype=bf16)
         self.views = {n: self.flat[o:o + k].view(s) for n, (o, k, s) in self.offsets.items()}
@@ -206,12 +222,17 @@ class Engine:
         self.dec = None
         self.use_decode_graph = True
         self.comm_stream = None
+        # sharded optimiser (ZeRO-1 style, enable_sharded_optimizer): this rank's slice of the decay region
+        self.shard_group, self.shard_world, self.shard_rank = None, 1, 0
+        self.shard_ready: List = []     # per shard: event recorded after its broadcast (None = already waited)
+        self._waited_upto = None        # flat offset up to which the compute stream has waited
 
     # ------------------------------------------------------------------------------------ layouts
     def _build_layouts(self):
         decay, nodecay, frozen, self.kpad = build_layout(self.args, self.vis)
-        self.w = FlatParams(decay + nodecay, self.device)
-        self.decay_numel = self.w.offsets[nodecay[0][0]][0]  # no-decay region starts here
+        self._segment_after = decay[-1][0]
+        self.w = FlatParams(decay + nodecay, self.device, segment_after=self._segment_after)
+        self.decay_numel = self.w.offsets[nodecay[0][0]][0]  # no-decay region starts here (multiple of 512)
         self.fz = FlatParams(frozen, self.device) if frozen else None
         self.g: Optional[FlatParams] = None  # gradients: allocated on first training use
         self._layout = decay + nodecay
@@ -299,7 +320,7 @@ class Engine:
 
     def _ensure_grads(self):
         if self.g is None:
-            self.g = FlatParams(self._layout, self.device)
+            self.g = FlatParams(self._layout, self.device, segment_after=self._segment_after)
 
     # ------------------------------------------------------------------------------------ ViT + projector
     def vit_forward(self, image: torch.Tensor, vw) -> torch.Tensor:
@@ -333,6 +354,7 @@ class Engine:
             ops.gemm(fc, f[r + "mlp.c_proj.weight"], x, bias=f[r + "mlp.c_proj.bias"], residual=x)
         ops.layernorm_fwd(x, f[c + "ln_post.weight"], f[c + "ln_post.bias"], v.ln_eps, out=vw["feats"])
         w = self.w.views
+        self.wait_weights(self._range("end_img")[1])
         ops.gemm(vw["feats"], w["visual_proj.0.weight"], vw["pre"], bias=w["visual_proj.0.bias"])
         ops.layernorm_fwd(vw["pre"], w["visual_proj.1.weight"], w["visual_proj.1.bias"], 1e-5, out=vw["tok"],
                           mean=vw["mean"], rstd=vw["rstd"])
@@ -380,11 +402,14 @@ class Engine:
             raise ValueError("sequence longer than the RoPE table (2 * max_seq_len)")
         examples = examples.contiguous()
         img = self.vit_forward(image, ws.vit) if W else None
+        self.wait_weights(self._range("tok_embeddings.weight")[1])
         ops.embed_splice(examples, w["tok_embeddings.weight"], img, w["start_img"] if W else None,
                          w["end_img"] if W else None, ws.x[0], B, T, self.vis.tokens if W else 0, D)
         for i in range(a.n_layers):
+            self.wait_weights(self._range(f"layers.{i}.feed_forward.w2.weight")[1])
             self._layer_fwd(i, ws.x[i], ws.xn[i], ws.qkv[i], ws.o[i], ws.h[i], ws.hn[i], ws.gu[i], ws.y[i],
                             ws.x[i + 1], ws.lse[i], ws.rstd1[i], ws.rstd2[i], B, L)
+        self.wait_weights()
         xf = ws.x[a.n_layers].view(B, L, D)
         for b in range(B):  # final norm on the text rows only (llama_ens5.py:485-486)
             ops.rmsnorm_fwd(xf[b, W:], w["norm.weight"], a.norm_eps, out=ws.fn[b * T:(b + 1) * T],
@@ -476,11 +501,37 @@ class Engine:
         return o, o + n
 
     # ------------------------------------------------------------------------------------ optimiser
+    def enable_sharded_optimizer(self, group=None) -> None:
+        """ZeRO-1 style: fp32 master / m / v of the decay region are split evenly over the data-parallel
+        ranks (the reference shards too: FSDP SHARD_GRAD_OP, M/main_finetune.py:256-260); every rank
+        updates its slice and broadcasts the new bf16 weights, shard by shard in forward-consumption
+        order on the side stream, so the exchange hides behind the next step's ViT + first layers.
+        The tiny no-decay region (norm weights, biases) is updated redundantly on every rank."""
+        import torch.distributed as dist
+
+        self.shard_group = group if group is not None else dist.group.WORLD
+        self.shard_world = dist.get_world_size(self.shard_group)
+        self.shard_rank = dist.get_rank(self.shard_group)
+        if self.decay_numel % (self.shard_world * 64):
+            raise ValueError("data-parallel world size must divide 8 for the sharded optimiser")
+        self.master = self.m = self.v = None
+        if self.comm_stream is None:
+            self.comm_stream = torch.cuda.Stream(device=self.device)
+
+    def _opt_ranges(self):
+        """[(lo, hi, decayed)] flat ranges this rank's optimiser owns."""
+        n, nd = self.w.flat.numel(), self.decay_numel
+        S = nd // self.shard_world
+        lo = self.shard_rank * S
+        return [(lo, lo + S, True), (nd, n, False)]
+
     def _ensure_opt(self):
         if self.master is None:
-            self.master = self.w.flat.float()
+            self.wait_weights()
+            self.master = [self.w.flat[lo:hi].float() for lo, hi, _ in self._opt_ranges()]
         if self.m is None:
-            self.m, self.v = self.w.like(torch.float32), self.w.like(torch.float32)
+            self.m = [torch.zeros_like(t) for t in self.master]
+            self.v = [torch.zeros_like(t) for t in self.master]
 
     def optimizer_step(self, lr: float, weight_decay: float = 0.0, max_norm: float = 0.0,
                        betas=(0.9, 0.95), eps: float = 1e-8) -> torch.Tensor:
@@ -490,14 +541,52 @@ class Engine:
         self._ensure_grads()
         self._ensure_opt()
         self.opt_step += 1
-        n, nd = self.w.flat.numel(), self.decay_numel
         self.norm_sq.zero_()
         ops.sumsq_bf16(self.g.flat, self.norm_sq)
-        for lo, hi, wd in ((0, nd, weight_decay), (nd, n, 0.0)):
+        for (lo, hi, decayed), ms, m, v in zip(self._opt_ranges(), self.master, self.m, self.v):
             if hi > lo:
-                ops.adamw(self.master[lo:hi], self.w.flat[lo:hi], self.g.flat[lo:hi], self.m[lo:hi],
-                          self.v[lo:hi], lr, betas[0], betas[1], eps, wd, self.opt_step, self.norm_sq, max_norm)
+                ops.adamw(ms, self.w.flat[lo:hi], self.g.flat[lo:hi], m, v, lr, betas[0], betas[1], eps,
+                          weight_decay if decayed else 0.0, self.opt_step, self.norm_sq, max_norm)
+        if self.shard_world > 1:
+            self._broadcast_shards()
         return self.norm_sq
+
+    def _broadcast_shards(self) -> None:
+        import torch.distributed as dist
+
+        S = self.decay_numel // self.shard_world
+        done = torch.cuda.Event()
+        done.record()
+        cs = self.comm_stream
+        cs.wait_event(done)
+        self.shard_ready = []
+        with torch.cuda.stream(cs):
+            for r in range(self.shard_world):
+                dist.broadcast(self.w.flat[r * S:(r + 1) * S], src=dist.get_global_rank(self.shard_group, r),
+                               group=self.shard_group)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+                self.shard_ready.append(ev)
+        self._waited_upto = 0
+
+    def wait_weights(self, upto: Optional[int] = None) -> None:
+        """Make the compute stream wait until the broadcast weights covering flat offsets [0, upto) have
+        arrived (all of them when upto is None).  No-op without a pending exchange."""
+        if not self.shard_ready or self._waited_upto is None:
+            return
+        S = self.decay_numel // self.shard_world
+        upto = self.decay_numel if upto is None else min(upto, self.decay_numel)
+        if upto <= self._waited_upto:
+            return
+        cur = torch.cuda.current_stream()
+        first, last = self._waited_upto // S, (upto - 1) // S
+        for r in range(first, last + 1):
+            if self.shard_ready[r] is not None:
+                cur.wait_event(self.shard_ready[r])
+                self.shard_ready[r] = None
+        self._waited_upto = (last + 1) * S
+        if self._waited_upto >= self.decay_numel:
+            self.shard_ready, self._waited_upto = [], None
 
     # ------------------------------------------------------------------------------------ data-parallel
     def allreduce_hook(self, group=None):
@@ -532,6 +621,7 @@ class Engine:
         a, w = self.args, self.w.views
         B, l = tokens.shape
         D, V = a.dim, a.vocab_size
+        self.wait_weights()
         if start_pos == 0:
             self.allocate_kv_cache(B)
         elif B != self.cache_B:

@@ -216,13 +216,21 @@ class Transformer(nn.Module):
     def get_quant_blocklist(self) -> List[str]:
         return [n for n, _ in self.named_modules() if n.startswith("clip.") or n.startswith("visual_proj.")]
 
-    def enable_data_parallel(self, group=None) -> None:
+    def enable_data_parallel(self, group=None, shard_optimizer: bool = True) -> None:
         """Replica data parallelism: gradients are all-reduced (sum, 1/world folded into the
-        loss gradient) bucket by bucket on a side stream while the backward is still running."""
+        loss gradient) bucket by bucket on a side stream while the backward is still running.
+        shard_optimizer: split the fp32 AdamW state over the ranks (ZeRO-1) and broadcast the updated
+        bf16 weights behind the next forward (Engine.enable_sharded_optimizer)."""
         import torch.distributed as dist
 
         self.dp_group = group if group is not None else dist.group.WORLD
         self.dp_world = dist.get_world_size(self.dp_group)
+        if shard_optimizer and self.dp_world > 1:
+            self.engine.enable_sharded_optimizer(self.dp_group)
+
+    def state_dict(self, *args, **kwargs):
+        self.engine.wait_weights()  # a pending weight exchange of the sharded optimiser must land first
+        return super().state_dict(*args, **kwargs)
 
     # ------------------------------------------------------------------ reference-facing forwards
     def forward(self, examples: torch.Tensor, image: Optional[torch.Tensor] = None, depth_imgs=None):

@@ -1,0 +1,94 @@
+"""Worker for tests/test_dp_gpu.py (launched with torch.distributed.run, one rank per GPU): a tiny model
+takes one data-parallel fine-tune step (bucketed all-reduce + sharded AdamW + shard broadcasts) and is
+compared with a single-replica model that accumulates the SAME per-rank batches locally."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+
+def main():
+    import a3vlm_oracle as O
+    from a3vlm_b200.model import MetaModel
+    from a3vlm_b200.train import AdamW, NativeScalerWithGradNormCount
+
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    a = O.ModelArgs(dim=256, n_layers=3, n_heads=2, vocab_size=512, multiple_of=128, max_seq_len=64, max_batch_size=4)
+    v = O.VisionArgs(image_size=28, patch=14, width=128, layers=2, heads=2, mlp=256)
+    sd = O.init_params(a, v, seed=31, output_scale=4.0)
+    cfg = dict(dim=a.dim, n_layers=a.n_layers, n_heads=a.n_heads, vocab_size=a.vocab_size, multiple_of=a.multiple_of,
+               image_size=v.image_size, vit_width=v.width, vit_layers=v.layers, vit_heads=v.heads, vit_mlp=v.mlp)
+
+    def build():
+        m = MetaModel("llama_b200", cfg, None, with_visual=True, max_seq_len=64, max_batch_size=4)
+        m.llma.load_state_dict(sd)
+        return m
+
+    def batch(r):
+        g = torch.Generator().manual_seed(100 + r)
+        tok = torch.randint(3, 512, (2, 12), generator=g)
+        tok[:, 0] = 1
+        lab = tok.clone()
+        lab[:, :5] = 0
+        return tok.cuda(), lab.cuda(), torch.randn(2, 3, 28, 28, generator=g).cuda()
+
+    dp = build()
+    dp.llma.enable_data_parallel()
+    opt = AdamW(dp, lr=1e-3, weight_decay=0.1)
+    scaler = NativeScalerWithGradNormCount()
+    ref = build()
+    ropt = AdamW(ref, lr=1e-3, weight_decay=0.1)
+    ok = True
+    for step in range(3):
+        tok, lab, img = batch(rank + 10 * step)
+        dp.zero_grad(set_to_none=True)
+        loss, _ = dp(tok, lab, images=img)
+        norm = scaler(loss, opt, dp, clip_grad=0.5, update_grad=True)
+        # reference: every rank's batch on one replica, accumulated, each scaled by 1/world
+        ref.zero_grad(set_to_none=True)
+        for r in range(world):
+            t2, l2, i2 = batch(r + 10 * step)
+            l, _ = ref(t2, l2, images=i2)
+            (l / world).backward()
+        ropt.step(max_norm=0.5)
+        rnorm = ropt.grad_norm()
+        step_ok = abs(norm.item() - rnorm.item()) <= 2e-2 * rnorm.item()
+        if not step_ok:
+            print(f"rank{rank} step{step}: grad norm {norm.item():.5f} vs single-replica {rnorm.item():.5f}", flush=True)
+        ok &= step_ok
+        # the next forward consumes the broadcast shards; state_dict() waits for all of them
+    got, want = dp.llma.state_dict(), ref.llma.state_dict()
+    worst = 0.0
+    for k in want:
+        if k.startswith("clip."):
+            continue
+        gk, wk = got[k].float(), want[k].float()
+        bad = ((gk - wk).abs() > 1e-5 + 2 ** -6 * wk.abs()).float().mean().item()
+        worst = max(worst, bad)
+        # replicas must be IDENTICAL across ranks after the shard broadcasts
+        other = got[k].clone()
+        dist.broadcast(other, src=0)
+        same = bool(torch.equal(other, got[k]))
+        if not same and rank == 1:
+            print(f"rank1 differs from rank0: {k} frac={(other != got[k]).float().mean().item():.4f}", flush=True)
+        ok &= same
+    if worst > 0.03:
+        print(f"rank{rank}: {worst:.4f} of some parameter's elements differ from the single-replica run", flush=True)
+    ok &= worst <= 0.03  # Adam's sign-like first steps flip where gradients are rounding noise
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(f"DP_CHECK ok={bool(flag.item())} worst_mismatch_fraction={worst:.4f} grad_norm={norm.item():.4f} ref={rnorm.item():.4f}")
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() else 1)
+
+
+if __name__ == "__main__":
+    main()
