@@ -96,10 +96,14 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ reference / CPU arm
+_CPU_REF_CACHE = {}
+
+
 def cpu_reference_sample(cfg, S, T, sample_layers=2, repeats=1):
     """Times the oracle restatement (PyTorch eager, bf16 linears on the host cores) on a bounded sample
     of the workload: batch 1, full ViT forward, `sample_layers` decoder layers fwd+bwd, LM head + loss
-    fwd+bwd; the decoder time is extrapolated linearly to n_layers.  Returns seconds per image."""
+    fwd+bwd, clip + AdamW on what was trained; the decoder time is extrapolated linearly to n_layers.
+    Returns (seconds per image, cores, description).  Weights / inputs are built once and cached."""
     import torch
 
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -107,20 +111,23 @@ def cpu_reference_sample(cfg, S, T, sample_layers=2, repeats=1):
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    a_small = O.ModelArgs(**{**cfg, "n_layers": sample_layers, "max_seq_len": 2048})
-    a_zero = O.ModelArgs(**{**cfg, "n_layers": 0, "max_seq_len": 2048})
-    v = O.VisionArgs(image_size=S)
-    sd = O.init_params(a_small, v, seed=2)
-    g = torch.Generator().manual_seed(1)
-    tok = torch.randint(3, cfg["vocab_size"], (1, T), generator=g)
-    tok[:, 0] = 1
-    lab = tok.clone()
-    lab[:, : T // 2] = 0
-    img = torch.randn(1, 3, S, S, generator=g)
-    train = [k for k in sd if not k.startswith("clip.")]
-
-    master = {k: sd[k].detach().float() for k in train}  # fp32 masters + AdamW state (M/util/tensor_type.py:60-66)
-    state = {k: (torch.zeros_like(master[k]), torch.zeros_like(master[k])) for k in train}
+    key = (json.dumps(cfg, sort_keys=True), S, T, sample_layers)
+    if key not in _CPU_REF_CACHE:
+        a_small = O.ModelArgs(**{**cfg, "n_layers": sample_layers, "max_seq_len": 2048})
+        a_zero = O.ModelArgs(**{**cfg, "n_layers": 0, "max_seq_len": 2048})
+        v = O.VisionArgs(image_size=S)
+        sd = O.init_params(a_small, v, seed=2)
+        g = torch.Generator().manual_seed(1)
+        tok = torch.randint(3, cfg["vocab_size"], (1, T), generator=g)
+        tok[:, 0] = 1
+        lab = tok.clone()
+        lab[:, : T // 2] = 0
+        img = torch.randn(1, 3, S, S, generator=g)
+        train = [k for k in sd if not k.startswith("clip.")]
+        master = {k: sd[k].detach().float() for k in train}  # fp32 masters + AdamW state (M/util/tensor_type.py:60-66)
+        state = {k: (torch.zeros_like(master[k]), torch.zeros_like(master[k])) for k in train}
+        _CPU_REF_CACHE[key] = (a_small, a_zero, v, sd, tok, lab, img, train, master, state)
+    a_small, a_zero, v, sd, tok, lab, img, train, master, state = _CPU_REF_CACHE[key]
 
     def run(args):
         for k in train:
@@ -150,7 +157,7 @@ def run_reference(args, cfg):
         return
     S, T = args.image_size, args.text_len
     for _ in range(min(args.warmup, 1)):
-        cpu_reference_sample(cfg, S, T, sample_layers=1)
+        cpu_reference_sample(cfg, S, T)
     times = []
     t_start = time.perf_counter()
     for _ in range(args.steps):
