@@ -52,6 +52,10 @@ struct GemmParams {
   long long ldc2;
   const __nv_bfloat16* dswiglu_gu;
   long long ldgu;
+  // small-M (decode-time) mode of the single-CTA kernel: only a_rows (< 128) rows of A are staged per
+  // k-block; the remaining rows of the 128-row MMA tile read stale shared memory and their
+  // accumulator rows are never stored.
+  int a_rows;
 };
 
 template <int BN>
@@ -59,7 +63,7 @@ struct GemmSmem {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int BAR_BYTES = 256;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
 };
@@ -352,10 +356,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S::STAGE_BYTES;
           uint8_t* sb = sa + S::A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+          mbar_arrive_expect_tx(&full_bar[stage], p.a_rows * (BK * 2) + S::B_BYTES);
           const int k0 = kb * BK;
           if (!p.a_mn) {
-            tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0);  // box {64 k, 128 rows}
+            tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0);  // box {64 k, a_rows (128) rows}
           } else {
 #pragma unroll
             for (int c = 0; c < BM / 64; ++c)  // box {64 m, 64 k-rows} per 64-wide chunk
@@ -700,9 +704,17 @@ extern "C" int a3_gemm_bf16(const void* A, const void* B, void* C, int M, int N,
     const double t_single = (double)((ts + sms - 1) / sms);
     pair = t_pair < t_single;
   }
-  const int bn = pair ? 128 : ((N <= 128 || (N % 256 != 0 && N % 128 == 0 && N < 2048)) ? 128 : 256);
+  int bn = pair ? 128 : ((N <= 128 || (N % 256 != 0 && N % 128 == 0 && N < 2048)) ? 128 : 256);
+  int a_rows = BM;
+  if (!pair && M <= 64 && !a_mn_major && !b_mn_major) {
+    // decode-time shapes (one short M block): HBM-bound on the weight stream, so what matters is
+    // enough CTAs pulling on HBM -> narrow N tiles, and only the live rows of A staged per k-block
+    const long long sms = num_sms();
+    bn = (N / 64 >= 2 * sms) ? 64 : 32;
+    a_rows = (M + 7) & ~7;
+  }
   CUtensorMap tmA, tmB;
-  int rc = encode_operand_map(&tmA, A, M, K, lda, a_mn_major, BM);
+  int rc = encode_operand_map(&tmA, A, M, K, lda, a_mn_major, a_rows);
   if (rc != A3_OK) return rc;
   rc = encode_operand_map(&tmB, B, N, K, ldb, b_mn_major, bn);  // pair: each CTA loads 128 B rows
   if (rc != A3_OK) return rc;
@@ -726,8 +738,11 @@ extern "C" int a3_gemm_bf16(const void* A, const void* B, void* C, int M, int N,
   p.alpha = alpha;
   p.group_m = 16;
   p.swiglu_F = 0; p.C2 = nullptr; p.ldc2 = 0; p.dswiglu_gu = nullptr; p.ldgu = 0;
+  p.a_rows = a_rows;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (pair) return launch_gemm2(tmA, tmB, p, s);
+  if (bn == 32) return launch_gemm<32>(tmA, tmB, p, s);
+  if (bn == 64) return launch_gemm<64>(tmA, tmB, p, s);
   return bn == 128 ? launch_gemm<128>(tmA, tmB, p, s) : launch_gemm<256>(tmA, tmB, p, s);
 }
 
@@ -735,7 +750,7 @@ static void init_params(a3::GemmParams& p, int M, int N, int K) {
   p.C = nullptr; p.bias = nullptr; p.residual = nullptr; p.rope = nullptr; p.ldc = 0; p.ldr = 0;
   p.rope_cols = 0; p.rope_period = 1; p.rope_pos0 = 0; p.M = M; p.N = N; p.K = K; p.a_mn = 0; p.b_mn = 0;
   p.act = 0; p.out_fp32 = 0; p.accumulate = 0; p.alpha = 1.f; p.group_m = 16; p.swiglu_F = 0; p.C2 = nullptr;
-  p.ldc2 = 0; p.dswiglu_gu = nullptr; p.ldgu = 0;
+  p.ldc2 = 0; p.dswiglu_gu = nullptr; p.ldgu = 0; p.a_rows = a3::BM;
 }
 
 extern "C" int a3_gemm_swiglu_bf16(const void* X, const void* W13, void* GU, void* Y, int M, int F, int K,

@@ -221,6 +221,7 @@ class Engine:
         self.cache_image_words = 0
         self.dec = None
         self.use_decode_graph = True
+        self.decode_fused_max_b = 4  # larger batches: tcgen05 GEMM path (measured: B=8 8.1 ms/token vs 11.6 fused)
         self.comm_stream = None
         # sharded optimiser (ZeRO-1 style, enable_sharded_optimizer): this rank's slice of the decay region
         self.shard_group, self.shard_world, self.shard_rank = None, 1, 0
@@ -655,8 +656,10 @@ class Engine:
 
     def _lm_head(self, fn: torch.Tensor) -> torch.Tensor:
         w, B = self.w.views, fn.shape[0]
-        if B <= 16:
-            return ops.linear_small_m(fn, w["output.weight"], out_fp32=True)
+        if B <= 8:
+            return ops.decode_linear(fn, w["output.weight"],
+                                     torch.empty(B, self.args.vocab_size, device=self.device, dtype=torch.float32),
+                                     out_fp32=True)
         return ops.gemm(fn, w["output.weight"]).float()
 
     def _decode_step(self, tokens: torch.Tensor, pos: int) -> torch.Tensor:
@@ -677,7 +680,7 @@ class Engine:
                         "tok": torch.zeros(B, 1, device=self.device, dtype=torch.int64),
                         "pos": torch.zeros(1, device=self.device, dtype=torch.int32),
                         "logits": e(B, a.vocab_size, dt=torch.float32), "graph": None, "eager_steps": 0}
-            if B > 16:
+            if B > self.decode_fused_max_b:
                 self.dec["logits_bf"] = e(B, a.vocab_size)
         d = self.dec
         d["tok"].copy_(tokens.reshape(B, 1))
@@ -702,7 +705,7 @@ class Engine:
         B, D, F = d["B"], a.dim, self.ffn_dim
         ops.embed_splice(d["tok"], w["tok_embeddings.weight"], None, None, None, d["x"], B, 1, 0, D)
         x, x2 = d["x"], d["x2"]
-        if B <= 8:
+        if B <= self.decode_fused_max_b:
             # five launches per layer: every norm / activation / RoPE / cache write is a prologue or
             # epilogue of the weight-streaming projection that consumes or produces it
             for i in range(a.n_layers):
@@ -718,9 +721,9 @@ class Engine:
                 x, x2 = x2, x
             ops.decode_linear(x, w["output.weight"], d["logits"], norm_w=w["norm.weight"], eps=a.norm_eps, out_fp32=True)
             return
-        small = B <= 16
-        lin = (lambda x, wt, out, residual=None: ops.linear_small_m(x, wt, out=out, residual=residual)) if small \
-            else (lambda x, wt, out, residual=None: ops.gemm(x, wt, out, residual=residual))
+        # larger decode batches: tcgen05 GEMM in its small-M mode (narrow N tiles so >= 2 CTAs per SM pull
+        # on the weight stream, only the live rows of X staged) + the small row kernels
+        lin = lambda x, wt, out, residual=None: ops.gemm(x, wt, out, residual=residual)
         for i in range(a.n_layers):
             p = f"layers.{i}."
             ops.rmsnorm_fwd(x, w[p + "attention_norm.weight"], a.norm_eps, out=d["xn"])
@@ -736,8 +739,5 @@ class Engine:
             lin(d["y"], w[p + "feed_forward.w2.weight"], x2, residual=d["h"])
             x, x2 = x2, x
         fn = ops.rmsnorm_fwd(x, w["norm.weight"], a.norm_eps, out=d["xn"])
-        if small:
-            ops.linear_small_m(fn, w["output.weight"], out=d["logits"], out_fp32=True)
-        else:
-            ops.gemm(fn, w["output.weight"], d["logits_bf"])
-            d["logits"].copy_(d["logits_bf"])  # .float() of the bf16 result (llama_ens5.py:530-531)
+        ops.gemm(fn, w["output.weight"], d["logits_bf"])
+        d["logits"].copy_(d["logits_bf"])  # .float() of the bf16 result (llama_ens5.py:530-531)

@@ -9,11 +9,15 @@ from a3vlm_b200.model import MetaModel
 cfg = bench.MODELS["7b"]
 dev = torch.device("cuda", 0)
 combos = {224: [(1, 128), (16, 128)], 336: [(1, 32), (1, 128), (1, 512), (4, 128), (16, 128), (64, 128)], 448: [(1, 128), (16, 128)]}
+if len(sys.argv) > 1 and sys.argv[1] == "quick":
+    combos = {336: [(1, 128), (2, 128), (4, 128), (8, 128), (16, 128), (64, 128)]}
+FUSED_MAX_B = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 rows = []
 for S, lst in combos.items():
     model = MetaModel("llama_b200", {**cfg, "image_size": S}, None, with_visual=True, max_seq_len=2048, max_batch_size=64)
     model.llma.reset_parameters(seed=2)
     eng = model.llma.engine
+    eng.decode_fused_max_b = FUSED_MAX_B
     g = torch.Generator().manual_seed(7)
     base_prompt = torch.randint(3, 32000, (1, 256), generator=g); base_prompt[:, 0] = 1
     base_img = torch.randn(1, 3, S, S, generator=g)
@@ -49,4 +53,4 @@ for S, lst in combos.items():
         print(rows[-1], flush=True)
     del model, eng
     torch.cuda.empty_cache()
-json.dump({"config": "llama-7b + ViT-L/14 random init, 256-token prompt, greedy, 1xB200", "rows": rows}, open("gpurun_out/sweep.json", "w"), indent=1)
+json.dump({"config": "llama-7b + ViT-L/14 random init, 256-token prompt, greedy, 1xB200", "rows": rows}, open("gpurun_out/sweep%s.json" % ("_" + "_".join(sys.argv[1:]) if len(sys.argv) > 1 else ""), "w"), indent=1)

@@ -53,6 +53,19 @@ def test_gemm_fp32_out(ops, M, N, K, a_mn, b_mn):
     torch.testing.assert_close(c, ref, rtol=1e-3, atol=1e-4 * math.sqrt(K))
 
 
+@pytest.mark.parametrize("M", [1, 9, 16, 64])
+def test_gemm_small_m_mode(ops, M):
+    """Decode-time shapes: one short M block, narrow N tiles, only the live rows of A staged."""
+    torch.manual_seed(M)
+    N, K = 1504, 1024
+    a, w, res = rnd(M, K), rnd(N, K, scale=0.05), rnd(M, N)
+    ref = a.float() @ w.float().t()
+    c = ops.gemm(a, w, out_fp32=True)
+    torch.testing.assert_close(c, ref, rtol=1e-3, atol=1e-4 * math.sqrt(K))
+    c = ops.gemm(a, w, residual=res)
+    close_bf16(c, ref.to(bf16).float() + res.float(), atol=2e-2)
+
+
 def test_gemm_epilogue_bias_gelu_residual(ops):
     torch.manual_seed(0)
     M, N, K = 577, 1024, 512
