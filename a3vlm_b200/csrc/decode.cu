@@ -314,6 +314,7 @@ attn_decode_partial_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloa
   // online-softmax chain (one L2 round trip per group instead of per key)
   constexpr int KU = 8;
   for (int t0 = k_begin + warp; t0 < k_end; t0 += DEC_WARPS * KU) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // a PDL successor may start prefetching weights
     uint2 kr[KU], vr[KU];
 #pragma unroll
     for (int u = 0; u < KU; ++u) {
@@ -430,6 +431,7 @@ decode_rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, long long ld, __nv_bfloat
   const float2 cs = table[(long long)pos * (HD / 2) + j];
   const long long ci = (((long long)b * max_seq + pos) * H + h) * HD + 2 * j;
   {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // a PDL successor may start prefetching weights
     const float2 x = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(row));
     *reinterpret_cast<uint32_t*>(row) = pack_bf16x2(x.x * cs.x - x.y * cs.y, x.x * cs.y + x.y * cs.x);
   }

@@ -84,6 +84,7 @@ __global__ void embed_splice_bwd_kernel(const long long* __restrict__ tokens,
                                         __nv_bfloat16* __restrict__ dE,
                                         __nv_bfloat16* __restrict__ d_img, int T, int Nimg, int D,
                                         int has_img) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // a PDL successor may start prefetching weights
   const int W = has_img ? Nimg + 2 : 0;
   const int L = T + W;
   const int b = blockIdx.x / L, l = blockIdx.x % L;

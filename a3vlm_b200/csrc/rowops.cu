@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(ROW_THREADS)
 rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                    __nv_bfloat16* __restrict__ y, float* __restrict__ rstd_out, int D,
                    long long ldx, long long ldy, float eps) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // a PDL successor may start prefetching weights
   __shared__ float red[32];
   const int row = blockIdx.x;
   const __nv_bfloat16* xr = x + row * ldx;
@@ -326,6 +327,7 @@ __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, int M, i
 // the product rounds).
 __global__ void swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloat16* __restrict__ y,
                                   long long total_chunks, int Fc) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // a PDL successor may start prefetching weights
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_chunks;
        i += (long long)gridDim.x * blockDim.x) {
     const long long row = i / Fc;

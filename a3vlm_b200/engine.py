@@ -221,7 +221,7 @@ class Engine:
         self.cache_image_words = 0
         self.dec = None
         self.use_decode_graph = True
-        self.decode_fused_max_b = 4  # larger batches: tcgen05 GEMM path (measured: B=8 8.1 ms/token vs 11.6 fused)
+        self.decode_fused_max_b = 1  # batch 1: fused CUDA-core weight streaming (3.05 ms); larger: swapped-operand tcgen05 (B=4 3.9 ms vs 5.9 fused)
         self.comm_stream = None
         # sharded optimiser (ZeRO-1 style, enable_sharded_optimizer): this rank's slice of the decay region
         self.shard_group, self.shard_world, self.shard_rank = None, 1, 0
@@ -721,9 +721,12 @@ class Engine:
                 x, x2 = x2, x
             ops.decode_linear(x, w["output.weight"], d["logits"], norm_w=w["norm.weight"], eps=a.norm_eps, out_fp32=True)
             return
-        # larger decode batches: tcgen05 GEMM in its small-M mode (narrow N tiles so >= 2 CTAs per SM pull
-        # on the weight stream, only the live rows of X staged) + the small row kernels
-        lin = lambda x, wt, out, residual=None: ops.gemm(x, wt, out, residual=residual)
+        # larger decode batches: swapped-operand tcgen05 projection (weights are the 128-row MMA operand,
+        # split-K over a cluster) + the small row kernels
+        if B <= 64:
+            lin = lambda x, wt, out, residual=None: ops.decode_gemm(x, wt, out, residual=residual)
+        else:
+            lin = lambda x, wt, out, residual=None: ops.gemm(x, wt, out, residual=residual)
         for i in range(a.n_layers):
             p = f"layers.{i}."
             ops.rmsnorm_fwd(x, w[p + "attention_norm.weight"], a.norm_eps, out=d["xn"])
@@ -739,5 +742,8 @@ class Engine:
             lin(d["y"], w[p + "feed_forward.w2.weight"], x2, residual=d["h"])
             x, x2 = x2, x
         fn = ops.rmsnorm_fwd(x, w["norm.weight"], a.norm_eps, out=d["xn"])
-        ops.gemm(fn, w["output.weight"], d["logits_bf"])
-        d["logits"].copy_(d["logits_bf"])  # .float() of the bf16 result (llama_ens5.py:530-531)
+        if B <= 64:
+            ops.decode_gemm(fn, w["output.weight"], d["logits"], out_fp32=True)
+        else:
+            ops.gemm(fn, w["output.weight"], d["logits_bf"])
+            d["logits"].copy_(d["logits_bf"])  # .float() of the bf16 result (llama_ens5.py:530-531)

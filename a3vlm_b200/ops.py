@@ -118,6 +118,15 @@ def decode_linear(x, w, out, *, K=None, norm_w=None, eps=1e-5, swiglu=False, res
     return out
 
 
+def decode_gemm(x, w, out, residual=None, out_fp32=False):
+    M, K = x.shape
+    N = w.shape[0]
+    rc = _L().a3_decode_gemm(_p(x), _p(w), _p(out), M, N, K, x.stride(0), w.stride(0), out.stride(0),
+                             _p(residual), residual.stride(0) if residual is not None else 0, int(out_fp32), _st())
+    _lib.check(rc, "a3_decode_gemm")
+    return out
+
+
 # ----------------------------------------------------------------------------------------- norms
 def rmsnorm_fwd(x, w, eps, out=None, rstd=None):
     rows, D = x.shape

@@ -94,6 +94,14 @@ int a3_decode_linear(const void* X, const void* W, void* Y, int M, int N, int K,
                      int n_heads, void* kcache, void* vcache, const int* pos_dev, int pos, int max_seq,
                      void* stream);
 
+/* Decode projection for a batch of M <= 64 single-token rows on tcgen05 with swapped operands: the
+ * weight tile is the 128-row MMA operand, the batch the narrow N side, split-K across a thread-block
+ * cluster with a distributed-shared-memory reduction, 8-11 TMA stages in flight (HBM-bound weight
+ * stream; llama_ens5.py:112,169,216-217,530 at seqlen 1).  Y[M][N] = X[M][K] W[N][K]^T (+residual). */
+int a3_decode_gemm(const void* X, const void* W, void* Y, int M, int N, int K, long long ldx,
+                   long long ldw, long long ldy, const void* residual, long long ldr, int out_fp32,
+                   void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Norms.  x,y bf16 [rows][D]; weights bf16; statistics fp32.
  * RMSNorm: reference model/accessory/model/components.py:39-53 -- y = bf16(x*rsqrt(mean(x^2)+eps)) * w

@@ -7,6 +7,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 model = MetaModel("llama_b200", {**bench.MODELS["7b"], "image_size": 336}, None, with_visual=True, max_seq_len=2048, max_batch_size=64)
 model.llma.reset_parameters(seed=2)
 model.llma.engine.use_decode_graph = False
+model.llma.engine.decode_fused_max_b = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 g = torch.Generator().manual_seed(7)
 tk = torch.randint(3, 32000, (B, 256), generator=g).cuda(); tk[:, 0] = 1
 img = torch.randn(B, 3, 336, 336, generator=g).cuda()

@@ -212,9 +212,30 @@ def test_live_oracle_midsize():
     check("midsize logits", got_logits, ref_logits, rel=2e-2, ulps=6)
     assert abs(got_loss.item() - ref_loss.item()) <= 2e-3 * abs(ref_loss.item())
     prompts = [[1, 5, 9], [1, 7, 8, 9, 10], [1, 3]]
+    seen = []
+    real_fi = orc.forward_inference
+
+    def recording_fi(tokens, start_pos, image=None):
+        lg = real_fi(tokens, start_pos, image)
+        seen.append(lg.clone())
+        return lg
+
+    orc.forward_inference = recording_fi
     ref_gen, ref_tok, _ = O.generate_tokens(orc, prompts, images=img, max_gen_len=6, eos_id=2)
     got_gen, got_tok, _ = m.generate_tokens(prompts, img, max_gen_len=6, eos_id=2)
-    assert got_gen == ref_gen
+    # Greedy ids must be identical, except that a row may part ways with the oracle at a step where the
+    # ORACLE's own top-2 logits are within bf16 rounding of each other (an exact or near tie: the two
+    # bf16 paths legitimately order them differently); everything before that step must match.
+    min_prompt = min(len(q) for q in prompts)
+    for r, (g, e) in enumerate(zip(got_gen, ref_gen)):
+        if g == e:
+            continue
+        k = next(i for i, (x, y) in enumerate(zip(g, e)) if x != y)
+        call = len(prompts[r]) + k - min_prompt
+        top2 = seen[call][r].topk(2).values
+        margin, mag = (top2[0] - top2[1]).item(), top2[0].abs().item()
+        print(f"row {r} diverges at generated token {k}: oracle top-2 margin {margin:.4f} at logit {mag:.2f}")
+        assert margin <= 4 * 2.0 ** -8 * max(mag, 1.0), (r, k, margin, mag, g, e)
 
 
 def test_no_cpu_fallback():

@@ -66,6 +66,21 @@ def test_gemm_small_m_mode(ops, M):
     close_bf16(c, ref.to(bf16).float() + res.float(), atol=2e-2)
 
 
+@pytest.mark.parametrize("M,N,K", [(1, 1000, 512), (5, 12288, 4096), (16, 4096, 4096), (17, 4096, 11008), (40, 512, 256), (64, 32000, 4096)])
+def test_decode_gemm_swapped_operands(ops, M, N, K):
+    """tcgen05 decode projection (weights as the 128-row operand, split-K over a cluster + DSMEM reduce)."""
+    torch.manual_seed(M + N)
+    x, w, res = rnd(M, K), rnd(N, K, scale=0.03), rnd(M, N)
+    ref = x.float() @ w.float().t()
+    y = torch.full((M, N), float("nan"), device=dev())
+    ops.decode_gemm(x, w, y, out_fp32=True)
+    close_bf16(y, ref, atol=4e-3)
+    assert torch.equal(y, y.to(bf16).float())
+    y2 = torch.full((M, N), float("nan"), device=dev(), dtype=bf16)
+    ops.decode_gemm(x, w, y2, residual=res)
+    close_bf16(y2, ref.to(bf16).float() + res.float(), atol=3e-2)
+
+
 def test_gemm_epilogue_bias_gelu_residual(ops):
     torch.manual_seed(0)
     M, N, K = 577, 1024, 512
