@@ -27,11 +27,6 @@ from . import ops
 bf16 = torch.bfloat16
 
 
-def _no_decay(name: str) -> bool:
-    # M/util/misc.py:586-599 (add_weight_decay): no weight decay for biases and norm weights
-    return name.endswith(".bias") or name.endswith("norm.weight")
-
-
 def ffn_hidden_dim(dim: int, multiple_of: int, ffn_dim_multiplier) -> int:
     """LLM/llama_ens5.py:196-200 with hidden_dim = 4 * dim (:228)."""
     hidden = int(2 * (4 * dim) / 3)

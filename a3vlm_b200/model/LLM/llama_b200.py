@@ -105,7 +105,7 @@ class _TrainFn(torch.autograd.Function):
         if labels is not None:
             return ws.loss[0].clone()
         B, T = examples.shape
-        return logits.view(B, T, -1)
+        return logits.view(B, T, -1).clone()  # the workspace is reused by the next call
 
     @staticmethod
     def backward(ctx, grad_out):
@@ -244,7 +244,7 @@ class Transformer(nn.Module):
         if torch.is_grad_enabled():
             return _TrainFn.apply(self, examples, image, None, self._anchor)
         _, logits = self.engine.forward_train(examples, image)
-        return logits.view(examples.shape[0], examples.shape[1], -1)
+        return logits.view(examples.shape[0], examples.shape[1], -1).clone()
 
     def loss_forward(self, examples: torch.Tensor, labels: torch.Tensor, image=None) -> torch.Tensor:
         """forward + the shifted CrossEntropyLoss(ignore_index=0) of M/model/meta.py:256-262 fused behind
