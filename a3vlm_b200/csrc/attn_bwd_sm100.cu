@@ -22,6 +22,7 @@
 // (model/accessory/engine_finetune.py:60-68).
 #include "common.cuh"
 #include "ptx.cuh"
+#include <cstdlib>
 
 namespace a3 {
 
@@ -56,6 +57,7 @@ struct BwdParams {
   int B, H, T;
   float scale;
   int causal;
+  int debug_skip;  // profiling experiments only (A3_ATTN_BWD_SKIP): 1 = no dQ reduce, 2 = no element-wise phase
 };
 
 __device__ __forceinline__ void red_add_f32(float* addr, float v) {
@@ -276,7 +278,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc_fence_before();
     fence_proxy_async_smem();
     __syncthreads();
-    if (tid == 0) {
+    if (tid == 0 && !(p.debug_skip & 1)) {
       tma_reduce_add_3d(&tmDQ, smem + S::OFF_DQ, h * BW_HD, qbase, b);  // rows >= T are clipped
       bulk_commit_group();
     }
@@ -453,6 +455,7 @@ extern "C" int a3_attn_bwd(const void* q, const void* k, const void* v, const vo
   p.B = B; p.H = H; p.T = T;
   p.scale = scale;
   p.causal = causal ? 1 : 0;
+  p.debug_skip = getenv("A3_ATTN_BWD_SKIP") ? atoi(getenv("A3_ATTN_BWD_SKIP")) : 0;
   dim3 grid((T + BW_KEYS - 1) / BW_KEYS, H, B);
   attn_bwd_kernel<<<grid, 256, BwdSmem::TOTAL, s>>>(tmQ, tmK, tmV, tmDO, tmDQ, p);
   rc = check_launch("a3_attn_bwd");

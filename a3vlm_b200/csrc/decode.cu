@@ -206,78 +206,91 @@ decode_linear_kernel(const DecLinParams p) {
         *reinterpret_cast<uint4*>(xs + m * K + ch * 8) = *reinterpret_cast<const uint4*>(p.X + m * p.ldx + ch * 8);
   }
   __syncthreads();
-  if (!active) return;
 
-  // ---- stream the two weight rows
-  float acc[LIN_COLS_PER_WARP][M];
+  // ---- persistent loop over column pairs: the activations are staged once per CTA, every warp walks
+  // pairs n0, n0 + stride, ... ; the first pair's leading chunks were prefetched before the PDL wait
+  const int stride = gridDim.x * LIN_WARPS * LIN_COLS_PER_WARP;
+  bool first_pair = true;
+  for (int n = n0; n < p.N; n += stride, first_pair = false) {
+    const __nv_bfloat16* wa = p.W + (long long)n * p.ldw;
+    const __nv_bfloat16* wb = (n + 1 < p.N) ? wa + p.ldw : wa;
+    float acc[LIN_COLS_PER_WARP][M];
 #pragma unroll
-  for (int c = 0; c < LIN_COLS_PER_WARP; ++c)
+    for (int c = 0; c < LIN_COLS_PER_WARP; ++c)
 #pragma unroll
-    for (int m = 0; m < M; ++m) acc[c][m] = 0.f;
+      for (int m = 0; m < M; ++m) acc[c][m] = 0.f;
+    if (!first_pair) {
 #pragma unroll
-  for (int i = 0; i < DL_PF; ++i) {
-    const int ch = lane + i * 32;
-    if (ch < nchunks) {
+      for (int i = 0; i < DL_PF; ++i) {
+        const int ch = lane + i * 32;
+        if (ch < nchunks) { pa[i] = ldg_stream(wa + ch * 8); pb[i] = ldg_stream(wb + ch * 8); }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < DL_PF; ++i) {
+      const int ch = lane + i * 32;
+      if (ch < nchunks) {
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+          const uint4 x = *reinterpret_cast<const uint4*>(xs + m * K + ch * 8);
+          acc[0][m] += dot8(pa[i], x);
+          acc[1][m] += dot8(pb[i], x);
+        }
+      }
+    }
+#pragma unroll 4
+    for (int ch = lane + DL_PF * 32; ch < nchunks; ch += 32) {
+      const uint4 a = ldg_stream(wa + ch * 8);
+      const uint4 b = ldg_stream(wb + ch * 8);
 #pragma unroll
       for (int m = 0; m < M; ++m) {
         const uint4 x = *reinterpret_cast<const uint4*>(xs + m * K + ch * 8);
-        acc[0][m] += dot8(pa[i], x);
-        acc[1][m] += dot8(pb[i], x);
+        acc[0][m] += dot8(a, x);
+        acc[1][m] += dot8(b, x);
       }
     }
-  }
-#pragma unroll 4
-  for (int ch = lane + DL_PF * 32; ch < nchunks; ch += 32) {
-    const uint4 a = ldg_stream(w0 + ch * 8);
-    const uint4 b = ldg_stream(w1 + ch * 8);
 #pragma unroll
-    for (int m = 0; m < M; ++m) {
-      const uint4 x = *reinterpret_cast<const uint4*>(xs + m * K + ch * 8);
-      acc[0][m] += dot8(a, x);
-      acc[1][m] += dot8(b, x);
-    }
-  }
+    for (int c = 0; c < LIN_COLS_PER_WARP; ++c)
 #pragma unroll
-  for (int c = 0; c < LIN_COLS_PER_WARP; ++c)
+      for (int m = 0; m < M; ++m)
 #pragma unroll
-    for (int m = 0; m < M; ++m)
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc[c][m] += __shfl_xor_sync(0xffffffffu, acc[c][m], o);
-  if (lane != 0) return;
+        for (int o = 16; o > 0; o >>= 1) acc[c][m] += __shfl_xor_sync(0xffffffffu, acc[c][m], o);
+    if (lane != 0) continue;
 
-  if (p.rope) {
-    // QKV projection: n0 is even, so this warp owns one RoPE pair (or a v pair)
-    const int D = p.n_heads * 128;
-    const int pos = p.pos_dev ? *p.pos_dev : p.pos;
-    const int sect = n0 / D, within = n0 - sect * D;  // 0 q, 1 k, 2 v
-    const float2 cs = p.rope[(long long)pos * 64 + ((within & 127) >> 1)];
+    if (p.rope) {
+      // QKV projection: n is even, so this warp owns one RoPE pair (or a v pair)
+      const int D = p.n_heads * 128;
+      const int pos = p.pos_dev ? *p.pos_dev : p.pos;
+      const int sect = n / D, within = n - sect * D;  // 0 q, 1 k, 2 v
+      const float2 cs = p.rope[(long long)pos * 64 + ((within & 127) >> 1)];
 #pragma unroll
-    for (int m = 0; m < M; ++m) {
-      float a = bf16_round(acc[0][m]), b = bf16_round(acc[1][m]);
-      if (sect < 2) { const float ra = a * cs.x - b * cs.y, rb = a * cs.y + b * cs.x; a = ra; b = rb; }
-      const uint32_t r = pack_bf16x2(a, b);
-      *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(p.Y) + m * p.ldy + n0) = r;
-      if (sect >= 1) {
-        __nv_bfloat16* cache = sect == 1 ? p.kc : p.vc;
-        *reinterpret_cast<uint32_t*>(cache + ((long long)m * p.max_seq + pos) * D + within) = r;
+      for (int m = 0; m < M; ++m) {
+        float a = bf16_round(acc[0][m]), b = bf16_round(acc[1][m]);
+        if (sect < 2) { const float ra = a * cs.x - b * cs.y, rb = a * cs.y + b * cs.x; a = ra; b = rb; }
+        const uint32_t r = pack_bf16x2(a, b);
+        *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(p.Y) + m * p.ldy + n) = r;
+        if (sect >= 1) {
+          __nv_bfloat16* cache = sect == 1 ? p.kc : p.vc;
+          *reinterpret_cast<uint32_t*>(cache + ((long long)m * p.max_seq + pos) * D + within) = r;
+        }
       }
+      continue;
     }
-    return;
-  }
 #pragma unroll
-  for (int c = 0; c < LIN_COLS_PER_WARP; ++c) {
-    const int n = n0 + c;
-    if (n >= p.N) break;
+    for (int c = 0; c < LIN_COLS_PER_WARP; ++c) {
+      const int nn = n + c;
+      if (nn >= p.N) break;
 #pragma unroll
-    for (int m = 0; m < M; ++m) {
-      float v = acc[c][m];
-      if (p.out_fp32) {
-        v = bf16_round(v);  // logits: .float() of a bf16 GEMM result (llama_ens5.py:530-531)
-        if (p.residual) v += __bfloat162float(p.residual[m * p.ldr + n]);
-        reinterpret_cast<float*>(p.Y)[m * p.ldy + n] = v;
-      } else {
-        if (p.residual) v = bf16_round(v) + __bfloat162float(p.residual[m * p.ldr + n]);
-        reinterpret_cast<__nv_bfloat16*>(p.Y)[m * p.ldy + n] = __float2bfloat16_rn(v);
+      for (int m = 0; m < M; ++m) {
+        float v = acc[c][m];
+        if (p.out_fp32) {
+          v = bf16_round(v);  // logits: .float() of a bf16 GEMM result (llama_ens5.py:530-531)
+          if (p.residual) v += __bfloat162float(p.residual[m * p.ldr + nn]);
+          reinterpret_cast<float*>(p.Y)[m * p.ldy + nn] = v;
+        } else {
+          if (p.residual) v = bf16_round(v) + __bfloat162float(p.residual[m * p.ldr + nn]);
+          reinterpret_cast<__nv_bfloat16*>(p.Y)[m * p.ldy + nn] = __float2bfloat16_rn(v);
+        }
       }
     }
   }
@@ -492,8 +505,11 @@ static int launch_decode_linear(const DecLinParams& p, cudaStream_t s) {
     configured = smem;
   }
   const int cols_per_block = LIN_WARPS * LIN_COLS_PER_WARP;
+  int grid = (p.N + cols_per_block - 1) / cols_per_block;
+  const int slots = num_sms() * 2;  // persistent: one resident wave (2 CTAs per SM), X staged once per CTA
+  if (grid > slots) grid = slots;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((p.N + cols_per_block - 1) / cols_per_block);
+  cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(LIN_WARPS * 32);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
