@@ -13,7 +13,8 @@
 // open_clip ViT linears (llama_ens5.py:354-370).
 //
 // CTA = 256 threads: warp 0 TMA producer, warp 1 MMA issuer (one elected lane), warp 2 TMEM
-// allocator, warps 4..7 epilogue (TMEM lane quarter = warp_idx % 4).  Tile 128 x BN x 64, 4-5 smem
+// allocator, warps 4..11 epilogue (TMEM lane quarter = warp_idx % 4, two warps per quarter split the
+// columns).  CTA = 384 threads.  Tile 128 x BN x 64, 4-8 smem
 // stages, two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "ptx.cuh"
 #include "a3vlm_b200.h"
@@ -25,7 +26,10 @@ namespace a3 {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;  // max: warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 epilogue
+// The epilogue runs on 4 warps (256-thread launch) or 8 warps (384 threads, two per TMEM lane quarter,
+// each taking half of the tile's columns).  Eight warps halve heavy epilogues (GELU, short-K ViT tiles:
+// c_fc 137 -> 80 us) but cost the long LLM projections ~3 % (measured), so the host picks per call.
 
 struct GemmParams {
   void* C;
@@ -112,11 +116,12 @@ __device__ __forceinline__ void store8f(__nv_bfloat16* ptr, const float* f) {
 // Backward of the gated SiLU fused behind the w2 dgrad: acc = dy tile; dg = bf16(dy*u) * silu'(g),
 // du = dy * bf16(silu(g))  (same rounding points as the stand-alone a3_swiglu_bwd).
 template <int BN>
-__device__ __forceinline__ void epilogue_dswiglu_rows(const GemmParams& p, uint32_t t_row, int row, int n0) {
+__device__ __forceinline__ void epilogue_dswiglu_rows(const GemmParams& p, uint32_t t_row, int row, int n0,
+                                                      int c0, int c1) {
   const bool row_ok = row < p.M;
   const int F = p.N;
 #pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
+  for (int c = c0; c < c1; ++c) {
     uint32_t r[32];
     tmem_ld_32x32(t_row + c * 32, r);
     tmem_ld_wait();
@@ -147,11 +152,12 @@ __device__ __forceinline__ void epilogue_dswiglu_rows(const GemmParams& p, uint3
 
 // Forward gated SiLU fused behind the w1 | w3 projection (CTA-pair kernel, swiglu_F mode): columns
 // [0,128) of the accumulator tile are g, [128,256) are u of features f0 .. f0+127.
-__device__ __forceinline__ void epilogue_swiglu_rows(const GemmParams& p, uint32_t t_row, int row, int f0) {
+__device__ __forceinline__ void epilogue_swiglu_rows(const GemmParams& p, uint32_t t_row, int row, int f0,
+                                                     int c0, int c1) {
   const bool row_ok = row < p.M;
   const int F = p.swiglu_F;
 #pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
+  for (int c = c0; c < c1; ++c) {
     uint32_t rg[32], ru[32];
     tmem_ld_32x32(t_row + c * 32, rg);
     tmem_ld_32x32(t_row + 128 + c * 32, ru);
@@ -176,15 +182,22 @@ __device__ __forceinline__ void epilogue_swiglu_rows(const GemmParams& p, uint32
   }
 }
 
+// Two warps share a TMEM lane quarter: `half` selects which half of the tile's 32-column chunks a warp
+// handles (c0..c1), doubling the threads that hide the epilogue's TMEM / global latencies and ALU work.
 template <int BN>
-__device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t t_row, int row, int n0) {
+__device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t t_row, int row, int n0, int half,
+                                              int nhalves) {
+  constexpr int NCH = BN / 32;
+  const int per = (NCH + nhalves - 1) / nhalves;
+  const int c0 = half * per;
+  const int c1 = min(NCH, c0 + per);
   if (p.dswiglu_gu) {
-    epilogue_dswiglu_rows<BN>(p, t_row, row, n0);
+    epilogue_dswiglu_rows<BN>(p, t_row, row, n0, c0, c1);
     return;
   }
   const bool row_ok = row < p.M;
 #pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
+  for (int c = c0; c < c1; ++c) {
     uint32_t r[32];
     tmem_ld_32x32(t_row + c * 32, r);
     tmem_ld_wait();
@@ -330,7 +343,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);
+      mbar_init(&tmem_empty[s], (blockDim.x >> 5) - 4);  // one arrival per epilogue warp
     }
     fence_mbar_init();
   }
@@ -413,7 +426,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ===================== epilogue: TMEM -> regs -> global =====================
-    const int ew = warp - 4;  // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
+    const int ew = (warp - 4) & 3;  // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
+    const int eh = (warp - 4) >> 2;  // column half of the tile
     int acc_stage = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -424,7 +438,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&tmem_full[acc_stage], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc_stage * BN;
-      epilogue_rows<BN>(p, t_row, row, n0);
+      epilogue_rows<BN>(p, t_row, row, n0, eh, ((int)blockDim.x >> 5) / 4 - 1);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc_stage]);
@@ -449,7 +463,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // accumulator rows of each CTA land in that CTA's own TMEM, so both CTAs run the same epilogue.
 // Barriers: full[] lives in the leader (both CTAs' TMA bytes are signalled there); empty[] and
 // tmem_full[] are arrived on in both CTAs by a multicast tcgen05.commit; tmem_empty[] lives in the
-// leader and counts the 8 epilogue warps of the pair.
+// leader and counts the 16 epilogue warps of the pair.
 // ------------------------------------------------------------------------------------------------
 struct Gemm2Smem {
   static constexpr int BN = 256;
@@ -499,7 +513,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 8);
+      mbar_init(&tmem_empty[s], 2 * ((blockDim.x >> 5) - 4));  // epilogue warps of both CTAs
     }
     fence_mbar_init();
   }
@@ -585,7 +599,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp >= 4) {
     // ===================== epilogue (both CTAs): own 128 rows of the 256-row tile =====================
-    const int ew = warp - 4;
+    const int ew = (warp - 4) & 3, eh = (warp - 4) >> 2;
     int acc_stage = 0;
     uint32_t acc_phase = 0;
     for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
@@ -596,8 +610,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(&tmem_full[acc_stage], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc_stage * BN;
-      if (p.swiglu_F) epilogue_swiglu_rows(p, t_row, row, nb * BNH);
-      else epilogue_rows<BN>(p, t_row, row, n0);
+      const int nhalves = ((int)blockDim.x >> 5) / 4 - 1;
+      if (p.swiglu_F) epilogue_swiglu_rows(p, t_row, row, nb * BNH, eh * (4 / nhalves), (eh + 1) * (4 / nhalves));
+      else epilogue_rows<BN>(p, t_row, row, n0, eh, nhalves);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(&tmem_empty[acc_stage], 0));
@@ -614,6 +629,17 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 }
 
 // ------------------------------------------------------------------ host side
+// 384 threads (8 epilogue warps) when the epilogue is heavy relative to the main loop: activations,
+// residual adds (wo +res 190 -> 170 us), the fused gate backward, or short reductions (K <= 2048, the
+// ViT tower); 256 threads otherwise.
+static int epilogue_threads(const GemmParams& p) {
+  static const int force = getenv("A3_GEMM_EPI_WARPS") ? atoi(getenv("A3_GEMM_EPI_WARPS")) : 0;  // 4 / 8: testing
+  if (force == 4) return 256;
+  if (force == 8) return 384;
+  if (p.swiglu_F) return 256;  // the fused gate forward measured faster on 4 warps (978 vs 1097 us)
+  return (p.act || p.dswiglu_gu || p.residual || p.K <= 2048) ? 384 : 256;
+}
+
 static int encode_operand_map(CUtensorMap* tm, const void* ptr, int rows_out, int k_red,
                               long long ld, int mn_major, int block_rows) {
   // K-major: memory [rows_out][k_red] -> dims {k_red, rows_out}, box {64, block_rows}
@@ -638,7 +664,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   const int m_blocks = (p.M + BM - 1) / BM, n_blocks = (p.N + BN - 1) / BN;
   const int tiles = m_blocks * n_blocks;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_bf16_kernel<BN><<<grid, GEMM_THREADS, S::TOTAL, stream>>>(tmA, tmB, p);
+  gemm_bf16_kernel<BN><<<grid, epilogue_threads(p), S::TOTAL, stream>>>(tmA, tmB, p);
   return check_launch("a3_gemm_bf16");
 }
 
@@ -657,7 +683,7 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ge
   const int tiles = m_blocks * n_blocks;
   const int pairs = num_sms() / 2;
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
-  gemm2_bf16_kernel<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(tmA, tmB, p);
+  gemm2_bf16_kernel<<<grid, epilogue_threads(p), S::TOTAL, stream>>>(tmA, tmB, p);
   return check_launch("a3_gemm_bf16(2cta)");
 }
 
@@ -736,7 +762,8 @@ extern "C" int a3_gemm_bf16(const void* A, const void* B, void* C, int M, int N,
   p.out_fp32 = out_fp32 ? 1 : 0;
   p.accumulate = accumulate ? 1 : 0;
   p.alpha = alpha;
-  p.group_m = 16;
+  static const int gm_env = getenv("A3_GEMM_GROUP_M") ? atoi(getenv("A3_GEMM_GROUP_M")) : 0;  // tuning experiments
+  p.group_m = gm_env > 0 ? gm_env : 16;
   p.swiglu_F = 0; p.C2 = nullptr; p.ldc2 = 0; p.dswiglu_gu = nullptr; p.ldgu = 0;
   p.a_rows = a_rows;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
