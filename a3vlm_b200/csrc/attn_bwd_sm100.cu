@@ -1,9 +1,9 @@
 // FlashAttention-style backward on tcgen05 / TMEM, fed by TMA (sm_100a), head_dim 128.
 //
-// One CTA = 128 keys of one (batch, head), 8 warps: threads t and t+128 share key row t (TMEM lane
-// t) and split the 64 query columns of a tile between them (two warps per SM sub-partition hide the
-// MUFU / TMEM / smem latencies of the element-wise phase -- ncu r01: it, not the MMAs, bounds the
-// kernel).  For each tile of 64 queries (all five contractions on tcgen05, transposes are free through the UMMA majorness):
+// One CTA = 128 keys of one (batch, head), 16 warps: threads t, t+128, t+256, t+384 share key row t
+// (TMEM lane t) and split the 64 query columns of a tile into four 16-column parts (four warps per SM
+// sub-partition hide the MUFU / TMEM / smem latencies of the element-wise phase -- ncu r01: it, not
+// the MMAs, bounds the kernel: 4 warps 779 us, 8 warps 438 us per layer).  For each tile of 64 queries (all five contractions on tcgen05, transposes are free through the UMMA majorness):
 //     S^T  = K Q^T            A = K  (K-major)   B = Q   (K-major)    -> TMEM [  0, 64)
 //     dP^T = V dO^T           A = V  (K-major)   B = dO  (K-major)    -> TMEM [ 64,128)
 //     P^T = exp2(S^T c - lse), dS^T = P^T (dP^T - delta) scale        -> smem (bf16, SW128)
@@ -64,7 +64,7 @@ __device__ __forceinline__ void red_add_f32(float* addr, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                 const __grid_constant__ CUtensorMap tmDQ, const BwdParams p) {
@@ -81,7 +81,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   float* s_delta = s_lse + 2 * BW_Q;                             // [2][64]
 
   const int warp = (threadIdx.x >> 5) & 3, lane = threadIdx.x & 31, tid = threadIdx.x;
-  const int half = threadIdx.x >> 7;  // which 32 of the 64 query columns this thread handles
+  const int part = threadIdx.x >> 7;  // which 16 of the 64 query columns this thread handles
   const int key0 = blockIdx.x * BW_KEYS, h = blockIdx.y, b = blockIdx.z;
   const int T = p.T;
   const int n_q_tiles = (T + BW_Q - 1) / BW_Q;
@@ -215,14 +215,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc_fence_after();
     const int qbase = i * BW_Q;
     {
-      uint32_t s[32], dp[32];
-      tmem_ld_32x32(t_lane + C_S + half * 32, s);
-      tmem_ld_32x32(t_lane + C_DP + half * 32, dp);
-      const float4* l4 = reinterpret_cast<const float4*>(s_lse + st * BW_Q + half * 32);
-      const float4* d4 = reinterpret_cast<const float4*>(s_delta + st * BW_Q + half * 32);
+      uint32_t s[16], dp[16];
+      tmem_ld_32x16(t_lane + C_S + part * 16, s);
+      tmem_ld_32x16(t_lane + C_DP + part * 16, dp);
+      const float4* l4 = reinterpret_cast<const float4*>(s_lse + st * BW_Q + part * 16);
+      const float4* d4 = reinterpret_cast<const float4*>(s_delta + st * BW_Q + part * 16);
       tmem_ld_wait();
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 2; ++u) {
         const float4 la = l4[2 * u], lb = l4[2 * u + 1], da = d4[2 * u], db = d4[2 * u + 1];
         const float l2[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
         const float dl[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
@@ -230,13 +230,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int idx = u * 8 + e;
-          const int qi = qbase + half * 32 + idx;
+          const int qi = qbase + part * 16 + idx;
           const bool vis = key_ok && (!p.causal || key <= qi);
           const float pr = vis ? exp2f(__uint_as_float(s[idx]) * c2 - l2[e]) : 0.f;
           pv[e] = pr;
           dv[e] = pr * (__uint_as_float(dp[idx]) - dl[e]) * p.scale;
         }
-        const int unit = half * 4 + u;
+        const int unit = part * 2 + u;
         *reinterpret_cast<uint4*>(p_row + ((unit ^ sw) << 4)) =
             make_uint4(pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]), pack_bf16x2(pv[4], pv[5]),
                        pack_bf16x2(pv[6], pv[7]));
@@ -268,11 +268,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     __syncwarp();
     {
       float* stage = reinterpret_cast<float*>(smem + S::OFF_DQ) + warp * 32 + lane;  // column d
-      uint32_t dq[32];
-      tmem_ld_32x32(t_lane + C_DQ + half * 32, dq);
+      uint32_t dq[16];
+      tmem_ld_32x16(t_lane + C_DQ + part * 16, dq);
       tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 32; ++c) stage[(half * 32 + c) * BW_HD] = __uint_as_float(dq[c]);
+      for (int c = 0; c < 16; ++c) stage[(part * 16 + c) * BW_HD] = __uint_as_float(dq[c]);
     }
     // The next iteration's issue_grads overwrites dQ^T; order the reads above before it.
     tc_fence_before();
@@ -290,9 +290,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // grad_bar of the last iteration has been waited on above by every thread
     __nv_bfloat16* dvr = p.dv + (static_cast<long long>(b) * T + key) * p.lddkv + h * BW_HD;
     __nv_bfloat16* dkr = p.dk + (static_cast<long long>(b) * T + key) * p.lddkv + h * BW_HD;
-#pragma unroll
-    for (int cc = 0; cc < BW_HD / 64; ++cc) {
-      const int c = half * (BW_HD / 64) + cc;
+    {
+      const int c = part;  // one 32-column chunk of dV and dK per thread
       uint32_t a[32], d[32];
       tmem_ld_32x32(t_lane + C_DV + c * 32, a);
       tmem_ld_32x32(t_lane + C_DK + c * 32, d);
@@ -324,7 +323,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
     }
-  } else if (key_ok && half == 0) {
+  } else if (key_ok && part == 0) {
     // keys no query can see (cannot happen for causal Tq == Tk, kept for safety): zero gradient
     __nv_bfloat16* dvr = p.dv + (static_cast<long long>(b) * T + key) * p.lddkv + h * BW_HD;
     __nv_bfloat16* dkr = p.dk + (static_cast<long long>(b) * T + key) * p.lddkv + h * BW_HD;
@@ -457,7 +456,7 @@ extern "C" int a3_attn_bwd(const void* q, const void* k, const void* v, const vo
   p.causal = causal ? 1 : 0;
   p.debug_skip = getenv("A3_ATTN_BWD_SKIP") ? atoi(getenv("A3_ATTN_BWD_SKIP")) : 0;
   dim3 grid((T + BW_KEYS - 1) / BW_KEYS, H, B);
-  attn_bwd_kernel<<<grid, 256, BwdSmem::TOTAL, s>>>(tmQ, tmK, tmV, tmDO, tmDQ, p);
+  attn_bwd_kernel<<<grid, 512, BwdSmem::TOTAL, s>>>(tmQ, tmK, tmV, tmDO, tmDQ, p);
   rc = check_launch("a3_attn_bwd");
   if (rc) return rc;
   const long long rows = (long long)B * T;
