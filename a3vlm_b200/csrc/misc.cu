@@ -3,6 +3,7 @@
 // grid-stride over flat ranges sized in multiples of the SM count.
 #include "common.cuh"
 #include "ptx.cuh"
+#include <cuda_fp16.h>
 
 namespace a3 {
 
@@ -54,23 +55,30 @@ __device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&f)[8]) {
 }
 
 // ------------------------------------------------------------------ embedding gather + splice
-// One CTA per output row of h [B][L][D], L = T + W, W = Nimg + 2 (0 without image).
+// One CTA per output row of h [B][L][D], L = T + W, W = n_views * (Nimg + 2) (0 without image).
+// Layout (llama_ens5.py:469-479): BOS | per view: start_img, Nimg tokens, end_img | text; the image
+// tokens are view-major: img[(v * B + b) * Nimg + i]  (torch.chunk(image_feats, 5), llama_ens5.py:457).
 __global__ void embed_splice_kernel(const long long* __restrict__ tokens,
                                     const __nv_bfloat16* __restrict__ E,
                                     const __nv_bfloat16* __restrict__ img,
                                     const __nv_bfloat16* __restrict__ start_img,
                                     const __nv_bfloat16* __restrict__ end_img,
-                                    __nv_bfloat16* __restrict__ h, int T, int Nimg, int D,
-                                    long long ld_img) {
-  const int W = img ? Nimg + 2 : 0;
+                                    __nv_bfloat16* __restrict__ h, int B, int T, int Nimg, int D,
+                                    long long ld_img, int n_views) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // a PDL successor may start prefetching weights
+  const int per = Nimg + 2;
+  const int W = img ? n_views * per : 0;
   const int L = T + W;
   const int b = blockIdx.x / L, l = blockIdx.x % L;
   const __nv_bfloat16* src;
   if (l == 0) src = E + tokens[(long long)b * T] * D;
   else if (l > W) src = E + tokens[(long long)b * T + (l - W)] * D;
-  else if (l == 1) src = start_img;
-  else if (l == W) src = end_img;
-  else src = img + ((long long)b * Nimg + (l - 2)) * ld_img;
+  else {
+    const int v = (l - 1) / per, r = (l - 1) % per;
+    if (r == 0) src = start_img;
+    else if (r == per - 1) src = end_img;
+    else src = img + (((long long)v * B + b) * Nimg + (r - 1)) * ld_img;
+  }
   // note: for W == 0, l >= 1 > W takes the text branch.
   __nv_bfloat16* dst = h + (long long)blockIdx.x * D;
   for (int c = threadIdx.x; c < D / 8; c += blockDim.x)
@@ -82,10 +90,10 @@ __global__ void embed_splice_kernel(const long long* __restrict__ tokens,
 __global__ void embed_splice_bwd_kernel(const long long* __restrict__ tokens,
                                         const __nv_bfloat16* __restrict__ dh,
                                         __nv_bfloat16* __restrict__ dE,
-                                        __nv_bfloat16* __restrict__ d_img, int T, int Nimg, int D,
-                                        int has_img) {
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // a PDL successor may start prefetching weights
-  const int W = has_img ? Nimg + 2 : 0;
+                                        __nv_bfloat16* __restrict__ d_img, int B, int T, int Nimg, int D,
+                                        int has_img, int n_views) {
+  const int per = Nimg + 2;
+  const int W = has_img ? n_views * per : 0;
   const int L = T + W;
   const int b = blockIdx.x / L, l = blockIdx.x % L;
   const __nv_bfloat16* src = dh + (long long)blockIdx.x * D;
@@ -94,25 +102,67 @@ __global__ void embed_splice_bwd_kernel(const long long* __restrict__ tokens,
     __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(dE + tok * D);
     for (int c = threadIdx.x; c < D / 2; c += blockDim.x)
       atomicAdd(dst + c, reinterpret_cast<const __nv_bfloat162*>(src)[c]);
-  } else if (l >= 2 && l < W) {
-    if (d_img) {
-      __nv_bfloat16* dst = d_img + ((long long)b * Nimg + (l - 2)) * D;
+  } else {
+    const int v = (l - 1) / per, r = (l - 1) % per;
+    if (r > 0 && r < per - 1 && d_img) {
+      __nv_bfloat16* dst = d_img + (((long long)v * B + b) * Nimg + (r - 1)) * D;
       for (int c = threadIdx.x; c < D / 8; c += blockDim.x)
         reinterpret_cast<uint4*>(dst)[c] = reinterpret_cast<const uint4*>(src)[c];
     }
   }
 }
+// start_img / end_img are shared by every view and sample: sum their rows in fp32.
 __global__ void tag_grad_kernel(const __nv_bfloat16* __restrict__ dh, float* __restrict__ d_start,
-                                float* __restrict__ d_end, int B, int L, int W, int D) {
+                                float* __restrict__ d_end, int B, int L, int per, int n_views, int D) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= D) return;
   float s = 0.f, e = 0.f;
-  for (int b = 0; b < B; ++b) {
-    s += __bfloat162float(dh[((long long)b * L + 1) * D + c]);
-    e += __bfloat162float(dh[((long long)b * L + W) * D + c]);
-  }
+  for (int b = 0; b < B; ++b)
+    for (int v = 0; v < n_views; ++v) {
+      s += __bfloat162float(dh[((long long)b * L + 1 + v * per) * D + c]);
+      e += __bfloat162float(dh[((long long)b * L + (v + 1) * per) * D + c]);
+    }
   d_start[c] = s;
   d_end[c] = e;
+}
+
+// Reference tiling of a (2V x 2V) image into five V x V views (llama_ens5.py:383-385): view 0 = bicubic
+// down-sample computed on the fp16-rounded image (F.interpolate(image.half(), "bicubic"): align_corners
+// False, A = -0.75, fp32 accumulation, fp16 result), views 1..4 = the four quadrants.  Output fp32
+// [5][B][3][V][V] (view-major, as torch.cat([image_224] + image_parts, dim=0)).
+template <typename T>
+__global__ void build_views_kernel(const T* __restrict__ image, float* __restrict__ out, int B, int V) {
+  const int S = 2 * V;
+  const long long total = 5LL * B * 3 * V * V;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % V), y = (int)((i / V) % V);
+    const long long plane = (i / ((long long)V * V)) % (3LL * B);  // b * 3 + c
+    const int v = (int)(i / ((long long)V * V * 3 * B));
+    const T* src = image + plane * S * S;
+    float r;
+    if (v == 0) {
+      // source coordinate 2*d + 0.5 -> taps 2d-1 .. 2d+2 (clamped), t = 0.5 in both directions
+      const float w[4] = {-0.09375f, 0.59375f, 0.59375f, -0.09375f};
+      float acc = 0.f;
+#pragma unroll
+      for (int ky = 0; ky < 4; ++ky) {
+        const int yy = min(max(2 * y - 1 + ky, 0), S - 1);
+        float row = 0.f;
+#pragma unroll
+        for (int kx = 0; kx < 4; ++kx) {
+          const int xx = min(max(2 * x - 1 + kx, 0), S - 1);
+          row += w[kx] * __half2float(__float2half_rn((float)src[(long long)yy * S + xx]));
+        }
+        acc += w[ky] * row;
+      }
+      r = __half2float(__float2half_rn(acc));
+    } else {
+      const int oy = (v - 1) / 2 * V, ox = (v - 1) % 2 * V;
+      r = (float)src[(long long)(oy + y) * S + ox + x];
+    }
+    out[i] = r;
+  }
 }
 
 // ------------------------------------------------------------------ ViT front end
@@ -430,30 +480,46 @@ using namespace a3;
 
 extern "C" int a3_embed_splice(const long long* tokens, const void* E, const void* img,
                                const void* start_img, const void* end_img, void* h, int B, int T,
-                               int Nimg, int D, long long ld_img, void* stream) {
+                               int Nimg, int D, long long ld_img, int n_views, void* stream) {
   if (D & 7) return set_error(A3_ERR_ARG, "a3_embed_splice: D % 8 != 0");
   if (img && (!start_img || !end_img)) return set_error(A3_ERR_ARG, "a3_embed_splice: tags missing");
-  const int L = T + (img ? Nimg + 2 : 0);
+  if (n_views < 1) n_views = 1;
+  const int L = T + (img ? n_views * (Nimg + 2) : 0);
   if (B * L <= 0) return A3_OK;
   embed_splice_kernel<<<B * L, 128, 0, ST(stream)>>>(tokens, BF(E), BF(img), BF(start_img),
-                                                     BF(end_img), BFM(h), T, Nimg, D, ld_img);
+                                                     BF(end_img), BFM(h), B, T, Nimg, D, ld_img, n_views);
   return check_launch("a3_embed_splice");
 }
 
 extern "C" int a3_embed_splice_bwd(const long long* tokens, const void* dh, void* dE, void* d_img,
                                    float* d_start_f32, float* d_end_f32, int B, int T, int Nimg,
-                                   int D, void* stream) {
+                                   int D, int n_views, void* stream) {
   if (D & 7) return set_error(A3_ERR_ARG, "a3_embed_splice_bwd: D % 8 != 0");
   const int has_img = d_start_f32 != nullptr;
-  const int W = has_img ? Nimg + 2 : 0;
+  if (n_views < 1) n_views = 1;
+  const int W = has_img ? n_views * (Nimg + 2) : 0;
   const int L = T + W;
   if (B * L <= 0) return A3_OK;
-  embed_splice_bwd_kernel<<<B * L, 128, 0, ST(stream)>>>(tokens, BF(dh), BFM(dE), BFM(d_img), T, Nimg,
-                                                         D, has_img);
+  embed_splice_bwd_kernel<<<B * L, 128, 0, ST(stream)>>>(tokens, BF(dh), BFM(dE), BFM(d_img), B, T, Nimg,
+                                                         D, has_img, n_views);
   int rc = check_launch("a3_embed_splice_bwd");
   if (rc != A3_OK || !has_img) return rc;
-  tag_grad_kernel<<<(D + 255) / 256, 256, 0, ST(stream)>>>(BF(dh), d_start_f32, d_end_f32, B, L, W, D);
+  tag_grad_kernel<<<(D + 255) / 256, 256, 0, ST(stream)>>>(BF(dh), d_start_f32, d_end_f32, B, L, Nimg + 2,
+                                                           n_views, D);
   return check_launch("a3_embed_splice_bwd(tags)");
+}
+
+extern "C" int a3_build_views(const void* image, int image_is_fp32, float* views, int B, int V,
+                              void* stream) {
+  if (B <= 0 || V <= 0) return A3_OK;
+  const long long total = 5LL * B * 3 * V * V;
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
+  if (image_is_fp32)
+    build_views_kernel<float><<<(int)blocks, 256, 0, ST(stream)>>>(reinterpret_cast<const float*>(image), views, B, V);
+  else
+    build_views_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, ST(stream)>>>(BF(image), views, B, V);
+  return check_launch("a3_build_views");
 }
 
 extern "C" int a3_vit_patchify(const void* image, int image_is_fp32, void* A, int B, int S,

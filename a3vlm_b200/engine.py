@@ -178,7 +178,10 @@ class Workspace:
             self.part2 = e(self.nparts, D, dt=torch.float32)
             self.tag_grad = e(2, D, dt=torch.float32)
         if W:
-            self.vit = eng._vit_workspace(B, train)
+            self.vit = eng._vit_workspace(B * eng.views, train)
+            if eng.views > 1:
+                S = eng.vis.image_size
+                self.vit["views"] = torch.empty(eng.views * B, 3, S, S, device=dev, dtype=torch.float32)
 
 
 class Engine:
@@ -204,7 +207,9 @@ class Engine:
         self.fuse_dswiglu = False  # backward: fused epilogue measured slower than dgrad + a3_swiglu_bwd
         self.n_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         self.rope = ops.rope_table(self.head_dim, a.max_seq_len * 2, a.rope_theta, device=self.device)
-        self.image_words = (vis.tokens + 2) if vis is not None else 0
+        # one view: start + N + end; reference tiling: 5 views of a (2S x 2S) image (llama_ens5.py:383-385)
+        self.views = getattr(vis, "views", 1) if vis is not None else 1
+        self.image_words = self.views * (vis.tokens + 2) if vis is not None else 0
         self.scale = 1.0 / math.sqrt(self.head_dim)
         self._build_layouts()
         self._ws: Dict[Tuple, Workspace] = {}
@@ -326,11 +331,15 @@ class Engine:
         v, f = self.vis, self.fz.views
         c = "clip.visual."
         B = image.shape[0]
-        if tuple(image.shape[1:]) != (3, v.image_size, v.image_size):
-            raise ValueError(f"image must be (B,3,{v.image_size},{v.image_size}), got {tuple(image.shape)}")
+        S_in = v.image_size * (2 if self.views == 5 else 1)
+        if tuple(image.shape[1:]) != (3, S_in, S_in):
+            raise ValueError(f"image must be (B,3,{S_in},{S_in}), got {tuple(image.shape)}")
         if image.dtype not in (torch.float32, bf16):
             image = image.float()
         image = image.contiguous()
+        if self.views == 5:  # [global bicubic | TL | TR | BL | BR] x B, view-major (llama_ens5.py:383-385)
+            image = ops.build_views(image, vw["views"], B, v.image_size)
+            B = 5 * B
         N, Wv, g2 = v.tokens, v.width, v.grid * v.grid
         act = ops.ACT_QUICKGELU if v.quick_gelu else ops.ACT_GELU
         ops.vit_patchify(image, vw["A"], B, v.image_size, v.patch, self.kpad)
@@ -401,7 +410,7 @@ class Engine:
         img = self.vit_forward(image, ws.vit) if W else None
         self.wait_weights(self._range("tok_embeddings.weight")[1])
         ops.embed_splice(examples, w["tok_embeddings.weight"], img, w["start_img"] if W else None,
-                         w["end_img"] if W else None, ws.x[0], B, T, self.vis.tokens if W else 0, D)
+                         w["end_img"] if W else None, ws.x[0], B, T, self.vis.tokens if W else 0, D, self.views)
         for i in range(a.n_layers):
             self.wait_weights(self._range(f"layers.{i}.feed_forward.w2.weight")[1])
             self._layer_fwd(i, ws.x[i], ws.xn[i], ws.qkv[i], ws.o[i], ws.h[i], ws.hn[i], ws.gu[i], ws.y[i],
@@ -475,7 +484,7 @@ class Engine:
         vw = ws.vit if W else None
         ops.embed_splice_bwd(examples, d, g["tok_embeddings.weight"], vw["dtok"] if W else None,
                              ws.tag_grad[0] if W else None, ws.tag_grad[1] if W else None, B, T,
-                             self.vis.tokens if W else 0, D)
+                             self.vis.tokens if W else 0, D, self.views)
         if W:
             ops.colsum_partials(ws.tag_grad[0:1], g["start_img"].view(-1), accumulate=acc)
             ops.colsum_partials(ws.tag_grad[1:2], g["end_img"].view(-1), accumulate=acc)
@@ -640,7 +649,7 @@ class Engine:
         tokens = tokens.contiguous()
         img = self.vit_forward(image, ws.vit) if W else None
         ops.embed_splice(tokens, w["tok_embeddings.weight"], img, w["start_img"] if W else None,
-                         w["end_img"] if W else None, ws.x[0], B, l, self.vis.tokens if W else 0, D)
+                         w["end_img"] if W else None, ws.x[0], B, l, self.vis.tokens if W else 0, D, self.views)
         xa, xb = ws.x[0], ws.x[1]
         for i in range(a.n_layers):
             self._layer_fwd(i, xa, ws.xn[0], ws.qkv[0], ws.o[0], ws.h[0], ws.hn[0], ws.gu[0], ws.y[0], xb,

@@ -40,7 +40,8 @@ class ModelArgs:
     rope_scaling: Optional[float] = None
     load_pretrained_visual_encoder: bool = False
     # --- vision geometry (the reference hard-codes open_clip ViT-L-14 at 224 px, llama_ens5.py:296-301,336)
-    image_size: int = 336
+    image_size: int = 336   # side of ONE ViT view
+    image_views: int = 1    # 1: single view of image_size; 5: the reference's tiling of a (2*image_size)^2 image
     vit_patch: int = 14
     vit_width: int = 1024
     vit_layers: int = 24
@@ -58,6 +59,7 @@ class _Vision:
     heads: int
     mlp: int
     quick_gelu: bool
+    views: int = 1
     ln_eps: float = 1e-5
 
     @property
@@ -146,13 +148,16 @@ class Transformer(nn.Module):
         vis = None
         if with_visual:
             quick = args.vit_quick_gelu if args.vit_quick_gelu is not None else args.load_pretrained_visual_encoder
+            if args.image_views not in (1, 5):
+                raise ValueError("image_views must be 1 (single view) or 5 (reference tiling, llama_ens5.py:383-385)")
             vis = _Vision(args.image_size, args.vit_patch, args.vit_width, args.vit_layers, args.vit_heads,
-                          args.vit_mlp, bool(quick))
+                          args.vit_mlp, bool(quick), views=args.image_views)
         self.engine = Engine(args, vis, dev)
-        self.image_words = self.engine.image_words  # (N + 2): start_img + N ViT tokens + end_img, one view
+        self.image_words = self.engine.image_words  # views x (start_img + N ViT tokens + end_img)
         self.cache_image_words = 0
         if with_visual:
-            self.image_size = args.image_size
+            # the size the data pipeline must deliver (M/main_finetune.py:295 reads model.llma.image_size)
+            self.image_size = args.image_size * (2 if args.image_views == 5 else 1)
         self.layers = nn.ModuleList([TransformerBlock() for _ in range(args.n_layers)])
         views = self.engine.param_views()
         self._trainable_named: List = []

@@ -264,17 +264,24 @@ def swiglu_bwd(gu, dy, dgu):
 
 
 # ----------------------------------------------------------------------------------------- embed / ViT front
-def embed_splice(tokens, E, img, start_img, end_img, out, B, T, Nimg, D):
+def embed_splice(tokens, E, img, start_img, end_img, out, B, T, Nimg, D, n_views=1):
     rc = _L().a3_embed_splice(_p(tokens), _p(E), _p(img), _p(start_img), _p(end_img), _p(out), B, T,
-                              Nimg, D, img.stride(-2) if img is not None else 0, _st())
+                              Nimg, D, img.stride(-2) if img is not None else 0, n_views, _st())
     _lib.check(rc, "a3_embed_splice")
     return out
 
 
-def embed_splice_bwd(tokens, dh, dE, d_img, d_start, d_end, B, T, Nimg, D):
+def embed_splice_bwd(tokens, dh, dE, d_img, d_start, d_end, B, T, Nimg, D, n_views=1):
     rc = _L().a3_embed_splice_bwd(_p(tokens), _p(dh), _p(dE), _p(d_img), _p(d_start), _p(d_end), B, T,
-                                  Nimg, D, _st())
+                                  Nimg, D, n_views, _st())
     _lib.check(rc, "a3_embed_splice_bwd")
+
+
+def build_views(image, out, B, V):
+    assert image.is_contiguous() and image.dtype in (torch.float32, bf16) and out.dtype == torch.float32
+    _lib.check(_L().a3_build_views(_p(image), int(image.dtype == torch.float32), _p(out), B, V, _st()),
+               "a3_build_views")
+    return out
 
 
 def vit_patchify(image, out, B, S, patch, Kpad):

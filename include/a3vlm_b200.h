@@ -186,16 +186,21 @@ int a3_swiglu_bwd(const void* gu, const void* dy, void* dgu, int rows, int F, vo
 
 /* ---------------------------------------------------------------------------------------------
  * Embedding gather + image splice (llama_ens5.py:464-479,495-511).
- * h[b, 0] = E[tok[b,0]]; h[b, 1] = start_img; h[b, 2..2+Nimg) = img[b]; h[b, Nimg+2] = end_img;
- * h[b, W + t] = E[tok[b,t]], t >= 1, W = Nimg + 2 (W = 0 when img is null).
+ * h[b, 0] = E[tok[b,0]]; per view v: start_img, Nimg tokens img[(v*B + b)*Nimg + i], end_img;
+ * h[b, W + t] = E[tok[b,t]], t >= 1, W = n_views * (Nimg + 2) (W = 0 when img is null).  n_views = 1:
+ * single view; 5: the reference's tiling (llama_ens5.py:383-385,457).
  * ------------------------------------------------------------------------------------------- */
 int a3_embed_splice(const long long* tokens, const void* E, const void* img, const void* start_img,
                     const void* end_img, void* h, int B, int T, int Nimg, int D, long long ld_img,
-                    void* stream);
+                    int n_views, void* stream);
 /* Backward: dE[tok] += dh rows of text positions (bf16 atomics), d_img, d_start, d_end. */
 int a3_embed_splice_bwd(const long long* tokens, const void* dh, void* dE, void* d_img,
                         float* d_start_f32, float* d_end_f32, int B, int T, int Nimg, int D,
-                        void* stream);
+                        int n_views, void* stream);
+/* The reference's five views of a (2V x 2V) image (llama_ens5.py:383-385): views[0] = bicubic
+ * down-sample of the fp16-rounded image (fp32 accumulate, fp16 result), views[1..4] = quadrants
+ * TL, TR, BL, BR.  views: fp32 [5][B][3][V][V]. */
+int a3_build_views(const void* image, int image_is_fp32, float* views, int B, int V, void* stream);
 
 /* ViT front end (llama_ens5.py:354-363).  patches: NCHW image (fp32 or bf16) -> A [B*g*g][Kpad]
  * bf16 with k = (c, ky, kx), zero padded to Kpad.  assemble: x[b,0] = cls + pos[0];

@@ -238,6 +238,52 @@ def test_live_oracle_midsize():
         assert margin <= 4 * 2.0 ** -8 * max(mag, 1.0), (r, k, margin, mag, g, e)
 
 
+def test_reference_five_view_tiling_matches_oracle():
+    """the reference's own geometry -- a (2S x 2S) image becomes five S x S views (fp16 bicubic
+    global view + four quadrants, llama_ens5.py:383-385), each wrapped in start/end tags (:471-477)."""
+    import a3vlm_oracle as O
+
+    a = O.ModelArgs(dim=256, n_layers=2, n_heads=2, vocab_size=512, multiple_of=128, max_seq_len=128, max_batch_size=4)
+    v = O.VisionArgs(image_size=28, patch=14, width=128, layers=2, heads=2, mlp=256, views=5)
+    sd = O.init_params(a, v, seed=41, output_scale=6.0)
+    orc = O.OracleTransformer(a, v, sd)
+    from a3vlm_b200.model import MetaModel
+
+    cfg = dict(dim=a.dim, n_layers=a.n_layers, n_heads=a.n_heads, vocab_size=a.vocab_size, multiple_of=a.multiple_of,
+               image_size=28, image_views=5, vit_width=128, vit_layers=2, vit_heads=2, vit_mlp=256)
+    m = MetaModel("llama_b200", cfg, None, with_visual=True, max_seq_len=128, max_batch_size=4)
+    m.llma.load_state_dict(sd)
+    assert m.get_image_words() == orc.image_words == 5 * (5 + 2) and m.llma.image_size == 56
+    g = torch.Generator().manual_seed(9)
+    tok = torch.randint(3, 512, (2, 10), generator=g)
+    tok[:, 0] = 1
+    lab = tok.clone()
+    lab[:, :4] = 0
+    img = torch.randn(2, 3, 56, 56, generator=g)
+    names = ["start_img", "end_img", "visual_proj.0.bias", "layers.0.attention.wq.weight"]
+    for k in sd:
+        if not k.startswith("clip."):
+            sd[k].requires_grad_(True)
+    ref_loss = O.meta_forward_loss(orc, tok, lab, img)
+    ref_loss.backward()
+    with torch.no_grad():
+        ref_logits = orc.forward(tok, img)
+    got_logits = m.llma(tok, img).detach()
+    check("5-view logits", got_logits, ref_logits)
+    m.zero_grad(set_to_none=True)
+    loss, _ = m(tok.cuda(), lab.cuda(), images=img.cuda())
+    assert abs(loss.item() - ref_loss.item()) <= 2e-3 * abs(ref_loss.item())
+    loss.backward()
+    named = dict(m.llma.named_parameters())
+    for k in names:
+        check("5-view grad " + k, named[k].grad, sd[k].grad, rel=2e-2, ulps=6)
+    for k in sd:
+        sd[k].requires_grad_(False)
+    ref_gen, _, _ = O.generate_tokens(orc, [[1, 5, 9], [1, 7]], images=img, max_gen_len=5, eos_id=2)
+    got_gen, _, _ = m.generate_tokens([[1, 5, 9], [1, 7]], img, max_gen_len=5, eos_id=2)
+    assert got_gen == ref_gen
+
+
 def test_no_cpu_fallback():
     from a3vlm_b200 import ops
     from a3vlm_b200._lib import A3Error

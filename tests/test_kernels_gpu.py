@@ -420,6 +420,44 @@ def test_embed_splice_and_bwd(ops):
     close_bf16(dE, refE, rtol=2 ** -6, atol=3e-2)
 
 
+def test_build_views_and_multiview_splice(ops):
+    """The reference's 5-view tiling (llama_ens5.py:383-385) and the per-view start/end wrapping (:471-477)."""
+    torch.manual_seed(14)
+    B, V = 2, 28
+    img = torch.randn(B, 3, 2 * V, 2 * V, device=dev())
+    views = torch.empty(5 * B, 3, V, V, device=dev())
+    ops.build_views(img, views, B, V)
+    g = torch.nn.functional.interpolate(img.half(), size=(V, V), mode="bicubic").to(img)
+    ref = torch.cat([g, img[..., :V, :V], img[..., :V, V:], img[..., V:, :V], img[..., V:, V:]], 0)
+    assert torch.equal(views[B:], ref[B:])
+    assert (views[:B] - ref[:B]).abs().max().item() <= 2 ** -10 * ref[:B].abs().max().item()  # <= 1 fp16 ulp
+    vb = torch.empty_like(views)
+    ops.build_views(img.to(bf16), vb, B, V)
+    assert torch.equal(vb[B:], ref[B:].to(bf16).float())
+    # multi-view splice: BOS | (start, N tokens, end) x 5 | text, image tokens view-major
+    T, N, D, Vc = 6, 3, 64, 40
+    E, toks, st, en = rnd(Vc, D), rnd(5 * B, N, D), rnd(D), rnd(D)
+    tok = torch.randint(1, Vc, (B, T), device=dev())
+    W = 5 * (N + 2)
+    h = torch.empty(B, T + W, D, device=dev(), dtype=bf16)
+    ops.embed_splice(tok, E, toks, st, en, h, B, T, N, D, n_views=5)
+    emb = E[tok]
+    chunks = [torch.cat([st.expand(B, 1, D), toks[v * B:(v + 1) * B], en.expand(B, 1, D)], 1) for v in range(5)]
+    ref = torch.cat([emb[:, :1]] + chunks + [emb[:, 1:]], 1)
+    assert torch.equal(h, ref)
+    dh = rnd(B, T + W, D)
+    dE, dimg = torch.zeros(Vc, D, device=dev(), dtype=bf16), torch.empty(5 * B, N, D, device=dev(), dtype=bf16)
+    ds, de = torch.empty(D, device=dev()), torch.empty(D, device=dev())
+    ops.embed_splice_bwd(tok, dh, dE, dimg, ds, de, B, T, N, D, n_views=5)
+    for v in range(5):
+        base = 1 + v * (N + 2)
+        assert torch.equal(dimg[v * B:(v + 1) * B], dh[:, base + 1:base + 1 + N])
+    starts = torch.stack([dh[:, 1 + v * (N + 2)] for v in range(5)], 0).float().sum((0, 1))
+    ends = torch.stack([dh[:, (v + 1) * (N + 2)] for v in range(5)], 0).float().sum((0, 1))
+    torch.testing.assert_close(ds, starts)
+    torch.testing.assert_close(de, ends)
+
+
 def test_vit_front(ops):
     torch.manual_seed(8)
     B, S, P, D = 2, 56, 14, 128
