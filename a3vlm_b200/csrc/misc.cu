@@ -64,7 +64,9 @@ __global__ void embed_splice_kernel(const long long* __restrict__ tokens,
                                     const __nv_bfloat16* __restrict__ start_img,
                                     const __nv_bfloat16* __restrict__ end_img,
                                     __nv_bfloat16* __restrict__ h, int B, int T, int Nimg, int D,
-                                    long long ld_img, int n_views) {
+                                    long long ld_img, int n_views,
+                                    const __nv_bfloat16* __restrict__ start2 = nullptr,
+                                    const __nv_bfloat16* __restrict__ end2 = nullptr, int views_per_stream = 0) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // a PDL successor may start prefetching weights
   const int per = Nimg + 2;
   const int W = img ? n_views * per : 0;
@@ -75,8 +77,9 @@ __global__ void embed_splice_kernel(const long long* __restrict__ tokens,
   else if (l > W) src = E + tokens[(long long)b * T + (l - W)] * D;
   else {
     const int v = (l - 1) / per, r = (l - 1) % per;
-    if (r == 0) src = start_img;
-    else if (r == per - 1) src = end_img;
+    const bool second = start2 != nullptr && v >= views_per_stream;  // RGB-D: the depth stream's own tags
+    if (r == 0) src = second ? start2 : start_img;
+    else if (r == per - 1) src = second ? end2 : end_img;
     else src = img + (((long long)v * B + b) * Nimg + (r - 1)) * ld_img;
   }
   // note: for W == 0, l >= 1 > W takes the text branch.
@@ -489,6 +492,22 @@ extern "C" int a3_embed_splice(const long long* tokens, const void* E, const voi
   embed_splice_kernel<<<B * L, 128, 0, ST(stream)>>>(tokens, BF(E), BF(img), BF(start_img),
                                                      BF(end_img), BFM(h), B, T, Nimg, D, ld_img, n_views);
   return check_launch("a3_embed_splice");
+}
+
+extern "C" int a3_embed_splice_rgbd(const long long* tokens, const void* E, const void* img,
+                                    const void* start_img, const void* end_img, const void* start_depth_img,
+                                    const void* end_depth_img, void* h, int B, int T, int Nimg, int D,
+                                    long long ld_img, int n_views, void* stream) {
+  if (D & 7) return set_error(A3_ERR_ARG, "a3_embed_splice_rgbd: D % 8 != 0");
+  if (!img || !start_img || !end_img || !start_depth_img || !end_depth_img)
+    return set_error(A3_ERR_ARG, "a3_embed_splice_rgbd: image tokens and all four tags are required");
+  if (n_views < 1) n_views = 1;
+  const int L = T + 2 * n_views * (Nimg + 2);
+  if (B * L <= 0) return A3_OK;
+  embed_splice_kernel<<<B * L, 128, 0, ST(stream)>>>(tokens, BF(E), BF(img), BF(start_img), BF(end_img),
+                                                     BFM(h), B, T, Nimg, D, ld_img, 2 * n_views,
+                                                     BF(start_depth_img), BF(end_depth_img), n_views);
+  return check_launch("a3_embed_splice_rgbd");
 }
 
 extern "C" int a3_embed_splice_bwd(const long long* tokens, const void* dh, void* dE, void* d_img,

@@ -79,6 +79,11 @@ def build_layout(args, vis):
                        (r + "ln_2.weight", (Wv,)), (r + "ln_2.bias", (Wv,)),
                        (r + "mlp.c_fc.weight", (v.mlp, Wv)), (r + "mlp.c_fc.bias", (v.mlp,)),
                        (r + "mlp.c_proj.weight", (Wv, v.mlp)), (r + "mlp.c_proj.bias", (Wv,))]
+        if getattr(v, "rgbd", False):
+            # LLM/llama_ens5_2images.py:343-344.  They live with the frozen tensors: the reference's
+            # training forward never sees the depth stream (M/model/meta.py:251), so these parameters
+            # never receive a gradient and its optimiser skips them -- no master / m / v needed.
+            frozen += [("start_depth_img", (1, 1, D)), ("end_depth_img", (1, 1, D))]
     return decay, nodecay, frozen, kpad
 
 
@@ -178,10 +183,11 @@ class Workspace:
             self.part2 = e(self.nparts, D, dt=torch.float32)
             self.tag_grad = e(2, D, dt=torch.float32)
         if W:
-            self.vit = eng._vit_workspace(B * eng.views, train)
+            streams = W // eng.visual_image_words  # 2 when the depth stream is spliced in as well
+            self.vit = eng._vit_workspace(B * eng.views * streams, train)
             if eng.views > 1:
                 S = eng.vis.image_size
-                self.vit["views"] = torch.empty(eng.views * B, 3, S, S, device=dev, dtype=torch.float32)
+                self.vit["views"] = torch.empty(streams * eng.views * B, 3, S, S, device=dev, dtype=torch.float32)
 
 
 class Engine:
@@ -209,7 +215,11 @@ class Engine:
         self.rope = ops.rope_table(self.head_dim, a.max_seq_len * 2, a.rope_theta, device=self.device)
         # one view: start + N + end; reference tiling: 5 views of a (2S x 2S) image (llama_ens5.py:383-385)
         self.views = getattr(vis, "views", 1) if vis is not None else 1
-        self.image_words = self.views * (vis.tokens + 2) if vis is not None else 0
+        # RGB-D build (LLM/llama_ens5_2images.py:335-336): a depth stream of the same geometry follows the
+        # RGB stream at inference; image_words counts both, visual_image_words one of them
+        self.rgbd = bool(getattr(vis, "rgbd", False)) if vis is not None else False
+        self.visual_image_words = self.views * (vis.tokens + 2) if vis is not None else 0
+        self.image_words = self.visual_image_words * (2 if self.rgbd else 1)
         self.scale = 1.0 / math.sqrt(self.head_dim)
         self._build_layouts()
         self._ws: Dict[Tuple, Workspace] = {}
@@ -325,24 +335,30 @@ class Engine:
             self.g = FlatParams(self._layout, self.device, segment_after=self._segment_after)
 
     # ------------------------------------------------------------------------------------ ViT + projector
-    def vit_forward(self, image: torch.Tensor, vw) -> torch.Tensor:
+    def vit_forward(self, image: torch.Tensor, vw, depth: Optional[torch.Tensor] = None) -> torch.Tensor:
         """clip_encode_image (LLM/llama_ens5.py:351-375) + visual_proj (:330-333,451), frozen tower.
-        image (B,3,S,S) fp32 or bf16 on the device -> image tokens [B*N][D] (vw['tok'])."""
+        image (B,3,S,S) fp32 or bf16 on the device -> image tokens [B*N][D] (vw['tok']).  With `depth`
+        (RGB-D build) both streams go through the tower as one batch, RGB views first."""
         v, f = self.vis, self.fz.views
         c = "clip.visual."
-        B = image.shape[0]
+        B0 = image.shape[0]
         S_in = v.image_size * (2 if self.views == 5 else 1)
-        if tuple(image.shape[1:]) != (3, S_in, S_in):
-            raise ValueError(f"image must be (B,3,{S_in},{S_in}), got {tuple(image.shape)}")
-        if image.dtype not in (torch.float32, bf16):
-            image = image.float()
-        image = image.contiguous()
-        if self.views == 5:  # [global bicubic | TL | TR | BL | BR] x B, view-major (llama_ens5.py:383-385)
-            image = ops.build_views(image, vw["views"], B, v.image_size)
-            B = 5 * B
         N, Wv, g2 = v.tokens, v.width, v.grid * v.grid
+        streams = [image] if depth is None else [image, depth]
+        for s, im in enumerate(streams):
+            if tuple(im.shape) != (B0, 3, S_in, S_in):
+                raise ValueError(f"image must be ({B0},3,{S_in},{S_in}), got {tuple(im.shape)}")
+            if im.dtype not in (torch.float32, bf16):
+                im = im.float()
+            im = im.contiguous()
+            if self.views == 5:  # [global bicubic | TL | TR | BL | BR] x B, view-major (llama_ens5.py:383-385)
+                ops.build_views(im, vw["views"][s * 5 * B0:(s + 1) * 5 * B0], B0, v.image_size)
+            else:
+                ops.vit_patchify(im, vw["A"][s * B0 * g2:(s + 1) * B0 * g2], B0, v.image_size, v.patch, self.kpad)
+        B = len(streams) * self.views * B0
+        if self.views == 5:
+            ops.vit_patchify(vw["views"], vw["A"], B, v.image_size, v.patch, self.kpad)
         act = ops.ACT_QUICKGELU if v.quick_gelu else ops.ACT_GELU
-        ops.vit_patchify(image, vw["A"], B, v.image_size, v.patch, self.kpad)
         ops.gemm(vw["A"], f[c + "conv1_padded"], vw["po"])
         ops.vit_assemble_lnpre(vw["po"], f[c + "class_embedding"], f[c + "positional_embedding"],
                                f[c + "ln_pre.weight"], f[c + "ln_pre.bias"], vw["x"], B, g2, Wv, v.ln_eps)
@@ -401,7 +417,8 @@ class Engine:
         of M/model/meta.py:256-262 (loss in ws.loss; logits are overwritten by dlogits)."""
         a, w = self.args, self.w.views
         B, T = examples.shape
-        W = self.image_words if image is not None else 0
+        # the training forward splices the RGB stream only, also in the RGB-D build (M/model/meta.py:251)
+        W = self.visual_image_words if image is not None else 0
         ws = self.workspace(B, T, W, True)
         L, D = ws.L, a.dim
         if L > 2 * a.max_seq_len:
@@ -557,6 +574,28 @@ class Engine:
             self._broadcast_shards()
         return self.norm_sq
 
+    def optimizer_state_dict(self) -> Dict:
+        """This rank's AdamW state (fp32 master / m / v of the flat ranges it owns, step count) on the host
+        -- the `consolidated.*.optimizer.pth` payload of checkpoint.save_checkpoint (M/util/misc.py:390-406).
+        With the sharded optimiser every rank owns a different slice of the decay region."""
+        self._ensure_opt()
+        cpu = lambda ts: [t.detach().to("cpu") for t in ts]
+        return {"step": self.opt_step, "ranges": [(lo, hi, d) for lo, hi, d in self._opt_ranges()],
+                "shard_world": self.shard_world, "shard_rank": self.shard_rank,
+                "master": cpu(self.master), "m": cpu(self.m), "v": cpu(self.v)}
+
+    def load_optimizer_state_dict(self, sd: Dict) -> None:
+        """Inverse of optimizer_state_dict (resume, M/util/misc.py:510-523).  The sharding must match the
+        one the state was saved with."""
+        ranges = [(lo, hi, d) for lo, hi, d in self._opt_ranges()]
+        if [tuple(r) for r in sd["ranges"]] != ranges:
+            raise ValueError(f"optimizer state was saved for flat ranges {sd['ranges']}, this engine owns {ranges} "
+                             "(different model geometry or data-parallel sharding)")
+        to = lambda ts: [t.to(device=self.device, dtype=torch.float32).contiguous() for t in ts]
+        self.wait_weights()
+        self.master, self.m, self.v = to(sd["master"]), to(sd["m"]), to(sd["v"])
+        self.opt_step = int(sd["step"])
+
     def _broadcast_shards(self) -> None:
         import torch.distributed as dist
 
@@ -622,9 +661,14 @@ class Engine:
     def destroy_kv_cache(self) -> None:
         self.kcache, self.vcache, self.cache_B, self.dec = [], [], 0, None
 
-    def forward_inference(self, tokens: torch.Tensor, start_pos: int, image=None) -> torch.Tensor:
-        """Transformer.forward_inference (LLM/llama_ens5.py:490-531): fp32 last-position logits (B,V)."""
+    def forward_inference(self, tokens: torch.Tensor, start_pos: int, image=None, depth=None) -> torch.Tensor:
+        """Transformer.forward_inference (LLM/llama_ens5.py:490-531): fp32 last-position logits (B,V).
+        RGB-D build (LLM/llama_ens5_2images.py:511-547): the prefill takes both image streams or none."""
         a, w = self.args, self.w.views
+        if self.rgbd and (image is None or depth is None):
+            image = depth = None  # llama_ens5_2images.py:518: `if image is not None and depth_images is not None`
+        if not self.rgbd:
+            depth = None
         B, l = tokens.shape
         D, V = a.dim, a.vocab_size
         self.wait_weights()
@@ -647,9 +691,15 @@ class Engine:
             raise ValueError(f"sequence {start_pos + L} exceeds max_seq_len {a.max_seq_len}")
         ws = self.workspace(B, l, W, False)
         tokens = tokens.contiguous()
-        img = self.vit_forward(image, ws.vit) if W else None
-        ops.embed_splice(tokens, w["tok_embeddings.weight"], img, w["start_img"] if W else None,
-                         w["end_img"] if W else None, ws.x[0], B, l, self.vis.tokens if W else 0, D, self.views)
+        img = self.vit_forward(image, ws.vit, depth) if W else None
+        if W and depth is not None:
+            fz = self.fz.views
+            ops.embed_splice_rgbd(tokens, w["tok_embeddings.weight"], img, w["start_img"], w["end_img"],
+                                  fz["start_depth_img"], fz["end_depth_img"], ws.x[0], B, l, self.vis.tokens, D,
+                                  self.views)
+        else:
+            ops.embed_splice(tokens, w["tok_embeddings.weight"], img, w["start_img"] if W else None,
+                             w["end_img"] if W else None, ws.x[0], B, l, self.vis.tokens if W else 0, D, self.views)
         xa, xb = ws.x[0], ws.x[1]
         for i in range(a.n_layers):
             self._layer_fwd(i, xa, ws.xn[0], ws.qkv[0], ws.o[0], ws.h[0], ws.hn[0], ws.gu[0], ws.y[0], xb,

@@ -18,6 +18,7 @@ import torch
 import torch.nn as nn
 
 from ... import _lib
+from ...checkpoint import holder_class_for
 from ...engine import Engine
 
 bf16 = torch.bfloat16
@@ -61,6 +62,7 @@ class _Vision:
     quick_gelu: bool
     views: int = 1
     ln_eps: float = 1e-5
+    rgbd: bool = False  # second (depth) image stream with its own tags: LLM/llama_ens5_2images.py
 
     @property
     def grid(self):
@@ -83,10 +85,13 @@ class TransformerBlock(_Holder):
 def _register(root: nn.Module, dotted: str, tensor: torch.Tensor, requires_grad: bool) -> nn.Parameter:
     parts = dotted.split(".")
     mod = root
-    for p in parts[:-1]:
+    for k, p in enumerate(parts[:-1]):
         child = mod._modules.get(p)
         if child is None:
-            child = _Holder()
+            # the module that owns a model-parallel weight carries the fairscale layer's class name, so
+            # the reference's checkpoint loader can resolve its split dimension (checkpoint.py)
+            leaf_cls = holder_class_for(dotted) if k == len(parts) - 2 else None
+            child = (leaf_cls or _Holder)()
             mod.add_module(p, child)
         mod = child
     prm = nn.Parameter(tensor, requires_grad=requires_grad)
@@ -135,6 +140,9 @@ class _TrainFn(torch.autograd.Function):
 
 
 class Transformer(nn.Module):
+    _RGBD = False  # llama_b200_2images.Transformer flips this (the reference's llama_ens5_2images build)
+    _FROZEN_TAGS = ("start_depth_img", "end_depth_img")
+
     def __init__(self, args: ModelArgs, with_visual: bool = False):
         super().__init__()
         if not torch.cuda.is_available():
@@ -151,9 +159,12 @@ class Transformer(nn.Module):
             if args.image_views not in (1, 5):
                 raise ValueError("image_views must be 1 (single view) or 5 (reference tiling, llama_ens5.py:383-385)")
             vis = _Vision(args.image_size, args.vit_patch, args.vit_width, args.vit_layers, args.vit_heads,
-                          args.vit_mlp, bool(quick), views=args.image_views)
+                          args.vit_mlp, bool(quick), views=args.image_views, rgbd=self._RGBD)
         self.engine = Engine(args, vis, dev)
-        self.image_words = self.engine.image_words  # views x (start_img + N ViT tokens + end_img)
+        # views x (start_img + N ViT tokens + end_img); the RGB-D build counts both streams in image_words
+        # and one in visual_image_words (LLM/llama_ens5_2images.py:335-336)
+        self.image_words = self.engine.image_words
+        self.visual_image_words = self.engine.visual_image_words
         self.cache_image_words = 0
         if with_visual:
             # the size the data pipeline must deliver (M/main_finetune.py:295 reads model.llma.image_size)
@@ -164,7 +175,9 @@ class Transformer(nn.Module):
         for name, t in views.items():
             frozen = name.startswith("clip.")
             prm = _register(self, name, t, requires_grad=not frozen)
-            if not frozen:
+            # the depth tags are trainable by name (llama_ens5_2images.py:343-344) but the training forward
+            # never reaches them (meta.py:251), so like in the reference their .grad stays None
+            if not frozen and name not in self._FROZEN_TAGS:
                 self._trainable_named.append((name, prm))
         self._trainable = [p for _, p in self._trainable_named]
         self._anchor = torch.zeros((), device=dev, requires_grad=True)
@@ -181,7 +194,7 @@ class Transformer(nn.Module):
         if seed is not None:
             g.manual_seed(seed)
         for name, p in self.named_parameters():
-            if name in ("start_img", "end_img"):
+            if name in ("start_img", "end_img") + self._FROZEN_TAGS:
                 p.copy_(torch.rand(p.shape, device=p.device, generator=g))
             elif name.endswith("norm.weight") or ".ln_" in name and name.endswith(".weight") or name == "visual_proj.1.weight":
                 p.fill_(1.0)
@@ -241,6 +254,11 @@ class Transformer(nn.Module):
     def forward(self, examples: torch.Tensor, image: Optional[torch.Tensor] = None, depth_imgs=None):
         """LLM/llama_ens5.py:461-487: (B,T) int64 ids [+ (B,3,S,S) image] -> (B,T,V) bf16 logits of the
         text positions.  Differentiable w.r.t. every trainable parameter."""
+        if depth_imgs is not None:
+            # dead code in the reference: MetaModel.forward drops depth_imgs (M/model/meta.py:251), and
+            # llama_ens5_2images.forward would return T + depth_words logit rows (:507 slices by the RGB
+            # count only), which the loss at meta.py:256-262 cannot consume
+            raise NotImplementedError("the training forward takes the RGB stream only (M/model/meta.py:251)")
         self._check_alias()
         self.engine.destroy_kv_cache()  # training always disables the kv cache (:462)
         examples = examples.to(self.engine.device)
@@ -266,14 +284,17 @@ class Transformer(nn.Module):
         return ws.loss[0].clone()
 
     @torch.inference_mode()
-    def forward_inference(self, tokens: torch.Tensor, start_pos: int, image=None) -> torch.Tensor:
+    def forward_inference(self, tokens: torch.Tensor, start_pos: int, image=None, depth_images=None) -> torch.Tensor:
         """LLM/llama_ens5.py:490-531: fp32 (B,V) logits of the last position; KV cache keyed on
-        start_pos == 0; decode positions offset by cache_image_words (:520)."""
+        start_pos == 0; decode positions offset by cache_image_words (:520).  `depth_images` is used by the
+        RGB-D build only (LLM/llama_ens5_2images.py:511-547)."""
         dev = self.engine.device
         tokens = tokens.to(dev)
         if image is not None:
             image = image.to(dev)
-        out = self.engine.forward_inference(tokens, start_pos, image)
+        if depth_images is not None:
+            depth_images = depth_images.to(dev)
+        out = self.engine.forward_inference(tokens, start_pos, image, depth_images)
         self.cache_image_words = self.engine.cache_image_words
         return out
 

@@ -15,6 +15,32 @@ import torch
 import torch.nn as nn
 
 
+def plan_generation(prompt_tokens: Sequence[Sequence[int]], max_seq_len: int, image_words: int, max_gen_len: int,
+                    eos_id: int, stop_sequences: Iterable[Sequence[int]] = ()) -> Dict:
+    """Host-side set-up of `generate` (meta.py:419-442), device-free: the sequence budget
+    (`max_seq_len -= image_words` when images are given :423-425, `total_len` :427), left truncation of
+    long prompts (:428-429), the pad-0 token matrix with the prompts written in (:431-435 --
+    `input_text_mask[b, c]` is `c < prompt_len[b]`), `start_pos = min prompt length` (:436), and the stop
+    sequences ([eos] first, :439-442) flattened for `a3_generate_step`."""
+    prompts = [list(t) for t in prompt_tokens]
+    min_prompt_size = min(len(t) for t in prompts)
+    max_prompt_size = max(len(t) for t in prompts)
+    max_seq_len = max_seq_len - image_words
+    total_len = min(max_seq_len, max_gen_len + max_prompt_size)
+    prompts = [t[-(max_seq_len - max_gen_len):] for t in prompts]
+    tokens = torch.zeros((len(prompts), total_len), dtype=torch.long)
+    for k, t in enumerate(prompts):
+        tokens[k, :len(t)] = torch.tensor(t, dtype=torch.long)
+    stops = [[eos_id]] + [list(s) for s in stop_sequences]
+    offs = [0]
+    for st in stops:
+        offs.append(offs[-1] + len(st))
+    return {"prompts": prompts, "total_len": total_len, "start_pos": min_prompt_size, "tokens": tokens,
+            "prompt_len": torch.tensor([len(t) for t in prompts], dtype=torch.int32), "stops": stops,
+            "stop_flat": torch.tensor([t for st in stops for t in st], dtype=torch.long),
+            "stop_offsets": torch.tensor(offs, dtype=torch.int32)}
+
+
 class MetaModel(nn.Module):
     def __init__(self, llama_type: str = "llama_b200", llama_config: Union[str, dict, Sequence] = (),
                  tokenizer_path: Optional[str] = None, with_visual: bool = False, max_seq_len: int = 4096,
@@ -53,6 +79,79 @@ class MetaModel(nn.Module):
         self.criterion = torch.nn.CrossEntropyLoss(ignore_index=0)
         self._set_default_trainability(pretrain_stage)
         self.is_peft = getattr(self.llma, "is_peft", False)
+
+    @classmethod
+    def from_pretrained(cls, pretrained_path: Union[str, List[str]], llama_type: Optional[str] = None,
+                        llama_config: Optional[Union[str, List[str]]] = None, tokenizer_path: Optional[str] = None,
+                        with_visual: bool = False, max_seq_len: int = 4096, mp_group=None,
+                        dtype=torch.bfloat16, device="cuda", quant: bool = False, max_batch_size: int = 32):
+        """meta.py:88-222: build the model from a checkpoint directory (or a list applied in order) --
+        `llama_type` from its `meta.json`, the config from `config.json`, the tokenizer probed next to the
+        weights -- then stream the `consolidated.*.pth` shards into the flat HBM buffers
+        (a3vlm_b200.checkpoint: any model-parallel shard count is merged on the way in).
+        Unsupported here, raising instead of silently differing: `hf://` paths (no network), a
+        model-parallel group (this implementation is model-parallel size 1), 4-bit `quant`, a dtype other
+        than bf16.  A `meta.json` naming one of the reference's own plugins is mapped to its B200
+        counterpart: llama_ens5 -> llama_b200, llama_ens5_2images -> llama_b200_2images."""
+        import os
+        import warnings
+
+        from .. import checkpoint as ckpt
+
+        if isinstance(pretrained_path, str):
+            pretrained_path = [pretrained_path]
+        if pretrained_path is None or len(pretrained_path) == 0:
+            raise ValueError("pretrained_path should be specified")
+        for path in pretrained_path:
+            if path.startswith("hf://"):
+                raise NotImplementedError("hf:// checkpoints need network access; download them and pass the directory")
+        if mp_group is not None:
+            import torch.distributed as dist
+
+            if dist.get_world_size(mp_group) != 1:
+                raise NotImplementedError("llama_b200 is model-parallel size 1 (the weights fit one B200)")
+        if quant:
+            raise NotImplementedError("4-bit quantisation is outside the B200 hot path (SURVEY section 8)")
+        if dtype != torch.bfloat16:
+            raise NotImplementedError("llama_b200 computes in bf16 (fp32 masters live in the optimiser)")
+        last = pretrained_path[-1]
+        if llama_type is None:
+            mj = os.path.join(last, "meta.json")
+            if not os.path.exists(mj):
+                raise ValueError("Cannot determine llama_type")
+            with open(mj, "r") as f:
+                llama_type = json.load(f)["llama_type"]
+        llama_type = {"llama_ens5": "llama_b200", "llama_ens5_2images": "llama_b200_2images"}.get(llama_type, llama_type)
+        if llama_config is None:
+            cj = os.path.join(last, "config.json")
+            llama_config = [cj] if os.path.exists(cj) else []
+        if isinstance(llama_config, str):
+            llama_config = [llama_config]
+        cfgs: List = []
+        for c in llama_config:  # config.json written by the reference carries only its own ModelArgs fields
+            if isinstance(c, str):
+                with open(c, "r") as f:
+                    c = json.loads(f.read())
+            cfgs.append(c)
+        for c in cfgs:  # max_seq_len / max_batch_size of a saved config are set by the arguments instead
+            c.pop("max_seq_len", None)
+            c.pop("max_batch_size", None)
+        if tokenizer_path is None:
+            tokenizer_path = ckpt.probe_tokenizer_path_from_pretrained(last)
+            # extension: a checkpoint saved from a tokenizer-less (token-level) model carries vocab_size in
+            # its config.json and loads without one; otherwise as the reference (meta.py:189-193)
+            if tokenizer_path is None and not any(c.get("vocab_size", -1) > 0 for c in cfgs):
+                raise FileNotFoundError("No tokenizer available")
+        with torch.cuda.device(torch.device(device) if str(device) != "cuda" else torch.cuda.current_device()):
+            model = cls(llama_type, cfgs, tokenizer_path, with_visual, max_seq_len, max_batch_size=max_batch_size)
+        print(f"Loading pretrained weights from {pretrained_path} ...")
+        load_result = ckpt.load_tensor_parallel_model_list(model, pretrained_path)
+        if load_result != {"missing_keys": [], "unexpected_keys": []}:
+            warnings.warn(f"checkpoint and model mismatch: \n{load_result}")
+        else:
+            print("all params match perfectly!")
+        model.eval()
+        return model
 
     # ------------------------------------------------------------------ trainability (meta.py:224-232)
     def get_trainable_params(self, pretrain_stage: bool = False):
@@ -101,58 +200,82 @@ class MetaModel(nn.Module):
     @torch.inference_mode()
     def generate_tokens(self, prompt_tokens: Sequence[Sequence[int]], images=None, max_gen_len: int = 512,
                         temperature: float = 0.0, top_p: float = 0.95,
-                        stop_sequences: Iterable[Sequence[int]] = (), eos_id: Optional[int] = None):
+                        stop_sequences: Iterable[Sequence[int]] = (), eos_id: Optional[int] = None,
+                        depth_images=None, generator: Optional[torch.Generator] = None, sync_lag: int = 4):
         """The token-level body of `generate` (meta.py:414-479).  Returns (generated ids per row,
-        tokens tensor, stop_pos)."""
+        tokens tensor, stop_pos).
+
+        Same control flow as the reference, with the per-token tensor work on the device kernels:
+        the token choice is `a3_argmax` (temperature 0, :461) or `a3_sample_top_p` (:456-459,568-583,
+        uniforms from `generator`), and the force-feed / token write / stop-sequence bookkeeping of
+        :463-475 is ONE `a3_generate_step` launch that also publishes `stopped.all()` (:476) to a
+        device flag.  The host reads that flag `sync_lag` steps late through pinned memory, so it never
+        stalls the GPU on a per-token `.all()` sync; the (at most `sync_lag`) steps issued after every
+        row had stopped change nothing the reference returns (stop_pos is frozen, their tokens are
+        zeroed again below)."""
+        from collections import deque
+
+        from .. import ops
+
         dev = self._device()
         if images is not None:
             images = images.to(dev)
+        if depth_images is not None:
+            depth_images = depth_images.to(dev)
         bsz = len(prompt_tokens)
         args = self.llma.args
         assert bsz <= args.max_batch_size, (bsz, args.max_batch_size)
-        prompt_tokens = [list(t) for t in prompt_tokens]
-        min_prompt_size = min(len(t) for t in prompt_tokens)
-        max_prompt_size = max(len(t) for t in prompt_tokens)
-        max_seq_len = args.max_seq_len
-        if images is not None:
-            max_seq_len -= self.llma.image_words
-        total_len = min(max_seq_len, max_gen_len + max_prompt_size)
-        for k, t in enumerate(prompt_tokens):
-            prompt_tokens[k] = t[-(max_seq_len - max_gen_len):]
-        tokens = torch.full((bsz, total_len), 0, device=dev, dtype=torch.long)
-        input_text_mask = torch.full((bsz, total_len), False, device=dev)
-        for k, t in enumerate(prompt_tokens):
-            tokens[k, :len(t)] = torch.tensor(t, device=dev).long()
-            input_text_mask[k, :len(t)] = True
-        start_pos, prev_pos = min_prompt_size, 0
         if eos_id is None:
             eos_id = self.tokenizer.eos_id
-        l_stop_tokens = [[eos_id]] + [list(s) for s in stop_sequences]
-        l_stop_tokens = [torch.tensor(s, dtype=tokens.dtype, device=dev) for s in l_stop_tokens]
+        plan = plan_generation(prompt_tokens, args.max_seq_len, self.llma.image_words if images is not None else 0,
+                               max_gen_len, eos_id, stop_sequences)
+        prompt_tokens, total_len, l_stop_tokens = plan["prompts"], plan["total_len"], plan["stops"]
+        tokens = plan["tokens"].to(dev)
+        prompt_len = plan["prompt_len"].to(dev)
+        stop_flat, stop_offs = plan["stop_flat"].to(dev), plan["stop_offsets"].to(dev)
+        start_pos, prev_pos = plan["start_pos"], 0
         stopped = torch.zeros(bsz, dtype=torch.bool, device=dev)
-        stop_pos = torch.full((bsz,), start_pos + 1, device=dev)
+        stop_pos = torch.full((bsz,), start_pos + 1, device=dev, dtype=torch.long)
+        next_token = torch.empty(bsz, dtype=torch.long, device=dev)
+        flags = torch.zeros(max(total_len, 1), dtype=torch.int32, device=dev)
+        flags_h = torch.zeros(max(total_len, 1), dtype=torch.int32).pin_memory()
+        uniforms = None
+        if temperature > 0:
+            uniforms = torch.rand((total_len, bsz), device=dev, dtype=torch.float32, generator=generator)
+        pending = deque()
+        last = None  # the step at which the reference's `if stopped.all(): break` fires
         for cur_pos in range(start_pos, total_len):
-            logits = self.llma.forward_inference(tokens[:, prev_pos:cur_pos], prev_pos,
-                                                 images if prev_pos == 0 else None).float()
-            if temperature > 0:
-                probs = torch.softmax(logits / temperature, dim=-1)
-                next_token = self.sample_top_p(probs, top_p)
+            first = prev_pos == 0
+            if depth_images is not None:  # meta.py:447-451
+                logits = self.llma.forward_inference(tokens[:, prev_pos:cur_pos], prev_pos,
+                                                     images if first else None, depth_images if first else None)
             else:
-                next_token = self._argmax(logits)
-            next_token = next_token.reshape(-1)
-            next_token = torch.where(input_text_mask[:, cur_pos], tokens[:, cur_pos], next_token)
-            tokens[:, cur_pos] = next_token
-            stop_pos = torch.where(stopped, stop_pos, cur_pos + 1)
-            for stop_token in l_stop_tokens:
-                if cur_pos + 1 - len(stop_token) >= 0:
-                    cond1 = (tokens[:, cur_pos + 1 - len(stop_token):cur_pos + 1] == stop_token.unsqueeze(0)).all(dim=-1)
-                    cond2 = ~input_text_mask[:, cur_pos]
-                    new_stop_cond = cond1 * cond2 * (~stopped)
-                    stop_pos = torch.where(new_stop_cond, cur_pos + 1 - len(stop_token), stop_pos)
-                    stopped = torch.logical_or(new_stop_cond, stopped)
-            if stopped.all():
-                break
+                logits = self.llma.forward_inference(tokens[:, prev_pos:cur_pos], prev_pos, images if first else None)
+            logits = logits.float().contiguous()  # already fp32 and contiguous: no kernel
+            if temperature > 0:
+                ops.sample_top_p(logits, temperature, top_p, uniforms[cur_pos], next_token)
+            else:
+                ops.argmax(logits, next_token)
+            ops.generate_step(tokens, prompt_len, next_token, cur_pos, stop_flat, stop_offs, len(l_stop_tokens),
+                              stopped, stop_pos, flags[cur_pos:cur_pos + 1])
+            flags_h[cur_pos:cur_pos + 1].copy_(flags[cur_pos:cur_pos + 1], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            pending.append((cur_pos, ev))
+            if len(pending) > sync_lag:
+                p, e = pending.popleft()
+                e.synchronize()
+                if int(flags_h[p]):
+                    last = p
+                    break
             prev_pos = cur_pos
+        while last is None and pending:
+            p, e = pending.popleft()
+            e.synchronize()
+            if int(flags_h[p]):
+                last = p
+        if last is not None and last + 1 < total_len:
+            tokens[:, last + 1:] = 0  # the reference stopped writing here
         rows = tokens.tolist()
         sp = stop_pos.tolist()
         out = [rows[i][len(prompt_tokens[i]):sp[i]] for i in range(bsz)]
@@ -173,12 +296,11 @@ class MetaModel(nn.Module):
             raise ValueError(f"{self.__class__}.generate expects a batched LIST of prompts, but str is given")
         if self.tokenizer is None:
             raise RuntimeError("generate(prompts: List[str]) needs a tokenizer; use generate_tokens")
-        if depth_images is not None:
-            raise NotImplementedError("the RGB-D variant (llama_ens5_2images) is out of scope (SURVEY 8f)")
         prompt_tokens = [self.tokenizer.encode(x, bos=True, eos=False) for x in prompts]
         stops = [self.tokenizer.encode_segment(s) for s in additional_stop_symbols]
         stops += [self.tokenizer.encode_wo_prefix_space(s) for s in additional_stop_symbols]
-        out, _, _ = self.generate_tokens(prompt_tokens, images, max_gen_len, temperature, top_p, stops)
+        out, _, _ = self.generate_tokens(prompt_tokens, images, max_gen_len, temperature, top_p, stops,
+                                         depth_images=depth_images)
         return [self.tokenizer.decode(t) for t in out]
 
     @torch.inference_mode()
@@ -227,7 +349,9 @@ class MetaModel(nn.Module):
         yield {"text": generated, "end_of_content": True}
 
     def sample_top_p(self, probs, p):
-        """meta.py:568-583 (kept on torch: not on the measured greedy path)."""
+        """meta.py:568-583, same signature (probabilities in).  `generate` itself draws with the fused
+        `a3_sample_top_p` kernel straight from the logits; this torch form is kept for callers of the
+        reference API."""
         probs_sort, probs_idx = torch.sort(probs, dim=-1, descending=True)
         probs_sum = torch.cumsum(probs_sort, dim=-1)
         mask = probs_sum - probs_sort > p

@@ -271,6 +271,15 @@ def embed_splice(tokens, E, img, start_img, end_img, out, B, T, Nimg, D, n_views
     return out
 
 
+def embed_splice_rgbd(tokens, E, img, start_img, end_img, start_depth_img, end_depth_img, out, B, T, Nimg, D,
+                      n_views=1):
+    """RGB stream then depth stream, each view wrapped in its own tags (llama_ens5_2images.py:517-547)."""
+    rc = _L().a3_embed_splice_rgbd(_p(tokens), _p(E), _p(img), _p(start_img), _p(end_img), _p(start_depth_img),
+                                   _p(end_depth_img), _p(out), B, T, Nimg, D, img.stride(-2), n_views, _st())
+    _lib.check(rc, "a3_embed_splice_rgbd")
+    return out
+
+
 def embed_splice_bwd(tokens, dh, dE, d_img, d_start, d_end, B, T, Nimg, D, n_views=1):
     rc = _L().a3_embed_splice_bwd(_p(tokens), _p(dh), _p(dE), _p(d_img), _p(d_start), _p(d_end), B, T,
                                   Nimg, D, n_views, _st())
@@ -326,6 +335,31 @@ def argmax(logits, out):
     B, V = logits.shape
     _lib.check(_L().a3_argmax(_p(logits), logits.stride(0), B, V, _p(out), _st()), "a3_argmax")
     return out
+
+
+def sample_top_p(logits, temperature, top_p, u, out=None):
+    """Nucleus sampling of one token per row from fp32 logits [B][V] (meta.py:456-459,568-583) with the
+    uniforms u [B] in [0,1) supplied by the caller."""
+    B, V = logits.shape
+    assert logits.dtype == torch.float32 and logits.stride(1) == 1 and u.dtype == torch.float32 and u.numel() == B
+    if out is None:
+        out = torch.empty(B, device=logits.device, dtype=torch.int64)
+    rc = _L().a3_sample_top_p(_p(logits), logits.stride(0), B, V, float(temperature), float(top_p), _p(u),
+                              _p(out), _st())
+    _lib.check(rc, "a3_sample_top_p")
+    return out
+
+
+def generate_step(tokens, prompt_len, next_token, cur_pos, stop_tokens, stop_offsets, n_stop, stopped, stop_pos,
+                  all_stopped=None, fed_token=None):
+    """meta.py:463-477 for the whole batch in one launch (see include/a3vlm_b200.h)."""
+    B = tokens.shape[0]
+    assert tokens.dtype == torch.int64 and tokens.stride(1) == 1 and prompt_len.dtype == torch.int32
+    assert stopped.dtype in (torch.bool, torch.uint8) and stop_pos.dtype == torch.int64
+    rc = _L().a3_generate_step(_p(tokens), tokens.stride(0), _p(prompt_len), _p(next_token), int(cur_pos),
+                               _p(stop_tokens), _p(stop_offsets), int(n_stop), _p(stopped), _p(stop_pos),
+                               _p(all_stopped), _p(fed_token), B, _st())
+    _lib.check(rc, "a3_generate_step")
 
 
 # ----------------------------------------------------------------------------------------- optimiser

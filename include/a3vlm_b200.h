@@ -193,6 +193,15 @@ int a3_swiglu_bwd(const void* gu, const void* dy, void* dgu, int rows, int F, vo
 int a3_embed_splice(const long long* tokens, const void* E, const void* img, const void* start_img,
                     const void* end_img, void* h, int B, int T, int Nimg, int D, long long ld_img,
                     int n_views, void* stream);
+/* RGB-D variant (LLM/llama_ens5_2images.py:487-501,517-547): a second image stream follows the first,
+ * wrapped in its own tags: BOS | n_views x (start_img, Nimg, end_img) | n_views x (start_depth_img, Nimg,
+ * end_depth_img) | text.  img holds the 2*n_views views of both streams, view-major
+ * (img[((s*n_views + v)*B + b)*Nimg + i]); W = 2*n_views*(Nimg+2).  Forward only: the reference never
+ * feeds depth images to the training forward (meta.py:251 passes `images` alone). */
+int a3_embed_splice_rgbd(const long long* tokens, const void* E, const void* img, const void* start_img,
+                         const void* end_img, const void* start_depth_img, const void* end_depth_img,
+                         void* h, int B, int T, int Nimg, int D, long long ld_img, int n_views,
+                         void* stream);
 /* Backward: dE[tok] += dh rows of text positions (bf16 atomics), d_img, d_start, d_end. */
 int a3_embed_splice_bwd(const long long* tokens, const void* dh, void* dE, void* d_img,
                         float* d_start_f32, float* d_end_f32, int B, int T, int Nimg, int D,
@@ -230,6 +239,24 @@ int a3_cross_entropy(void* logits, long long ld, const long long* labels, float*
 int a3_loss_reduce(const float* row_loss, int rows, const int* count, float* out, void* stream);
 /* Greedy sampling (meta.py:461): argmax over fp32 logits [B][V], lowest index wins ties. */
 int a3_argmax(const float* logits, long long ld, int B, int V, long long* out, void* stream);
+/* Nucleus sampling (meta.py:456-459,568-583) in one launch, one CTA per row: probs =
+ * softmax(logits / temperature) in fp32; in descending order (ties by token id) keep the entries whose
+ * exclusive cumulative sum is <= top_p, renormalise, and draw by inverse CDF with the caller's uniform
+ * u[b] in [0,1) -- the distribution torch.multinomial samples in the reference; the uniform is an input
+ * because multinomial's random stream is not reproducible across devices.  No sort: the crossing value
+ * of the sorted cumulative sum is found by bisection over the float bit pattern.  V <= 51200. */
+int a3_sample_top_p(const float* logits, long long ld, int B, int V, float temperature, float top_p,
+                    const float* u, long long* out, void* stream);
+/* The body of the generation loop after the token choice (meta.py:463-477) for the whole batch in one
+ * launch: prompt force-feeding (prompt position = cur_pos < prompt_len[b]), tokens[b][cur_pos] write,
+ * stop_pos / stopped update against n_stop stop sequences (stop_tokens flattened, sequence s =
+ * stop_tokens[stop_offsets[s] .. stop_offsets[s+1])), all_stopped[0] = all(stopped) (the `break`
+ * condition of :476, read by the host whenever it likes -- no per-token sync), fed_token[b] (nullable) =
+ * the token written.  tokens int64 [B][ld_tokens]; stopped uint8 [B]; stop_pos int64 [B]. */
+int a3_generate_step(long long* tokens, long long ld_tokens, const int* prompt_len,
+                     const long long* next_token, int cur_pos, const long long* stop_tokens,
+                     const int* stop_offsets, int n_stop, unsigned char* stopped, long long* stop_pos,
+                     int* all_stopped, long long* fed_token, int B, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Optimiser (main_finetune.py:284-285, util/misc.py:586-599, util/clip_grad.py:187-193).

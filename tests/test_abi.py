@@ -30,7 +30,7 @@ def test_signatures_have_no_torch_types():
     from a3vlm_b200 import _lib
 
     allowed = {"int", "float", "long long", "void", "const void*", "void*", "const float*", "float*",
-               "const long long*", "long long*", "const int*", "int*", "const char*"}
+               "const long long*", "long long*", "const int*", "int*", "const char*", "unsigned char*"}
     for name, (ret, args) in _lib.PROTOS.items():
         assert ret.replace(" ", "") in {a.replace(" ", "") for a in allowed}, (name, ret)
         for t, _ in args:

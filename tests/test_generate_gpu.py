@@ -1,0 +1,277 @@
+"""GPU parity of the device-side generation loop and of the RGB-D build (8f #1):
+
+* `a3_generate_step` + the lagged stop check of `MetaModel.generate_tokens` against the oracle's
+  line-by-line restatement of meta.py:379-485 -- integer work, compared EXACTLY (tokens tensor, stop
+  positions, generated ids, and the sequence of calls made to the inner model);
+* `a3_sample_top_p` against the oracle's sort / cumsum / mask / renormalise restatement of
+  meta.py:568-583 with the draw made explicit (inverse CDF at a supplied uniform).  Floating point:
+  the kernel's token must be the oracle's, or one whose CDF interval contains u within 2e-6 (the two
+  sides sum 32000 fp32 probabilities in different orders; fp32 cumsum resolution near 1 is 6e-8 per
+  element) -- plus exact checks where the maths is order-independent (top_p = 0 is the argmax; the
+  chosen token always lies inside the nucleus) and a goodness-of-fit check of the sampled distribution;
+* `llama_b200_2images`: prefill logits and greedy ids of the RGB + depth splice against the oracle's
+  restatement of llama_ens5_2images.py, same tolerances as tests/test_e2e_gpu.py.
+"""
+import os
+import sys
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+class _FakeLLM(torch.nn.Module):
+    """Deterministic inner model on any device: next token = (last * 7 + 3 + row) % V, as one-hot logits."""
+
+    def __init__(self, V=50, max_seq_len=32, image_words=0, device="cpu"):
+        super().__init__()
+        self.args = SimpleNamespace(max_seq_len=max_seq_len, max_batch_size=8)
+        self.image_words = image_words
+        self.w = torch.nn.Parameter(torch.zeros(1, device=device))
+        self.V = V
+        self.calls = []
+
+    def forward_inference(self, tokens, start_pos, image=None):
+        self.calls.append((tuple(tokens.shape), start_pos, image is not None))
+        row = torch.arange(tokens.shape[0], device=tokens.device)
+        nxt = (tokens[:, -1] * 7 + 3 + row) % self.V
+        return torch.nn.functional.one_hot(nxt, self.V).float() * 10
+
+
+def _meta_with(llma):
+    from a3vlm_b200.model.meta import MetaModel
+
+    m = MetaModel.__new__(MetaModel)
+    torch.nn.Module.__init__(m)
+    m.llma = llma
+    m.tokenizer = None
+    return m
+
+
+CASES = [
+    # unequal prompts (force-feeding), a multi-token stop sequence, eos
+    dict(prompts=[[1, 5, 6], [1, 9, 10, 11, 12]], max_gen_len=6, stops=[[38, 19], [18, 29]], max_seq_len=32),
+    # every row stops early: the loop must break (lagged) and leave the tail of `tokens` zero
+    # (row 0 emits 31 20 43 ..., row 1 is fed 31 then emits 21 1 ..., row 2 emits 24 23 16 17 ...)
+    dict(prompts=[[1, 4], [1, 4, 31], [1, 17]], max_gen_len=20, stops=[[43], [21, 1], [16, 17]], max_seq_len=64),
+    # left truncation + budget-bound total_len with image words
+    dict(prompts=[[1] + list(range(3, 30)), [1, 4]], max_gen_len=5, stops=[], max_seq_len=24, image_words=7),
+    # a stop sequence that only matches inside a prompt must not stop the row (cond2, meta.py:471)
+    dict(prompts=[[1, 38, 19, 6], [1, 8]], max_gen_len=8, stops=[[38, 19]], max_seq_len=32),
+    # single row, stop sequence longer than the generated text so far
+    dict(prompts=[[1, 2, 3]], max_gen_len=4, stops=[[5, 6, 7, 8, 9, 10, 11]], max_seq_len=16),
+]
+
+
+@pytest.mark.parametrize("case", range(len(CASES)))
+@pytest.mark.parametrize("lag", [0, 1, 4])
+def test_generate_loop_token_exact_vs_oracle(case, lag):
+    import a3vlm_oracle as O
+
+    c = CASES[case]
+    iw = c.get("image_words", 0)
+    img = torch.zeros(1) if iw else None
+    dev_llm = _FakeLLM(max_seq_len=c["max_seq_len"], image_words=iw, device="cuda")
+    m = _meta_with(dev_llm)
+    out, toks, sp = m.generate_tokens(c["prompts"], img, max_gen_len=c["max_gen_len"], eos_id=2,
+                                      stop_sequences=c["stops"], sync_lag=lag)
+    cpu_llm = _FakeLLM(max_seq_len=c["max_seq_len"], image_words=iw)
+    orc = SimpleNamespace(args=O.ModelArgs(max_seq_len=c["max_seq_len"], max_batch_size=8), image_words=iw,
+                          forward_inference=cpu_llm.forward_inference)
+    ref, rtoks, rsp = O.generate_tokens(orc, c["prompts"], images=img, max_gen_len=c["max_gen_len"], eos_id=2,
+                                        stop_sequences=c["stops"])
+    assert out == ref, (out, ref)
+    assert torch.equal(toks.cpu(), rtoks), (toks.cpu(), rtoks)
+    assert torch.equal(sp.cpu(), rsp)
+    # same calls to the inner model; at most `lag` extra single-token steps after every row had stopped
+    n = len(cpu_llm.calls)
+    assert dev_llm.calls[:n] == cpu_llm.calls
+    assert len(dev_llm.calls) - n <= lag
+    assert all(cl[0][1] == 1 for cl in dev_llm.calls[1:])
+
+
+def _sample_case(B, V, temperature, top_p, seed, kind):
+    g = torch.Generator().manual_seed(seed)
+    scale = {"flat": 0.3, "normal": 3.0, "peaked": 10.0, "ties": 3.0}[kind]
+    logits = torch.randn(B, V, generator=g) * scale
+    if kind == "ties":
+        logits = logits.round()
+    u = torch.rand(B, generator=g)
+    u[0], u[-1] = 0.0, 1.0 - 2.0 ** -24
+    return logits, u
+
+
+@pytest.mark.parametrize("V", [32000, 1000, 50])
+@pytest.mark.parametrize("kind", ["flat", "normal", "peaked", "ties"])
+def test_sample_top_p_matches_oracle(V, kind):
+    import a3vlm_oracle as O
+    from a3vlm_b200 import ops
+
+    B = 24
+    exact = total = 0
+    for temperature, top_p in [(1.0, 0.75), (0.1, 0.75), (0.7, 0.95), (1.0, 1.0), (1.0, 0.3)]:
+        logits, u = _sample_case(B, V, temperature, top_p, seed=V + int(top_p * 100), kind=kind)
+        got = ops.sample_top_p(logits.cuda(), temperature, top_p, u.cuda()).cpu()
+        # fp32 softmax as the reference; the sort / cumsum restatement then runs in float64 so that the
+        # comparison is against the exact answer rather than against a sequential fp32 cumsum's own noise
+        probs = torch.softmax(logits / temperature, dim=-1).double()
+        ref, _, _ = O.sample_top_p_u(probs, top_p, u.double())
+        lo, hi = O.top_p_token_interval(probs, top_p, got)
+        tol = 2e-6
+        ok = (got == ref) | ((lo - tol <= u) & (u <= hi + tol))
+        assert ok.all(), (temperature, top_p, got[~ok], ref[~ok], u[~ok], lo[~ok], hi[~ok])
+        # inside the nucleus: the chosen token's pre-mask probability rank keeps exclusive cumsum <= top_p
+        ps, pi = torch.sort(probs, dim=-1, descending=True, stable=True)
+        excl = torch.cumsum(ps, -1) - ps
+        rank = (pi == got.reshape(-1, 1)).float().argmax(-1, keepdim=True)
+        assert (torch.gather(excl, -1, rank).reshape(-1) <= top_p + tol).all()
+        exact += int((got == ref).sum())
+        total += B
+    assert exact >= 0.9 * total, (exact, total)  # boundary cases are rare
+
+
+def test_sample_top_p_zero_is_argmax_and_rows_are_independent():
+    from a3vlm_b200 import ops
+
+    g = torch.Generator().manual_seed(3)
+    logits = torch.randn(16, 32000, generator=g) * 4
+    u = torch.rand(16, generator=g)
+    got = ops.sample_top_p(logits.cuda(), 0.8, 0.0, u.cuda()).cpu()
+    assert torch.equal(got, logits.argmax(-1))
+    # a strided view (ld != V) and a different batch give the same per-row answers
+    wide = torch.zeros(16, 32768)
+    wide[:, :32000] = logits
+    got2 = ops.sample_top_p(wide.cuda()[:, :32000], 0.8, 0.9, u.cuda()).cpu()
+    got3 = ops.sample_top_p(logits[5:9].cuda(), 0.8, 0.9, u[5:9].cuda()).cpu()
+    assert torch.equal(got2[5:9], got3)
+
+
+def test_sample_top_p_distribution():
+    """Goodness of fit: 65536 draws from one 64-token distribution follow the renormalised nucleus."""
+    from a3vlm_b200 import ops
+
+    g = torch.Generator().manual_seed(11)
+    row = torch.randn(64, generator=g) * 1.5
+    n = 65536
+    u = torch.rand(n, generator=g)
+    got = ops.sample_top_p(row.repeat(n, 1).cuda(), 1.0, 0.9, u.cuda()).cpu()
+    probs = torch.softmax(row, -1)
+    ps, pi = torch.sort(probs, descending=True, stable=True)
+    keep = (torch.cumsum(ps, -1) - ps) <= 0.9
+    expect = torch.zeros(64)
+    expect[pi[keep]] = ps[keep] / ps[keep].sum()
+    freq = torch.bincount(got, minlength=64).float() / n
+    assert freq[expect == 0].sum() == 0  # nothing outside the nucleus
+    assert (freq - expect).abs().max() < 4 * (expect.max() / n) ** 0.5 + 1e-3
+
+
+def _tiny(rgbd, views=1, seed=21):
+    import a3vlm_oracle as O
+
+    a = O.ModelArgs(dim=256, n_layers=2, n_heads=2, vocab_size=512, multiple_of=64, max_seq_len=160 if views == 5 else 64,
+                    max_batch_size=4)
+    v = O.VisionArgs(image_size=28, patch=14, width=128, layers=2, heads=2, mlp=256, views=views)
+    sd = O.init_params(a, v, seed=seed, output_scale=8.0, rgbd=rgbd)
+    return a, v, sd
+
+
+def _build(llama_type, a, v, sd):
+    from a3vlm_b200.model import MetaModel
+
+    cfg = dict(dim=a.dim, n_layers=a.n_layers, n_heads=a.n_heads, vocab_size=a.vocab_size, multiple_of=a.multiple_of,
+               image_size=v.image_size, image_views=v.views, vit_width=v.width, vit_layers=v.layers, vit_heads=v.heads,
+               vit_mlp=v.mlp)
+    m = MetaModel(llama_type, cfg, None, with_visual=True, max_seq_len=a.max_seq_len, max_batch_size=4)
+    missing, unexpected = m.llma.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    return m
+
+
+@pytest.mark.parametrize("views", [1, 5])
+def test_rgbd_prefill_and_greedy_match_oracle(views):
+    import a3vlm_oracle as O
+    from test_e2e_gpu import check
+
+    a, v, sd = _tiny(True, views)
+    m = _build("llama_b200_2images", a, v, sd)
+    per = views * (v.tokens + 2)
+    assert m.llma.image_words == 2 * per and m.llma.visual_image_words == per  # llama_ens5_2images.py:335-336
+    assert {"llma.start_depth_img", "llma.end_depth_img"} <= set(m.get_trainable_params())
+    orc = O.OracleTransformer(a, v, sd, rgbd=True)
+    g = torch.Generator().manual_seed(5)
+    S = v.image_size * (2 if views == 5 else 1)
+    img, dep = torch.randn(2, 3, S, S, generator=g), torch.randn(2, 3, S, S, generator=g)
+    tok = torch.randint(3, 512, (2, 6), generator=g)
+    tok[:, 0] = 1
+    ref = orc.forward_inference(tok, 0, img, dep)
+    got = m.llma.forward_inference(tok, 0, img, dep)
+    check("rgbd_prefill_logits", got, ref)
+    assert m.llma.cache_image_words == 2 * per == orc.cache_image_words
+    # swapping the two streams must change the result (the depth tags and order matter)
+    swapped = m.llma.forward_inference(tok, 0, dep, img)
+    assert (swapped - got).abs().max() > 1e-3
+    # the RGB-D build ignores a lone RGB image at inference (llama_ens5_2images.py:518)
+    lone = m.llma.forward_inference(tok, 0, img)
+    check("rgbd_lone_image_is_text_only", lone, orc.forward_inference(tok, 0, img))
+    assert m.llma.cache_image_words == 0
+    # greedy decode with both streams, unequal prompts
+    prompts = [[1, 17, 33, 49], [1, 100, 101, 102, 103, 104]]
+    ref_gen, ref_toks, _ = O.generate_tokens(orc, prompts, images=img, depth_images=dep, max_gen_len=8, eos_id=2)
+    out, toks, _ = m.generate_tokens(prompts, img, max_gen_len=8, eos_id=2, depth_images=dep)
+    assert out == ref_gen, (out, ref_gen)
+    assert torch.equal(toks.cpu(), ref_toks)
+
+
+def test_rgbd_training_forward_sees_rgb_only():
+    """meta.py:251 passes `images` alone: the 2images build trains exactly like the RGB build (same loss,
+    no gradient for the depth tags)."""
+    import a3vlm_oracle as O
+
+    a, v, sd = _tiny(True)
+    m = _build("llama_b200_2images", a, v, sd)
+    g = torch.Generator().manual_seed(9)
+    tok = torch.randint(3, 512, (2, 9), generator=g)
+    tok[:, 0] = 1
+    lab = tok.clone()
+    lab[:, :4] = 0
+    img = torch.randn(2, 3, 28, 28, generator=g)
+    orc = O.OracleTransformer(a, v, sd, rgbd=True)
+    with torch.no_grad():
+        ref = O.meta_forward_loss(orc, tok, lab, img).item()
+    loss, _ = m(tok.cuda(), lab.cuda(), images=img.cuda(), depth_imgs=img.cuda())
+    loss.backward()
+    assert abs(loss.item() - ref) <= 2e-3 * abs(ref), (loss.item(), ref)
+    assert m.llma.start_depth_img.grad is None and m.llma.start_img.grad is not None
+    with pytest.raises(NotImplementedError):
+        m.llma(tok.cuda(), img.cuda(), img.cuda())
+
+
+def test_sampled_generate_is_consistent_with_oracle_probabilities():
+    """End to end with temperature > 0: teacher-force the oracle on the CUDA-sampled tokens; every sampled
+    token's oracle CDF interval must contain that step's uniform within the bf16 logit noise (5e-2)."""
+    import a3vlm_oracle as O
+
+    a, v, sd = _tiny(False, seed=23)
+    m = _build("llama_b200", a, v, sd)
+    orc = O.OracleTransformer(a, v, sd)
+    g = torch.Generator().manual_seed(5)
+    img = torch.randn(2, 3, 28, 28, generator=g)
+    prompts = [[1, 17, 33, 49], [1, 100, 101, 102]]
+    T, P = 0.8, 0.9
+    gen = torch.Generator(device="cuda").manual_seed(77)
+    out, toks, sp = m.generate_tokens(prompts, img, max_gen_len=6, temperature=T, top_p=P, eos_id=2, generator=gen)
+    total_len = toks.shape[1]
+    u = torch.rand((total_len, 2), device="cuda", generator=torch.Generator(device="cuda").manual_seed(77)).cpu()
+    toks = toks.cpu()
+    for cur in range(4, total_len):
+        if (toks[:, cur] == 0).all():
+            break
+        logits = orc.forward_inference(toks[:, :cur], 0, img)
+        probs = torch.softmax(logits / T, dim=-1)
+        lo, hi = O.top_p_token_interval(probs, P, toks[:, cur])
+        assert ((lo - 5e-2 <= u[cur]) & (u[cur] <= hi + 5e-2)).all(), (cur, lo, hi, u[cur], toks[:, cur])

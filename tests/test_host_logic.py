@@ -1,6 +1,6 @@
 """CPU tests of the host-side logic that does not need the CUDA library: flat-buffer layout and
 bucket plan, the data-parallel gradient exchange (world_size 2 over gloo), rope table, the FLOP model
-of bench.py against SURVEY 8d, and MetaModel.generate's control flow driven by a fake inner model."""
+of bench.py against SURVEY 8d, and the host-side set-up of MetaModel.generate."""
 import os
 import sys
 from types import SimpleNamespace
@@ -141,23 +141,38 @@ class _FakeLLM(torch.nn.Module):
         return torch.nn.functional.one_hot(nxt, self.V).float() * 10
 
 
-def test_generate_control_flow_matches_oracle_restatement():
-    """meta.py:379-485 on the host: our MetaModel.generate_tokens and the oracle's restatement walk the
-    same prompts / stops identically when driven by the same (fake) logits."""
+def test_generation_plan_matches_oracle_restatement():
+    """meta.py:419-442 on the host: budget, left truncation, token matrix and stop list of our
+    `plan_generation` equal what the oracle's restatement of `generate` sets up (the loop itself runs on
+    the device kernels and is compared with the oracle in tests/test_generate_gpu.py)."""
     import a3vlm_oracle as O
-    from a3vlm_b200.model.meta import MetaModel
+    from a3vlm_b200.model.meta import plan_generation
 
-    m = MetaModel.__new__(MetaModel)
-    torch.nn.Module.__init__(m)
-    m.llma = _FakeLLM()
-    m.tokenizer = None
-    m._argmax = lambda logits: torch.argmax(logits, dim=-1)  # CPU stand-in for the argmax kernel
-    prompts = [[1, 5, 6], [1, 9, 10, 11, 12]]
-    out, toks, sp = m.generate_tokens(prompts, None, max_gen_len=6, eos_id=2, stop_sequences=[[38, 19]])
-    fake = _FakeLLM()
-    orc = SimpleNamespace(args=O.ModelArgs(max_seq_len=32, max_batch_size=4), image_words=0,
-                          forward_inference=fake.forward_inference)
-    ref, rtoks, rsp = O.generate_tokens(orc, prompts, max_gen_len=6, eos_id=2, stop_sequences=[[38, 19]])
-    assert out == ref and torch.equal(toks, rtoks) and torch.equal(sp, rsp)
-    assert m.llma.calls == fake.calls
-    assert m.llma.calls[0] == ((2, 3), 0) and all(c[0] == (2, 1) for c in m.llma.calls[1:])
+    cases = [dict(prompts=[[1, 5, 6], [1, 9, 10, 11, 12]], max_seq_len=32, image_words=0, max_gen_len=6),
+             dict(prompts=[[1] + list(range(3, 30)), [1, 4]], max_seq_len=24, image_words=7, max_gen_len=5),  # truncation
+             dict(prompts=[[1, 2, 3]], max_seq_len=16, image_words=0, max_gen_len=64)]                      # budget-bound
+    for c in cases:
+        plan = plan_generation(c["prompts"], c["max_seq_len"], c["image_words"], c["max_gen_len"], 2, [[38, 19], [7]])
+        calls = []
+
+        class Fake:
+            args = O.ModelArgs(max_seq_len=c["max_seq_len"], max_batch_size=4)
+            image_words = c["image_words"]
+
+            def forward_inference(self, tokens, start_pos, image=None):
+                calls.append((tuple(tokens.shape), start_pos))
+                return torch.nn.functional.one_hot((tokens[:, -1] * 7 + 3) % 50, 50).float()
+
+        img = torch.zeros(1) if c["image_words"] else None
+        _, rtoks, _ = O.generate_tokens(Fake(), c["prompts"], images=img, max_gen_len=c["max_gen_len"], eos_id=2,
+                                        stop_sequences=[[38, 19], [7]])
+        assert plan["total_len"] == rtoks.shape[1]
+        assert plan["start_pos"] == min(len(t) for t in c["prompts"])
+        for b, t in enumerate(plan["prompts"]):
+            assert rtoks[b, :len(t)].tolist() == t  # the oracle wrote the same (truncated) prompt
+            assert plan["tokens"][b, :len(t)].tolist() == t and plan["tokens"][b, len(t):].sum() == 0
+            assert int(plan["prompt_len"][b]) == len(t)
+        assert plan["stops"] == [[2], [38, 19], [7]]
+        assert plan["stop_flat"].tolist() == [2, 38, 19, 7] and plan["stop_offsets"].tolist() == [0, 1, 3, 4]
+        if calls:
+            assert calls[0] == ((len(c["prompts"]), plan["start_pos"]), 0)
