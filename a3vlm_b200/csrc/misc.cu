@@ -609,6 +609,17 @@ extern "C" int a3_sumsq_bf16(const void* g, long long n, float* out, void* strea
   return check_launch("a3_sumsq_bf16");
 }
 
+// Resident AdamW CTAs per SM.  16 = the stand-alone optimum (6.1 TB/s).  The pipelined optimiser step
+// (Engine.overlap_optimizer) runs AdamW on a side stream underneath the next step's forward: there a
+// small grid (1-2 CTAs of 64 registers x 256 threads per SM) fits NEXT TO a resident 384-thread GEMM CTA
+// instead of taking the SM's register file first.
+static int g_adamw_blocks_per_sm = 16;
+extern "C" int a3_set_adamw_blocks_per_sm(int n) {
+  if (n < 1 || n > 32) return set_error(A3_ERR_ARG, "a3_set_adamw_blocks_per_sm: 1..32");
+  g_adamw_blocks_per_sm = n;
+  return A3_OK;
+}
+
 extern "C" int a3_adamw(float* master, void* weight_bf16, const void* grad_bf16, float* m, float* v,
                         long long n, float lr, float beta1, float beta2, float eps, float weight_decay,
                         int step, const float* norm_sq, float max_norm, void* stream) {
@@ -621,7 +632,7 @@ extern "C" int a3_adamw(float* master, void* weight_bf16, const void* grad_bf16,
   const double bc1 = 1.0 - pow((double)beta1, step);
   const double bc2 = 1.0 - pow((double)beta2, step);
   long long blocks = ((n >> 3) + 255) / 256;
-  const long long cap = (long long)num_sms() * 16;
+  const long long cap = (long long)num_sms() * g_adamw_blocks_per_sm;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   adamw_kernel<<<(int)blocks, 256, 0, ST(stream)>>>(master, BFM(weight_bf16), BF(grad_bf16), m, v, n, lr,

@@ -122,6 +122,14 @@ def bucket_plan(offsets, numel: int, n_layers: int):
     return plan
 
 
+def optimizer_chunks(offsets, decay_numel: int, n_layers: int):
+    """Flat ranges of the decay region in the order the forward consumes them: projector + tags +
+    embedding, one per decoder layer, LM head.  They tile [0, decay_numel) exactly once (the pipelined
+    AdamW updates one chunk per launch and publishes an event after each)."""
+    cuts = [0] + [offsets[f"layers.{i}.wqkv"][0] for i in range(n_layers)] + [offsets["output.weight"][0], decay_numel]
+    return [(lo, hi) for lo, hi in zip(cuts[:-1], cuts[1:]) if hi > lo]
+
+
 class FlatParams:
     """Flat bf16 storage for a set of named parameters.  `layout` is an ordered list of
     (name, shape); views[name] aliases the flat buffer."""
@@ -236,8 +244,16 @@ class Engine:
         self.comm_stream = None
         # sharded optimiser (ZeRO-1 style, enable_sharded_optimizer): this rank's slice of the decay region
         self.shard_group, self.shard_world, self.shard_rank = None, 1, 0
-        self.shard_ready: List = []     # per shard: event recorded after its broadcast (None = already waited)
-        self._waited_upto = None        # flat offset up to which the compute stream has waited
+        # weight ranges still being written on a side stream (shard broadcasts, or the pipelined AdamW), in
+        # forward-consumption order: (lo, hi, event).  wait_weights(upto) makes the compute stream wait for
+        # those that start below `upto`.
+        self._pending: List[Tuple[int, int, "torch.cuda.Event"]] = []
+        # pipelined optimiser step (single replica / unsharded state): sumsq + AdamW run on a side stream,
+        # chunk by chunk in forward-consumption order, underneath the NEXT step's ViT + decoder forward
+        self.overlap_optimizer = False
+        self.overlap_adamw_blocks_per_sm = 1
+        self.opt_stream = None
+        self.norm_ready = None
 
     # ------------------------------------------------------------------------------------ layouts
     def _build_layouts(self):
@@ -249,6 +265,7 @@ class Engine:
         self.g: Optional[FlatParams] = None  # gradients: allocated on first training use
         self._layout = decay + nodecay
         self._buckets = bucket_plan(self.w.offsets, self.w.numel, self.args.n_layers)
+        self._opt_chunks = optimizer_chunks(self.w.offsets, self.decay_numel, self.args.n_layers)
 
     def param_views(self) -> Dict[str, torch.Tensor]:
         """Reference-named views (SURVEY 8b state-dict names) into the flat buffers."""
@@ -564,6 +581,10 @@ class Engine:
         self._ensure_grads()
         self._ensure_opt()
         self.opt_step += 1
+        if self.overlap_optimizer and self.shard_world == 1:
+            return self._optimizer_step_pipelined(lr, weight_decay, max_norm, betas, eps)
+        self.wait_weights()
+        self.norm_ready = None
         self.norm_sq.zero_()
         ops.sumsq_bf16(self.g.flat, self.norm_sq)
         for (lo, hi, decayed), ms, m, v in zip(self._opt_ranges(), self.master, self.m, self.v):
@@ -574,11 +595,62 @@ class Engine:
             self._broadcast_shards()
         return self.norm_sq
 
+    def _optimizer_step_pipelined(self, lr, weight_decay, max_norm, betas, eps) -> torch.Tensor:
+        """Same arithmetic as the plain step, issued on a side stream behind an event that marks the end
+        of the backward: norm, then the small no-decay tail (norm weights / biases -- layer 0 needs its norm
+        weight first), then the decay region chunk by chunk in forward-consumption order with an event
+        after each.  The caller's next forward waits per chunk (wait_weights), so the frozen ViT tower and
+        the early layers run while later chunks are still being updated: AdamW is HBM-bound (28 B/param)
+        and the forward tensor-bound, and a one-CTA-per-SM AdamW grid fits beside the resident GEMM CTA.
+        Hazards: the forward's last wait_weights() (before the LM head) leaves the update fully consumed
+        before any backward can overwrite the gradients or read the weights for dgrad."""
+        self.wait_weights()  # an earlier update nobody consumed
+        if self.opt_stream is None:
+            self.opt_stream = torch.cuda.Stream(device=self.device)
+        done = torch.cuda.Event()
+        done.record()
+        st = self.opt_stream
+        st.wait_event(done)
+        (dlo, dhi, _), (nlo, nhi, _) = self._opt_ranges()
+        b1, b2 = betas
+        pend = []
+        ops.set_adamw_blocks_per_sm(self.overlap_adamw_blocks_per_sm)
+        try:
+            with torch.cuda.stream(st):
+                self.norm_sq.zero_()
+                ops.sumsq_bf16(self.g.flat, self.norm_sq)
+                self.norm_ready = torch.cuda.Event()
+                self.norm_ready.record(st)
+                if nhi > nlo:
+                    ops.adamw(self.master[1], self.w.flat[nlo:nhi], self.g.flat[nlo:nhi], self.m[1], self.v[1], lr, b1, b2,
+                              eps, 0.0, self.opt_step, self.norm_sq, max_norm)
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                    pend.append((-1, 0, ev))
+                for lo, hi in self._opt_chunks:
+                    a, b = lo - dlo, hi - dlo
+                    ops.adamw(self.master[0][a:b], self.w.flat[lo:hi], self.g.flat[lo:hi], self.m[0][a:b], self.v[0][a:b],
+                              lr, b1, b2, eps, weight_decay, self.opt_step, self.norm_sq, max_norm)
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                    pend.append((lo, hi, ev))
+        finally:
+            ops.set_adamw_blocks_per_sm(16)
+        self._pending = pend
+        return self.norm_sq
+
+    def grad_norm_sq(self) -> torch.Tensor:
+        """Squared global gradient norm of the last optimiser step, safe to read on the current stream."""
+        if self.norm_ready is not None:
+            torch.cuda.current_stream().wait_event(self.norm_ready)
+        return self.norm_sq
+
     def optimizer_state_dict(self) -> Dict:
         """This rank's AdamW state (fp32 master / m / v of the flat ranges it owns, step count) on the host
         -- the `consolidated.*.optimizer.pth` payload of checkpoint.save_checkpoint (M/util/misc.py:390-406).
         With the sharded optimiser every rank owns a different slice of the decay region."""
         self._ensure_opt()
+        self.wait_weights()
         cpu = lambda ts: [t.detach().to("cpu") for t in ts]
         return {"step": self.opt_step, "ranges": [(lo, hi, d) for lo, hi, d in self._opt_ranges()],
                 "shard_world": self.shard_world, "shard_rank": self.shard_rank,
@@ -604,34 +676,25 @@ class Engine:
         done.record()
         cs = self.comm_stream
         cs.wait_event(done)
-        self.shard_ready = []
+        self._pending = []
         with torch.cuda.stream(cs):
             for r in range(self.shard_world):
                 dist.broadcast(self.w.flat[r * S:(r + 1) * S], src=dist.get_global_rank(self.shard_group, r),
                                group=self.shard_group)
                 ev = torch.cuda.Event()
                 ev.record(cs)
-                self.shard_ready.append(ev)
-        self._waited_upto = 0
+                self._pending.append((r * S, (r + 1) * S, ev))
 
     def wait_weights(self, upto: Optional[int] = None) -> None:
-        """Make the compute stream wait until the broadcast weights covering flat offsets [0, upto) have
-        arrived (all of them when upto is None).  No-op without a pending exchange."""
-        if not self.shard_ready or self._waited_upto is None:
-            return
-        S = self.decay_numel // self.shard_world
-        upto = self.decay_numel if upto is None else min(upto, self.decay_numel)
-        if upto <= self._waited_upto:
+        """Make the current stream wait until the weights at flat offsets [0, upto) written on a side
+        stream (shard broadcasts / pipelined AdamW chunks) have landed -- all of them when upto is None.
+        No-op without a pending update."""
+        if not self._pending:
             return
         cur = torch.cuda.current_stream()
-        first, last = self._waited_upto // S, (upto - 1) // S
-        for r in range(first, last + 1):
-            if self.shard_ready[r] is not None:
-                cur.wait_event(self.shard_ready[r])
-                self.shard_ready[r] = None
-        self._waited_upto = (last + 1) * S
-        if self._waited_upto >= self.decay_numel:
-            self.shard_ready, self._waited_upto = [], None
+        while self._pending and (upto is None or self._pending[0][0] < upto):
+            _, _, ev = self._pending.pop(0)
+            cur.wait_event(ev)
 
     # ------------------------------------------------------------------------------------ data-parallel
     def allreduce_hook(self, group=None):

@@ -190,6 +190,7 @@ class Transformer(nn.Module):
         """Random init of the same families the reference uses: kaiming_uniform_(a=sqrt(5)) for the
         decoder linears / embedding (llama_ens5.py:28), ones for norms, U(0,1) tags (:338-339),
         width^-0.5 N(0,1) for the ViT class / positional embeddings (open_clip)."""
+        self.engine.wait_weights()
         g = torch.Generator(device=self.engine.device)
         if seed is not None:
             g.manual_seed(seed)
@@ -216,6 +217,7 @@ class Transformer(nn.Module):
                 ".float()/.to(other device) on the module (fp32 masters live in a3vlm_b200.train.AdamW)")
 
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        self.engine.wait_weights()  # never copy underneath a weight update still running on a side stream
         out = super().load_state_dict(state_dict, strict=strict, assign=False)
         self._check_alias()
         self.engine.weights_changed()

@@ -367,6 +367,10 @@ def sumsq_bf16(g, out):
     _lib.check(_L().a3_sumsq_bf16(_p(g), g.numel(), _p(out), _st()), "a3_sumsq_bf16")
 
 
+def set_adamw_blocks_per_sm(n: int) -> None:
+    _lib.check(_L().a3_set_adamw_blocks_per_sm(int(n)), "a3_set_adamw_blocks_per_sm")
+
+
 def adamw(master, weight_bf16, grad_bf16, m, v, lr, beta1, beta2, eps, weight_decay, step,
           norm_sq=None, max_norm=0.0):
     rc = _L().a3_adamw(_p(master), _p(weight_bf16), _p(grad_bf16), _p(m), _p(v), master.numel(),

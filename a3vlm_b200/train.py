@@ -29,7 +29,7 @@ class AdamW(torch.optim.Optimizer):
 
     def grad_norm(self) -> torch.Tensor:
         """Pre-clip global gradient norm of the last step (device tensor; reading it syncs)."""
-        return self.last_norm_sq.sqrt()
+        return self.engine.grad_norm_sq().sqrt()
 
 
 class NativeScalerWithGradNormCount:

@@ -183,7 +183,8 @@ def workload_config(args, cfg, fl, n):
                         f"T={args.text_len} text tokens, W={fl['N'] + 2} image words, L={fl['L']}",
             "step": "ViT fwd (frozen) + visual_proj/LLM fwd+bwd + fused CE + grad all-reduce (N>1) + global-norm clip + AdamW",
             "global_batch": args.batch * n, "text_len": args.text_len, "seq_len": fl["L"], "image_size": args.image_size,
-            "parallelism": f"dp{n}", "l2_policy": "working set (13.5 GB weights + activations) >> 126 MB L2, no flush needed",
+            "parallelism": f"dp{n}", "optimizer": "pipelined under the next forward" if getattr(args, "overlap_opt", 0) and n == 1 else "in line",
+            "l2_policy": "working set (13.5 GB weights + activations) >> 126 MB L2, no flush needed",
             "tflop_per_image": fl["total"] / 1e12}
 
 
@@ -199,6 +200,8 @@ def main():
     ap.add_argument("--text-len", type=int, default=256)
     ap.add_argument("--image-size", type=int, default=336)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--overlap-opt", type=int, default=int(os.environ.get("A3_OVERLAP_OPT", "0")),
+                    help="1: pipelined optimiser step (sumsq + AdamW on a side stream underneath the next step's forward)")
     ap.add_argument("--ncu", action="store_true",
                     help="profiling aid: warm up, run ONE device step between cudaProfilerStart/Stop, exit "
                          "(use with `ncu --profile-from-start off`; prints no bench line)")
@@ -237,6 +240,7 @@ def main():
     model = MetaModel("llama_b200", {**cfg, "image_size": S}, None, with_visual=True, max_seq_len=2048)
     model.llma.reset_parameters(seed=2 + 0)  # identical replicas on every rank
     eng = model.llma.engine
+    eng.overlap_optimizer = bool(args.overlap_opt)  # no effect with the sharded optimiser (N > 1)
     if world > 1:
         model.llma.enable_data_parallel()
     opt = AdamW(model, lr=2e-5, betas=(0.9, 0.95), weight_decay=0.0)  # M/scripts/a3vlm_train.sh: lr 2e-5, wd 0

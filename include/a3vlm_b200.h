@@ -265,6 +265,9 @@ int a3_generate_step(long long* tokens, long long ld_tokens, const int* prompt_l
  * clip: coef = min(1, max_norm / (sqrt(norm_sq) + 1e-6)); max_norm <= 0 disables clipping.
  * ------------------------------------------------------------------------------------------- */
 int a3_sumsq_bf16(const void* g, long long n, float* out, void* stream);
+/* Grid of a3_adamw in CTAs per SM (default 16; 1-2 when the update runs on a side stream underneath
+ * the next step's forward, so that its CTAs co-reside with the persistent GEMM CTAs). */
+int a3_set_adamw_blocks_per_sm(int n);
 int a3_adamw(float* master, void* weight_bf16, const void* grad_bf16, float* m, float* v,
              long long n, float lr, float beta1, float beta2, float eps, float weight_decay,
              int step, const float* norm_sq, float max_norm, void* stream);

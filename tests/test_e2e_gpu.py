@@ -157,6 +157,47 @@ def test_loss_grads_and_adamw_step_match_golden(tiny, gold):
         assert (got - ref).abs().max().item() <= 2.5e-3, k  # never more than 2*lr (+ rounding) away
 
 
+def test_pipelined_optimizer_step_equals_plain(tiny, gold):
+    """Engine.overlap_optimizer (sumsq + AdamW chunked on a side stream underneath the next forward) is the
+    same arithmetic in a different schedule: four fine-tune steps give the same losses, gradient norms and
+    weights bit for bit, also when inference / state_dict / a reload follow an update directly."""
+    from a3vlm_b200.train import AdamW, NativeScalerWithGradNormCount
+
+    m, sd = tiny
+    eng = m.llma.engine
+    tok, lab, img = gold["tokens"].cuda(), gold["labels"].cuda(), gold["image"].cuda()
+
+    def run(overlap, bps):
+        eng.overlap_optimizer, eng.overlap_adamw_blocks_per_sm = overlap, bps
+        m.llma.load_state_dict(sd)
+        eng.opt_step = 0
+        eng.m = eng.v = None
+        opt = AdamW(m, lr=1e-3, betas=(0.9, 0.95), weight_decay=0.1)
+        scaler = NativeScalerWithGradNormCount()
+        losses, norms = [], []
+        for _ in range(4):
+            m.zero_grad(set_to_none=True)
+            loss, _ = m(tok, lab, images=img)
+            norms.append(scaler(loss, opt, m, clip_grad=0.5, update_grad=True))
+            losses.append(loss.detach().clone())
+        logits = m.llma.forward_inference(tok[:, :6], 0, img).clone()  # right behind an update
+        state = {k: v.clone() for k, v in m.llma.state_dict().items()}
+        return torch.stack(losses).cpu(), torch.stack(norms).cpu(), logits.cpu(), state
+
+    try:
+        ref = run(False, 1)
+        assert ref[0][3] < ref[0][0]  # it trains
+        for bps in (1, 2):
+            got = run(True, bps)
+            assert torch.equal(got[0], ref[0]), (got[0], ref[0])
+            assert torch.equal(got[1], ref[1]), (got[1], ref[1])
+            assert torch.equal(got[2], ref[2])
+            assert all(torch.equal(got[3][k], ref[3][k]) for k in ref[3])
+            assert not eng._pending
+    finally:
+        eng.overlap_optimizer = False
+
+
 def test_autograd_logits_path_and_accumulation(tiny, gold):
     """Transformer.forward returns differentiable logits (reference engine path: CE outside the model);
     two accumulated micro-steps double the gradients (M/util/misc.py:311-313 no_sync semantics)."""
