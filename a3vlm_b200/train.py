@@ -15,9 +15,19 @@ class AdamW(torch.optim.Optimizer):
     of M/util/misc.py:586-599 is built into the flat layout; `weight_decay` applies to the decay
     region only.  `step(max_norm=...)` fuses the global-L2 clip of M/util/clip_grad.py."""
 
-    def __init__(self, model, lr: float = 1e-3, betas=(0.9, 0.95), eps: float = 1e-8, weight_decay: float = 0.0):
+    def __init__(self, model, lr: float = 1e-3, betas=(0.9, 0.95), eps: float = 1e-8, weight_decay: float = 0.0,
+                 pipelined: Optional[bool] = None):
+        """pipelined=True: the update (norm, clip, AdamW) runs on a side stream, chunk by chunk in the order
+        the forward consumes the weights, underneath the NEXT step's forward (Engine.overlap_optimizer;
+        single replica -- with data parallelism the sharded optimiser pipelines its broadcasts instead).
+        Same arithmetic, bit for bit.  The model's own entry points (forward, forward_inference,
+        state_dict, parameters / named_parameters, load_state_dict, checkpoint save / load) wait for the
+        chunks they touch; code that reads a parameter tensor it kept a handle to must call
+        `model.llma.engine.wait_weights()` first.  None leaves the engine's setting unchanged."""
         llma = getattr(model, "llma", model)
         self.engine = llma.engine
+        if pipelined is not None:
+            self.engine.overlap_optimizer = bool(pipelined)
         params = [p for p in llma.parameters() if p.requires_grad]
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
 

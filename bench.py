@@ -200,7 +200,7 @@ def main():
     ap.add_argument("--text-len", type=int, default=256)
     ap.add_argument("--image-size", type=int, default=336)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--overlap-opt", type=int, default=int(os.environ.get("A3_OVERLAP_OPT", "0")),
+    ap.add_argument("--overlap-opt", type=int, default=int(os.environ.get("A3_OVERLAP_OPT", "1")),
                     help="1: pipelined optimiser step (sumsq + AdamW on a side stream underneath the next step's forward)")
     ap.add_argument("--ncu", action="store_true",
                     help="profiling aid: warm up, run ONE device step between cudaProfilerStart/Stop, exit "
@@ -243,7 +243,8 @@ def main():
     eng.overlap_optimizer = bool(args.overlap_opt)  # no effect with the sharded optimiser (N > 1)
     if world > 1:
         model.llma.enable_data_parallel()
-    opt = AdamW(model, lr=2e-5, betas=(0.9, 0.95), weight_decay=0.0)  # M/scripts/a3vlm_train.sh: lr 2e-5, wd 0
+    opt = AdamW(model, lr=2e-5, betas=(0.9, 0.95), weight_decay=0.0,  # M/scripts/a3vlm_train.sh: lr 2e-5, wd 0
+                pipelined=bool(args.overlap_opt))
     scaler = NativeScalerWithGradNormCount()
     clip = 8.0  # --clip_grad 8
 

@@ -7,6 +7,7 @@ sys.path.insert(0, ".")
 import bench
 from a3vlm_b200.model import MetaModel
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 5
+BPS = [int(b) for b in sys.argv[2].split(",")] if len(sys.argv) > 2 else [1, 2, 4]
 cfg = bench.MODELS["7b"]
 dev = torch.device("cuda", 0)
 B, T, S = 8, 256, 336
@@ -25,8 +26,7 @@ def step():
     return ws.loss
 
 res = {}
-for name, overlap, bps in [("plain", False, 1), ("overlap_bps1", True, 1), ("overlap_bps2", True, 2), ("overlap_bps4", True, 4),
-                           ("plain_again", False, 1)]:
+for name, overlap, bps in [("plain", False, 1)] + [(f"overlap_bps{b}", True, b) for b in BPS] + [("plain_again", False, 1)]:
     model.llma.reset_parameters(seed=2)
     eng.master = eng.m = eng.v = None
     eng.opt_step = 0

@@ -106,7 +106,7 @@ def _sample_case(B, V, temperature, top_p, seed, kind):
     return logits, u
 
 
-@pytest.mark.parametrize("V", [32000, 1000, 50])
+@pytest.mark.parametrize("V", [32000, 40000, 1000, 50])  # 40000: the row no longer fits the register file
 @pytest.mark.parametrize("kind", ["flat", "normal", "peaked", "ties"])
 def test_sample_top_p_matches_oracle(V, kind):
     import a3vlm_oracle as O
@@ -124,6 +124,12 @@ def test_sample_top_p_matches_oracle(V, kind):
         lo, hi = O.top_p_token_interval(probs, top_p, got)
         tol = 2e-6
         ok = (got == ref) | ((lo - tol <= u) & (u <= hi + tol))
+        # two tokens whose probabilities agree to fp32 exp() rounding (1e-6 relative) may be ordered either
+        # way by the two softmax implementations: then the kernel's token sits in the slot next to u's
+        p_got, p_ref = probs.gather(-1, got.reshape(-1, 1)).reshape(-1), probs.gather(-1, ref.reshape(-1, 1)).reshape(-1)
+        w = hi - lo  # the slot width (normalised mass of the kernel's token)
+        twin = ((p_got - p_ref).abs() <= 1e-6 * p_ref) & (lo - w - tol <= u) & (u <= hi + w + tol)
+        ok = ok | twin
         assert ok.all(), (temperature, top_p, got[~ok], ref[~ok], u[~ok], lo[~ok], hi[~ok])
         # inside the nucleus: the chosen token's pre-mask probability rank keeps exclusive cumsum <= top_p
         ps, pi = torch.sort(probs, dim=-1, descending=True, stable=True)
@@ -221,10 +227,29 @@ def test_rgbd_prefill_and_greedy_match_oracle(views):
     assert m.llma.cache_image_words == 0
     # greedy decode with both streams, unequal prompts
     prompts = [[1, 17, 33, 49], [1, 100, 101, 102, 103, 104]]
+    seen, inner = [], orc.forward_inference
+
+    def recording(*args, **kw):
+        seen.append(inner(*args, **kw))
+        return seen[-1]
+
+    orc.forward_inference = recording
     ref_gen, ref_toks, _ = O.generate_tokens(orc, prompts, images=img, depth_images=dep, max_gen_len=8, eos_id=2)
     out, toks, _ = m.generate_tokens(prompts, img, max_gen_len=8, eos_id=2, depth_images=dep)
-    assert out == ref_gen, (out, ref_gen)
-    assert torch.equal(toks.cpu(), ref_toks)
+    # Greedy ids are exact, except that a row may part ways with the oracle at a step where the ORACLE's own
+    # top-2 logits are within one bf16 rounding step of each other (the two bf16 paths may legitimately order
+    # a tie differently -- same rule as tests/test_e2e_gpu.py::test_live_oracle_midsize); everything before
+    # that step must match.
+    min_prompt = min(len(q) for q in prompts)
+    for r, (g_, e_) in enumerate(zip(out, ref_gen)):
+        if g_ == e_:
+            assert torch.equal(toks[r].cpu(), ref_toks[r])
+            continue
+        k = next(i for i, (x, y) in enumerate(zip(g_, e_)) if x != y)
+        top2 = seen[len(prompts[r]) + k - min_prompt][r].topk(2).values
+        margin, mag = (top2[0] - top2[1]).item(), top2[0].abs().item()
+        print(f"row {r} diverges at generated token {k}: oracle top-2 margin {margin:.4f} at logit {mag:.2f}")
+        assert margin <= 4 * 2.0 ** -8 * max(mag, 1.0), (r, k, margin, mag, g_, e_)
 
 
 def test_rgbd_training_forward_sees_rgb_only():
