@@ -105,20 +105,22 @@ def flat_offsets(layout, align: int = 64, segment_after: Optional[str] = None):
     return offsets, off
 
 
-def bucket_plan(offsets, numel: int, n_layers: int):
-    """Flat element ranges in the order the backward completes them (the all-reduce buckets):
+def bucket_plan(offsets, numel: int, n_layers: int, decay_numel: Optional[int] = None):
+    """Flat element ranges in the order the backward completes them (the gradient-exchange buckets):
     LM head, decoder layers last to first, then projector + tags + embedding (the head of the buffer),
     then everything after the LM head (all norm weights, projector biases).  Together they tile
-    [0, numel) exactly once."""
+    [0, numel) exactly once.  With `decay_numel` the LM-head bucket runs to the end of the decay region
+    (alignment padding included), so the decay buckets are exactly optimizer_chunks() in reverse."""
     rng = lambda n: (offsets[n][0], offsets[n][0] + offsets[n][1])
-    plan = [rng("output.weight")]
+    head_hi = rng("output.weight")[1] if decay_numel is None else decay_numel
+    plan = [(rng("output.weight")[0], head_hi)]
     prev_lo = rng("output.weight")[0]
     for i in reversed(range(n_layers)):
         lo = rng(f"layers.{i}.wqkv")[0]
         plan.append((lo, prev_lo))  # up to the next bucket's start: alignment padding is covered once
         prev_lo = lo
     plan.append((0, prev_lo))
-    plan.append((rng("output.weight")[1], numel))
+    plan.append((head_hi, numel))
     return plan
 
 
@@ -128,6 +130,17 @@ def optimizer_chunks(offsets, decay_numel: int, n_layers: int):
     AdamW updates one chunk per launch and publishes an event after each)."""
     cuts = [0] + [offsets[f"layers.{i}.wqkv"][0] for i in range(n_layers)] + [offsets["output.weight"][0], decay_numel]
     return [(lo, hi) for lo, hi in zip(cuts[:-1], cuts[1:]) if hi > lo]
+
+
+def owned_ranges(chunks, decay_numel: int, numel: int, world: int = 1, rank: int = 0):
+    """[(lo, hi, decayed)]: rank's 1/world slice of every decay chunk, in order, then the no-decay tail
+    (replicated).  For world = 1 the chunks themselves."""
+    out = []
+    for lo, hi in chunks:
+        n = (hi - lo) // world
+        out.append((lo + rank * n, lo + (rank + 1) * n, True))
+    out.append((decay_numel, numel, False))
+    return out
 
 
 class FlatParams:
@@ -264,7 +277,7 @@ class Engine:
         self.fz = FlatParams(frozen, self.device) if frozen else None
         self.g: Optional[FlatParams] = None  # gradients: allocated on first training use
         self._layout = decay + nodecay
-        self._buckets = bucket_plan(self.w.offsets, self.w.numel, self.args.n_layers)
+        self._buckets = bucket_plan(self.w.offsets, self.w.numel, self.args.n_layers, self.decay_numel)
         self._opt_chunks = optimizer_chunks(self.w.offsets, self.decay_numel, self.args.n_layers)
 
     def param_views(self) -> Dict[str, torch.Tensor]:
@@ -543,28 +556,33 @@ class Engine:
 
     # ------------------------------------------------------------------------------------ optimiser
     def enable_sharded_optimizer(self, group=None) -> None:
-        """ZeRO-1 style: fp32 master / m / v of the decay region are split evenly over the data-parallel
-        ranks (the reference shards too: FSDP SHARD_GRAD_OP, M/main_finetune.py:256-260); every rank
-        updates its slice and broadcasts the new bf16 weights, shard by shard in forward-consumption
-        order on the side stream, so the exchange hides behind the next step's ViT + first layers.
-        The tiny no-decay region (norm weights, biases) is updated redundantly on every rank."""
+        """ZeRO-2 style sharding over the data-parallel ranks (the reference shards too: FSDP
+        SHARD_GRAD_OP, M/main_finetune.py:256-260).  Ownership is sliced PER CHUNK: the decay region is cut
+        into chunks in forward-consumption order (projector + embedding, one per decoder layer, LM head) and
+        rank r owns the r-th 1/N of every chunk.  Then
+          * the backward's gradient exchange is one in-place REDUCE-SCATTER per chunk (each rank receives
+            only the summed gradients of its slice: half the bytes of an all-reduce),
+          * fp32 master / m / v exist for the owned slices only (13B: 26 + 26 + 156/8 GB per GPU),
+          * the step updates the owned slice of a chunk and ALL-GATHERs the chunk's bf16 weights in place,
+            chunk by chunk on the side stream, so the next forward (which waits per chunk) starts while
+            later chunks are still being updated and exchanged.
+        The tiny no-decay tail (norm weights, biases) is all-reduced and updated redundantly on every rank."""
         import torch.distributed as dist
 
         self.shard_group = group if group is not None else dist.group.WORLD
         self.shard_world = dist.get_world_size(self.shard_group)
         self.shard_rank = dist.get_rank(self.shard_group)
-        if self.decay_numel % (self.shard_world * 64):
-            raise ValueError("data-parallel world size must divide 8 for the sharded optimiser")
+        for lo, hi in self._opt_chunks:
+            if (hi - lo) % (self.shard_world * 8):
+                raise ValueError(f"chunk [{lo}, {hi}) does not split into {self.shard_world} 16-byte aligned slices")
         self.master = self.m = self.v = None
         if self.comm_stream is None:
             self.comm_stream = torch.cuda.Stream(device=self.device)
 
     def _opt_ranges(self):
-        """[(lo, hi, decayed)] flat ranges this rank's optimiser owns."""
-        n, nd = self.w.flat.numel(), self.decay_numel
-        S = nd // self.shard_world
-        lo = self.shard_rank * S
-        return [(lo, lo + S, True), (nd, n, False)]
+        """[(lo, hi, decayed)] flat ranges whose optimiser state this rank holds: its slice of every decay
+        chunk in forward order (the whole chunk for a single replica), then the no-decay tail."""
+        return owned_ranges(self._opt_chunks, self.decay_numel, self.w.flat.numel(), self.shard_world, self.shard_rank)
 
     def _ensure_opt(self):
         if self.master is None:
@@ -578,65 +596,74 @@ class Engine:
                        betas=(0.9, 0.95), eps: float = 1e-8) -> torch.Tensor:
         """Global-L2 clip (M/util/clip_grad.py:187-193) + AdamW on fp32 masters with the bf16 weights
         rewritten in the same pass (M/main_finetune.py:284-285; M/util/misc.py:586-599 decay groups).
-        Returns the device tensor holding the squared gradient norm (no host sync)."""
+        Returns the device tensor holding the squared gradient norm (no host sync; read it through
+        grad_norm_sq()).
+
+        Schedule.  In line on the current stream for a single replica unless `overlap_optimizer`; otherwise
+        (and always with the sharded optimiser) on a side stream behind an event that marks the end of the
+        backward: norm, the small no-decay tail first (layer 0 needs its norm weight at once), then the decay
+        chunks in forward-consumption order -- AdamW on the owned range, all-gather of the chunk when sharded,
+        an event after each.  The caller's next forward waits per chunk (wait_weights), so the frozen ViT
+        tower and the early layers run while later chunks are still being updated: AdamW is HBM-bound
+        (28 B/param), the forward tensor-bound, and a small AdamW grid fits beside the resident GEMM CTA.
+        Hazards: the forward's last wait_weights() (before the LM head) leaves the update fully consumed
+        before any backward can overwrite the gradients or read the weights for dgrad."""
         self._ensure_grads()
         self._ensure_opt()
         self.opt_step += 1
-        if self.overlap_optimizer and self.shard_world == 1:
-            return self._optimizer_step_pipelined(lr, weight_decay, max_norm, betas, eps)
-        self.wait_weights()
-        self.norm_ready = None
-        self.norm_sq.zero_()
-        ops.sumsq_bf16(self.g.flat, self.norm_sq)
-        for (lo, hi, decayed), ms, m, v in zip(self._opt_ranges(), self.master, self.m, self.v):
-            if hi > lo:
-                ops.adamw(ms, self.w.flat[lo:hi], self.g.flat[lo:hi], m, v, lr, betas[0], betas[1], eps,
-                          weight_decay if decayed else 0.0, self.opt_step, self.norm_sq, max_norm)
-        if self.shard_world > 1:
-            self._broadcast_shards()
-        return self.norm_sq
-
-    def _optimizer_step_pipelined(self, lr, weight_decay, max_norm, betas, eps) -> torch.Tensor:
-        """Same arithmetic as the plain step, issued on a side stream behind an event that marks the end
-        of the backward: norm, then the small no-decay tail (norm weights / biases -- layer 0 needs its norm
-        weight first), then the decay region chunk by chunk in forward-consumption order with an event
-        after each.  The caller's next forward waits per chunk (wait_weights), so the frozen ViT tower and
-        the early layers run while later chunks are still being updated: AdamW is HBM-bound (28 B/param)
-        and the forward tensor-bound, and a one-CTA-per-SM AdamW grid fits beside the resident GEMM CTA.
-        Hazards: the forward's last wait_weights() (before the LM head) leaves the update fully consumed
-        before any backward can overwrite the gradients or read the weights for dgrad."""
         self.wait_weights()  # an earlier update nobody consumed
-        if self.opt_stream is None:
-            self.opt_stream = torch.cuda.Stream(device=self.device)
-        done = torch.cuda.Event()
-        done.record()
-        st = self.opt_stream
-        st.wait_event(done)
-        (dlo, dhi, _), (nlo, nhi, _) = self._opt_ranges()
+        sharded = self.shard_world > 1
+        side = sharded or self.overlap_optimizer
+        ranges = self._opt_ranges()
         b1, b2 = betas
+        if side:
+            st = self.comm_stream if sharded else self.opt_stream
+            if st is None:
+                st = self.opt_stream = torch.cuda.Stream(device=self.device)
+            done = torch.cuda.Event()
+            done.record()
+            st.wait_event(done)
+        else:
+            st = torch.cuda.current_stream()
         pend = []
-        ops.set_adamw_blocks_per_sm(self.overlap_adamw_blocks_per_sm)
+        if side:
+            ops.set_adamw_blocks_per_sm(self.overlap_adamw_blocks_per_sm)
         try:
             with torch.cuda.stream(st):
                 self.norm_sq.zero_()
-                ops.sumsq_bf16(self.g.flat, self.norm_sq)
-                self.norm_ready = torch.cuda.Event()
-                self.norm_ready.record(st)
-                if nhi > nlo:
-                    ops.adamw(self.master[1], self.w.flat[nlo:nhi], self.g.flat[nlo:nhi], self.m[1], self.v[1], lr, b1, b2,
-                              eps, 0.0, self.opt_step, self.norm_sq, max_norm)
-                    ev = torch.cuda.Event()
-                    ev.record(st)
-                    pend.append((-1, 0, ev))
-                for lo, hi in self._opt_chunks:
-                    a, b = lo - dlo, hi - dlo
-                    ops.adamw(self.master[0][a:b], self.w.flat[lo:hi], self.g.flat[lo:hi], self.m[0][a:b], self.v[0][a:b],
-                              lr, b1, b2, eps, weight_decay, self.opt_step, self.norm_sq, max_norm)
-                    ev = torch.cuda.Event()
-                    ev.record(st)
-                    pend.append((lo, hi, ev))
+                if sharded:
+                    import torch.distributed as dist
+
+                    for lo, hi, decayed in ranges:  # owned slices hold fully reduced gradients
+                        if decayed and hi > lo:
+                            ops.sumsq_bf16(self.g.flat[lo:hi], self.norm_sq)
+                    dist.all_reduce(self.norm_sq, op=dist.ReduceOp.SUM, group=self.shard_group)
+                    tlo, thi, _ = ranges[-1]  # the tail was all-reduced: identical on every rank, counted once
+                    if thi > tlo:
+                        ops.sumsq_bf16(self.g.flat[tlo:thi], self.norm_sq)
+                else:
+                    ops.sumsq_bf16(self.g.flat, self.norm_sq)
+                if side:
+                    self.norm_ready = torch.cuda.Event()
+                    self.norm_ready.record(st)
+                else:
+                    self.norm_ready = None
+                order = [len(ranges) - 1] + list(range(len(ranges) - 1))  # tail first, then forward order
+                for k in order:
+                    lo, hi, decayed = ranges[k]
+                    if hi > lo:
+                        ops.adamw(self.master[k], self.w.flat[lo:hi], self.g.flat[lo:hi], self.m[k], self.v[k], lr, b1, b2,
+                                  eps, weight_decay if decayed else 0.0, self.opt_step, self.norm_sq, max_norm)
+                    clo, chi = (self._opt_chunks[k] if decayed else (-1, 0))
+                    if sharded and decayed:
+                        dist.all_gather_into_tensor(self.w.flat[clo:chi], self.w.flat[lo:hi], group=self.shard_group)
+                    if side:
+                        ev = torch.cuda.Event()
+                        ev.record(st)
+                        pend.append((clo, chi, ev))
         finally:
-            ops.set_adamw_blocks_per_sm(16)
+            if side:
+                ops.set_adamw_blocks_per_sm(16)
         self._pending = pend
         return self.norm_sq
 
@@ -649,7 +676,7 @@ class Engine:
     def optimizer_state_dict(self) -> Dict:
         """This rank's AdamW state (fp32 master / m / v of the flat ranges it owns, step count) on the host
         -- the `consolidated.*.optimizer.pth` payload of checkpoint.save_checkpoint (M/util/misc.py:390-406).
-        With the sharded optimiser every rank owns a different slice of the decay region."""
+        With the sharded optimiser every rank owns a different slice of every chunk."""
         self._ensure_opt()
         self.wait_weights()
         cpu = lambda ts: [t.detach().to("cpu") for t in ts]
@@ -662,33 +689,16 @@ class Engine:
         one the state was saved with."""
         ranges = [(lo, hi, d) for lo, hi, d in self._opt_ranges()]
         if [tuple(r) for r in sd["ranges"]] != ranges:
-            raise ValueError(f"optimizer state was saved for flat ranges {sd['ranges']}, this engine owns {ranges} "
+            raise ValueError("optimizer state was saved for different flat ranges than this engine owns "
                              "(different model geometry or data-parallel sharding)")
         to = lambda ts: [t.to(device=self.device, dtype=torch.float32).contiguous() for t in ts]
         self.wait_weights()
         self.master, self.m, self.v = to(sd["master"]), to(sd["m"]), to(sd["v"])
         self.opt_step = int(sd["step"])
 
-    def _broadcast_shards(self) -> None:
-        import torch.distributed as dist
-
-        S = self.decay_numel // self.shard_world
-        done = torch.cuda.Event()
-        done.record()
-        cs = self.comm_stream
-        cs.wait_event(done)
-        self._pending = []
-        with torch.cuda.stream(cs):
-            for r in range(self.shard_world):
-                dist.broadcast(self.w.flat[r * S:(r + 1) * S], src=dist.get_global_rank(self.shard_group, r),
-                               group=self.shard_group)
-                ev = torch.cuda.Event()
-                ev.record(cs)
-                self._pending.append((r * S, (r + 1) * S, ev))
-
     def wait_weights(self, upto: Optional[int] = None) -> None:
         """Make the current stream wait until the weights at flat offsets [0, upto) written on a side
-        stream (shard broadcasts / pipelined AdamW chunks) have landed -- all of them when upto is None.
+        stream (pipelined AdamW chunks / all-gathered chunks) have landed -- all of them when upto is None.
         No-op without a pending update."""
         if not self._pending:
             return
@@ -699,13 +709,18 @@ class Engine:
 
     # ------------------------------------------------------------------------------------ data-parallel
     def allreduce_hook(self, group=None):
-        """(on_bucket, finish) for the backward: see dp.BucketAllReduce."""
-        from .dp import BucketAllReduce
+        """(on_bucket, finish) for the backward.  Replicated optimiser: bucketed all-reduce
+        (dp.BucketAllReduce).  Sharded optimiser: reduce-scatter of every decay chunk to its owners and an
+        all-reduce of the small tail (dp.BucketReduceScatter)."""
+        from .dp import BucketAllReduce, BucketReduceScatter
 
         self._ensure_grads()
         if self.comm_stream is None:
             self.comm_stream = torch.cuda.Stream(device=self.device)
-        r = BucketAllReduce(self.g.flat, group, self.comm_stream)
+        if self.shard_world > 1:
+            r = BucketReduceScatter(self.g.flat, self.decay_numel, self.shard_world, self.shard_rank, group, self.comm_stream)
+        else:
+            r = BucketAllReduce(self.g.flat, group, self.comm_stream)
         return r.on_bucket, r.finish
 
     # ------------------------------------------------------------------------------------ inference

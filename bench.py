@@ -183,7 +183,8 @@ def workload_config(args, cfg, fl, n):
                         f"T={args.text_len} text tokens, W={fl['N'] + 2} image words, L={fl['L']}",
             "step": "ViT fwd (frozen) + visual_proj/LLM fwd+bwd + fused CE + grad all-reduce (N>1) + global-norm clip + AdamW",
             "global_batch": args.batch * n, "text_len": args.text_len, "seq_len": fl["L"], "image_size": args.image_size,
-            "parallelism": f"dp{n}", "optimizer": "pipelined under the next forward" if getattr(args, "overlap_opt", 0) and n == 1 else "in line",
+            "parallelism": f"dp{n}", "optimizer": ("sharded over the ranks (reduce-scatter grads, all-gather weights), pipelined under the next forward" if n > 1
+                          else "pipelined under the next forward" if getattr(args, "overlap_opt", 0) else "in line"),
             "l2_policy": "working set (13.5 GB weights + activations) >> 126 MB L2, no flush needed",
             "tflop_per_image": fl["total"] / 1e12}
 

@@ -65,12 +65,19 @@ def main():
         ok &= step_ok
         # the next forward consumes the broadcast shards; state_dict() waits for all of them
     got, want = dp.llma.state_dict(), ref.llma.state_dict()
-    worst = 0.0
+    worst, over = 0.0, []
     for k in want:
         if k.startswith("clip."):
             continue
         gk, wk = got[k].float(), want[k].float()
         bad = ((gk - wk).abs() > 1e-5 + 2 ** -6 * wk.abs()).float().mean().item()
+        # Adam's sign-like first steps flip where a gradient is rounding noise (the two runs sum the ranks'
+        # bf16 gradients in different places); a 256-element bias that starts at zero moves in steps of 1/256,
+        # so small tensors get a wider allowance.  A lost update or exchange would be ~100 % either way.
+        limit = 0.03 if wk.numel() >= 4096 else 0.08
+        if bad > limit:
+            over.append((k, round(bad, 4)))
+        assert (gk - wk).abs().max().item() <= 2 * 1e-3 * 3 + 2 ** -6 * wk.abs().max().item(), k  # never beyond 2*lr*steps
         worst = max(worst, bad)
         # replicas must be IDENTICAL across ranks after the shard broadcasts
         other = got[k].clone()
@@ -79,9 +86,9 @@ def main():
         if not same and rank == 1:
             print(f"rank1 differs from rank0: {k} frac={(other != got[k]).float().mean().item():.4f}", flush=True)
         ok &= same
-    if worst > 0.03:
-        print(f"rank{rank}: {worst:.4f} of some parameter's elements differ from the single-replica run", flush=True)
-    ok &= worst <= 0.03  # Adam's sign-like first steps flip where gradients are rounding noise
+    if over:
+        print(f"rank{rank}: too many elements differ from the single-replica run: {over}", flush=True)
+    ok &= not over
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

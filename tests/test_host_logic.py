@@ -70,21 +70,35 @@ def test_bucket_plan_tiles_the_flat_buffer_exactly_once():
         assert bool((cover == 1).all())
 
 
-def _dp_worker(rank, world, port, total, plan, out):
+def _dp_worker(rank, world, port, total, plan, out, decay_numel=None, chunks=None):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from a3vlm_b200.dp import BucketAllReduce
+    from a3vlm_b200.dp import BucketAllReduce, BucketReduceScatter
+    from a3vlm_b200.engine import owned_ranges
 
     g = torch.Generator().manual_seed(rank)
     # local gradients already carry the 1/world factor (folded into the loss gradient)
     local = torch.randn(total, generator=g) / world
+    expect = sum(torch.randn(total, generator=torch.Generator().manual_seed(k)) for k in range(world)) / world
     flat = local.clone()
     r = BucketAllReduce(flat, None, None)
     for lo, hi in plan:
         r.on_bucket(lo, hi)
     r.finish()
-    expect = sum(torch.randn(total, generator=torch.Generator().manual_seed(k)) for k in range(world)) / world
     ok = torch.allclose(flat, expect, atol=1e-6) and sorted(r.covered) == sorted(plan)
+    if decay_numel is not None:
+        # sharded optimiser: after the exchange every range this rank OWNS (its slice of each chunk + the
+        # replicated tail) holds the mean gradient; the ranks' slices tile every chunk
+        flat = local.clone()
+        rs = BucketReduceScatter(flat, decay_numel, world, rank, None, None)
+        for lo, hi in plan:
+            rs.on_bucket(lo, hi)
+        rs.finish()
+        mine = owned_ranges(chunks, decay_numel, total, world, rank)
+        for (lo, hi, decayed), (clo, chi) in zip(mine, chunks + [(decay_numel, total)]):
+            ok = ok and torch.allclose(flat[lo:hi], expect[lo:hi], atol=1e-6)
+            ok = ok and ((lo, hi) == rs.owned(clo, chi) if decayed else (lo, hi) == (decay_numel, total))
+        ok = ok and sorted(rs.covered) == sorted(plan)
     out[rank] = bool(ok)
     dist.barrier()
     dist.destroy_process_group()
@@ -92,18 +106,49 @@ def _dp_worker(rank, world, port, total, plan, out):
 
 def test_data_parallel_gradient_exchange_world2_gloo():
     """N > 1 path on CPU: two ranks, the bucketed SUM all-reduce over the engine's bucket plan yields
-    the mean gradient on both ranks."""
-    from a3vlm_b200.engine import bucket_plan, build_layout, flat_offsets
+    the mean gradient on both ranks; the sharded variant (reduce-scatter per chunk, all-reduce of the
+    tail) yields it on every range a rank owns."""
+    from a3vlm_b200.engine import bucket_plan, build_layout, flat_offsets, optimizer_chunks
 
     a = _args()
     decay, nodecay, _, _ = build_layout(a, _vis())
-    offs, total = flat_offsets(decay + nodecay)
-    plan = bucket_plan(offs, total, a.n_layers)
+    offs, total = flat_offsets(decay + nodecay, segment_after=decay[-1][0])
+    decay_numel = offs[nodecay[0][0]][0]
+    plan = bucket_plan(offs, total, a.n_layers, decay_numel)
+    chunks = optimizer_chunks(offs, decay_numel, a.n_layers)
     mgr = mp.Manager()
     out = mgr.dict()
     port = 29500 + os.getpid() % 2000
-    mp.spawn(_dp_worker, args=(2, port, total, plan, out), nprocs=2, join=True)
+    mp.spawn(_dp_worker, args=(2, port, total, plan, out, decay_numel, chunks), nprocs=2, join=True)
     assert out[0] and out[1]
+
+
+def test_optimizer_chunks_and_owned_slices_tile_the_decay_region():
+    """The pipelined / sharded optimiser's plan: chunks in forward-consumption order tile [0, decay_numel),
+    are the decay buckets of the backward in reverse, and for 1 / 2 / 4 / 8 ranks the ranks' 16-byte aligned
+    slices tile every chunk exactly once."""
+    from a3vlm_b200.engine import bucket_plan, build_layout, flat_offsets, optimizer_chunks, owned_ranges
+
+    for vis in (None, _vis()):
+        a = _args()
+        decay, nodecay, _, _ = build_layout(a, vis)
+        offs, total = flat_offsets(decay + nodecay, segment_after=decay[-1][0])
+        decay_numel = offs[nodecay[0][0]][0]
+        chunks = optimizer_chunks(offs, decay_numel, a.n_layers)
+        assert chunks[0][0] == 0 and chunks[-1][1] == decay_numel
+        assert all(x[1] == y[0] for x, y in zip(chunks[:-1], chunks[1:]))
+        assert chunks[1][0] == offs["layers.0.wqkv"][0] and chunks[-1][0] == offs["output.weight"][0]
+        plan = bucket_plan(offs, total, a.n_layers, decay_numel)
+        assert plan[:-1] == chunks[::-1] and plan[-1] == (decay_numel, total)
+        for world in (1, 2, 4, 8):
+            cover = torch.zeros(total, dtype=torch.int32)
+            for rank in range(world):
+                mine = owned_ranges(chunks, decay_numel, total, world, rank)
+                assert mine[-1] == (decay_numel, total, False) and len(mine) == len(chunks) + 1
+                for lo, hi, decayed in mine[:-1]:
+                    assert decayed and lo % 8 == 0 and (hi - lo) % 8 == 0
+                    cover[lo:hi] += 1
+            assert bool((cover[:decay_numel] == 1).all())
 
 
 def test_rope_table_is_the_reference_expression():
