@@ -279,6 +279,61 @@ def test_live_oracle_midsize():
         assert margin <= 4 * 2.0 ** -8 * max(mag, 1.0), (r, k, margin, mag, g, e)
 
 
+def test_13b_geometry_two_layers_matches_oracle():
+    """BASELINE config 4's decoder geometry (Llama-2-13B: D 5120, 40 heads x 128, F 13824, V 32000) and the
+    real ViT-L/14 width (1024, 16 heads x 64, MLP 4096 at 224 px), cut to 2 + 2 layers so the CPU oracle
+    finishes in seconds: logits, loss, per-parameter gradients and one clipped AdamW step's norm through the
+    reference-facing API.  Exercises the N / K shapes (5120, 15360, 27648, 13824) that the 7B runs never
+    touch."""
+    import a3vlm_oracle as O
+    from a3vlm_b200.train import AdamW, NativeScalerWithGradNormCount
+
+    a = O.ModelArgs(dim=5120, n_layers=2, n_heads=40, vocab_size=32000, multiple_of=256, max_seq_len=512, max_batch_size=4)
+    v = O.VisionArgs(image_size=224, patch=14, width=1024, layers=2, heads=16, mlp=4096)
+    assert O.ffn_hidden_dim(a.dim, a.multiple_of, None) == 13824
+    sd = O.init_params(a, v, seed=13, output_scale=1.0)
+    m = build(a, v, sd)
+    g = torch.Generator().manual_seed(8)
+    B, T = 2, 24
+    tok = torch.randint(3, 32000, (B, T), generator=g)
+    tok[:, 0] = 1
+    lab = tok.clone()
+    lab[:, :8] = 0
+    img = torch.randn(B, 3, 224, 224, generator=g)
+    train = [k for k in sd if not k.startswith("clip.")]
+    for k in train:
+        sd[k].requires_grad_(True)
+    orc = O.OracleTransformer(a, v, sd, native_linear=True)
+    ref_loss = O.meta_forward_loss(orc, tok, lab, img)
+    ref_loss.backward()
+    exact = O.OracleTransformer(a, v, sd, act_dtype=torch.float32)  # same bf16 weights, no activation rounding
+    with torch.no_grad():
+        ref_logits = orc.forward(tok, img)
+        exact_logits = exact.forward(tok, img)
+    m.zero_grad(set_to_none=True)
+    with torch.no_grad():
+        got_logits = m.llma(tok, img)
+    # at this width both bf16 paths sit ~1e-2 from the unrounded model (5120-long reductions of bf16-rounded
+    # activations); ours must not be further from it than the oracle's own bf16 path by more than 25 %
+    e_ref, e_got = rel_l2(ref_logits, exact_logits), rel_l2(got_logits, exact_logits)
+    print(f"13b geometry: |oracle_bf16 - fp32| = {e_ref:.3e}, |cuda - fp32| = {e_got:.3e}")
+    assert e_got <= 1.25 * e_ref + 1e-3, (e_got, e_ref)
+    check("13b-geometry logits", got_logits, ref_logits, rel=3e-2, ulps=8)
+    loss, _ = m(tok.cuda(), lab.cuda(), images=img.cuda())
+    assert abs(loss.item() - ref_loss.item()) <= 2e-3 * abs(ref_loss.item()), (loss.item(), ref_loss.item())
+    opt = AdamW(m, lr=1e-4, betas=(0.9, 0.95), weight_decay=0.0)
+    norm = NativeScalerWithGradNormCount()(loss, opt, m, clip_grad=1.0, update_grad=True)
+    named = dict(m.llma.named_parameters())
+    ref_total = math.sqrt(sum(float(sd[k].grad.float().pow(2).sum()) for k in train))
+    assert abs(norm.item() - ref_total) <= 1e-2 * ref_total, (norm.item(), ref_total)
+    for k in ("layers.1.feed_forward.w2.weight", "layers.0.attention.wq.weight", "layers.0.feed_forward.w3.weight",
+              "layers.1.attention.wo.weight", "output.weight", "visual_proj.0.weight", "layers.0.attention_norm.weight",
+              "norm.weight", "start_img"):
+        check("13b-geometry grad " + k, named[k].grad, sd[k].grad, rel=4e-2, ulps=8)  # measured 1.7e-2 .. 2.7e-2
+    for k in train:
+        sd[k].requires_grad_(False)
+
+
 def test_reference_five_view_tiling_matches_oracle():
     """the reference's own geometry -- a (2S x 2S) image becomes five S x S views (fp16 bicubic
     global view + four quadrants, llama_ens5.py:383-385), each wrapped in start/end tags (:471-477)."""
