@@ -9,16 +9,28 @@ CLIP ViT-L/14 tower -> visual_proj -> start/end tags + splice -> Llama decoder -
 Every function cites the reference file:line it follows (paths relative to /root/reference;
 `M/` = model/accessory/, `LLM/` = model/accessory/model/LLM/).
 
-PARITY PINNING.  The reference ships no tests, golden vectors or fixtures for this path
-(SURVEY section 4), it cannot be imported here (LLM/llama.py and configs/global_configs.py are
-absent from the tree; fairscale / open_clip / apex are not installed), so "parity unpinned" by the
-reference itself.  The pins we can and do make (tests/test_oracle.py):
-  * decoder math (RoPE layout, RMSNorm rounding order, SwiGLU, causal mask, FFN width rule) against
-    `transformers.LlamaForCausalLM` after the q/k row permutation the reference's own exporter
-    documents (M/tools/convert_weights_to_hf.py:209-219);
-  * ViT tower against `transformers.CLIPVisionModel` (+ post_layernorm on all tokens), for exact
-    GELU (open_clip built with pretrained=None, LLM/llama_ens5.py:299) and QuickGELU (:297);
-  * committed golden vectors under tests/golden/ generated by tests/golden/make_golden.py.
+PARITY PINNING.  The reference ships no tests, golden vectors or fixtures for this path (SURVEY
+section 4) and cannot be imported as shipped (LLM/llama.py and configs/global_configs.py are absent
+from the tree; fairscale / open_clip / apex / dacite are not installed).  Pins (tests/test_reference_pins.py,
+tests/test_oracle.py):
+  * OUTPUTS OF THE REFERENCE'S OWN SOURCE executed in the authoring container with the missing third-party
+    names stubbed (tests/golden/make_reference_golden.py lists what ran unmodified and what was stubbed;
+    vectors committed as tests/golden/reference_exec.pt): components.RMSNorm (bit-exact); llama_ens5
+    Attention (SDPA branch, KV cache, right-aligned mask) / FeedForward / TransformerBlock /
+    Transformer.forward / forward_inference in fp32 (2e-4) and run in bf16 (rounding points); the image
+    splice, `image_words` logit slice and decode offset; clip_encode_image's glue over a tower built from
+    torch.nn primitives; MetaModel.forward's trimmed shifted loss; MetaModel.generate's greedy loop
+    (token-exact); MetaModel.sample_top_p under a fixed seed;
+  * what that execution had to stub stays pinned independently: the RoPE helpers of the absent LLM/llama.py
+    and the decoder as a whole against `transformers.LlamaForCausalLM` after the q/k row permutation the
+    reference's own exporter documents (M/tools/convert_weights_to_hf.py:209-219); the open_clip tower
+    against `transformers.CLIPVisionModel` (+ post_layernorm on all tokens), exact GELU (open_clip built
+    with pretrained=None, LLM/llama_ens5.py:299) and QuickGELU (:297);
+  * committed golden vectors of the whole multimodal path under tests/golden/tiny_e2e.pt
+    (tests/golden/make_golden.py).
+Not pinned by the reference itself (stated in DESIGN.md section 2): flash-attn (GPU-only; same function as
+the SDPA branch that was executed), the ConvNeXt / DINOv2 / Q-Former encoders (out of scope), the bicubic
+global view (torch's own F.interpolate in fp16, as the reference calls it).
 
 Third-party arithmetic restated from published algorithms (un-vendored, unpinned -- the reference
 has no requirements file): open_clip `VisionTransformer` (ViT-L-14), Meta Llama `precompute_freqs_cis

@@ -1,0 +1,181 @@
+"""The oracle (and, on a GPU, the CUDA path itself) against outputs of THE REFERENCE'S OWN SOURCE executed
+in the authoring container -- tests/golden/reference_exec.pt, produced by
+tests/golden/make_reference_golden.py (its docstring lists exactly what ran unmodified and what was
+stubbed).  fp32 vectors: the oracle's mathematics vs the reference's (tolerance = fp32 summation order,
+SDPA vs an explicit softmax).  bf16 vectors: the rounding points vs the reference module run in
+bf16 (tolerance = a few bf16 ulps: CPU SDPA / matmul accumulate differently)."""
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+bf16 = torch.bfloat16
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return torch.load(os.path.join(ROOT, "tests", "golden", "reference_exec.pt"))
+
+
+@pytest.fixture(scope="module")
+def cfg(gold):
+    import a3vlm_oracle as O
+    import make_reference_golden as G
+
+    a, v = G.tiny_cfg()
+    sd = O.init_params(a, v, seed=gold["seed"], output_scale=gold["output_scale"])
+    return a, v, sd
+
+
+def close(got, ref, atol, rtol=0.0):
+    torch.testing.assert_close(got.float(), ref.float(), atol=atol, rtol=rtol)
+
+
+def test_rmsnorm_is_the_reference_class_bit_for_bit(gold):
+    import a3vlm_oracle as O
+
+    assert torch.equal(O.rmsnorm(gold["rms_x"], gold["rms_w"], 1e-5), gold["rms_fp32"])
+    got = O.rmsnorm(gold["rms_x"].to(bf16), gold["rms_w"].to(bf16), 1e-5)
+    assert got.dtype == bf16 and torch.equal(got, gold["rms_bf16"])  # normalise in fp32, round, then scale
+
+
+def test_decoder_fp32_matches_reference_transformer(gold, cfg):
+    """Attention (SDPA branch, KV cache, right-aligned mask), FeedForward, TransformerBlock, Transformer.forward /
+    forward_inference of LLM/llama_ens5.py, text only."""
+    import a3vlm_oracle as O
+
+    a, _, sd = cfg
+    orc = O.OracleTransformer(a, None, sd, act_dtype=torch.float32)
+    tok = gold["tokens"]
+    close(orc.forward(tok), gold["fwd_fp32"], 2e-4)
+    close(orc.forward_inference(tok[:, :6], 0), gold["prefill_fp32"], 2e-4)
+    close(orc.forward_inference(tok[:, 6:7], 6), gold["decode1_fp32"], 2e-4)
+    close(orc.forward_inference(tok[:, 7:8], 7), gold["decode2_fp32"], 2e-4)
+    close(orc.forward_inference(tok[:, 8:11], 8), gold["chunk_fp32"], 2e-4)  # l > 1 on the cache: mask alignment
+
+
+def test_decoder_bf16_rounding_points_match_reference_run_in_bf16(gold, cfg):
+    import a3vlm_oracle as O
+
+    a, _, sd = cfg
+    orc = O.OracleTransformer(a, None, sd)  # act_dtype bf16
+    tok = gold["tokens"]
+    pairs = [(orc.forward(tok), gold["fwd_bf16"]), (orc.forward_inference(tok[:, :6], 0), gold["prefill_bf16"]),
+             (orc.forward_inference(tok[:, 6:7], 6), gold["decode1_bf16"]),
+             (orc.forward_inference(tok[:, 7:8], 7), gold["decode2_bf16"]),
+             (orc.forward_inference(tok[:, 8:11], 8), gold["chunk_bf16"])]
+    for got, ref in pairs:
+        got, ref = got.float(), ref.float()
+        rel = ((got - ref).norm() / ref.norm()).item()
+        assert rel <= 1e-2, rel
+        assert (got - ref).abs().max().item() <= 4 * 2.0 ** -8 * ref.abs().max().item()
+        # and both are the same distance from the unrounded model (fp32 vectors of the same reference code)
+    exact = gold["fwd_fp32"]
+    e_ref = ((gold["fwd_bf16"].float() - exact).norm() / exact.norm()).item()
+    e_got = ((pairs[0][0].float() - exact).norm() / exact.norm()).item()
+    assert e_got <= 1.25 * e_ref + 1e-3, (e_got, e_ref)
+
+
+def test_image_splice_logit_slice_and_decode_offset_match_reference(gold, cfg):
+    """llama_ens5.py:469-486,500-520 run on given per-view tokens: BOS | 5 x (start, tokens, end) | text, logits
+    for the text positions only, `cache_image_words` added to later start positions."""
+    import a3vlm_oracle as O
+
+    a, _, sd = cfg
+    v5 = O.VisionArgs(image_size=28, patch=14, width=128, layers=2, heads=2, mlp=256, views=5)
+    orc = O.OracleTransformer(a, v5, sd, act_dtype=torch.float32)
+    views = gold["img_views"]  # (5, B, 5, D)
+    orc.encode_image = lambda image: torch.cat(list(views), dim=0)  # view-major, as :455-457 returns it
+    tok = gold["tokens"]
+    fake = torch.zeros(2, 3, 4, 4)
+    assert orc.image_words == 35
+    close(orc.forward(tok, fake), gold["img_fwd_fp32"], 2e-4)
+    close(orc.forward_inference(tok[:, :5], 0, fake), gold["img_prefill_fp32"], 2e-4)
+    assert orc.cache_image_words == gold["img_cache_image_words"] == 35
+    close(orc.forward_inference(tok[:, 5:6], 5), gold["img_decode_fp32"], 2e-4)
+
+
+def test_vit_tower_matches_reference_glue_over_torch_primitives(gold, cfg):
+    """clip_encode_image (llama_ens5.py:351-375) executed over conv / LayerNorm / nn.MultiheadAttention."""
+    import a3vlm_oracle as O
+
+    a, v, sd = cfg
+    orc = O.OracleTransformer(a, v, sd, act_dtype=torch.float32)
+    close(orc.clip_encode_image(gold["vit_image"]), gold["vit_tokens_fp32"], 1e-4)
+
+
+def test_loss_matches_reference_metamodel_forward(gold, cfg):
+    import a3vlm_oracle as O
+
+    a, _, sd = cfg
+    orc = O.OracleTransformer(a, None, sd, act_dtype=torch.float32)
+    loss = O.meta_forward_loss(orc, gold["loss_examples"], gold["loss_labels"])
+    close(loss, gold["loss_fp32"], 1e-5, 1e-5)
+    ex, lab = O.trim_trailing_pad(gold["loss_examples"], gold["loss_labels"])
+    assert ex.shape[1] == 10  # the reference dropped the all-pad tail columns
+
+
+def test_generate_matches_reference_metamodel_generate(gold, cfg):
+    """Greedy ids from the reference's own loop (meta.py:379-485): unequal prompts, stops that end every row
+    early, left truncation with a row that keeps generating while the long prompt is force-fed."""
+    import a3vlm_oracle as O
+
+    a, _, sd = cfg
+    orc = O.OracleTransformer(a, None, sd, act_dtype=torch.float32)
+    for c in gold["generate_cases"]:
+        prompts = [[1] + [int(x) for x in p.split()] for p in c["prompts"]]
+        stops = [[int(x) for x in s.split()] for s in c["stops"]] * 2  # encode_segment + encode_wo_prefix_space
+        out, _, _ = O.generate_tokens(orc, prompts, max_gen_len=c["max_gen_len"], eos_id=2, stop_sequences=stops)
+        assert out == c["generated"], (c["prompts"], out, c["generated"])
+
+
+def test_sample_top_p_matches_reference_under_the_same_seed(gold):
+    import a3vlm_oracle as O
+
+    torch.manual_seed(1234)
+    got = O.sample_top_p(gold["topp_probs"].clone(), gold["topp_p"])
+    assert torch.equal(got, gold["topp_tokens_seed1234"])
+    # and the explicit-uniform form draws from the same support: every reference draw has positive mass in it
+    lo, hi = O.top_p_token_interval(gold["topp_probs"].double(), gold["topp_p"], gold["topp_tokens_seed1234"].reshape(-1))
+    assert bool((hi > lo).all())
+
+
+@pytest.mark.gpu
+def test_cuda_decoder_matches_reference_run_in_bf16(gold, cfg):
+    """The CUDA path itself (text-only llama_b200 through MetaModel) against the reference module's bf16
+    outputs -- no oracle in between.  Tolerances as tests/test_e2e_gpu.py."""
+    from a3vlm_b200.model import MetaModel
+    from test_e2e_gpu import check
+
+    a, _, sd = cfg
+    text = {k: t for k, t in sd.items() if not k.startswith(("clip.", "visual_proj", "start_img", "end_img"))}
+    m = MetaModel("llama_b200", dict(dim=a.dim, n_layers=a.n_layers, n_heads=a.n_heads, vocab_size=a.vocab_size,
+                                     multiple_of=a.multiple_of, norm_eps=a.norm_eps), None, with_visual=False,
+                  max_seq_len=a.max_seq_len, max_batch_size=4)
+    m.llma.load_state_dict(text)
+    tok = gold["tokens"]
+    with torch.no_grad():
+        check("cuda vs reference fwd", m.llma(tok), gold["fwd_bf16"])
+    check("cuda vs reference prefill", m.llma.forward_inference(tok[:, :6], 0), gold["prefill_bf16"])
+    check("cuda vs reference decode 1", m.llma.forward_inference(tok[:, 6:7], 6), gold["decode1_bf16"])
+    check("cuda vs reference decode 2", m.llma.forward_inference(tok[:, 7:8], 7), gold["decode2_bf16"])
+    check("cuda vs reference 3-token step on the cache", m.llma.forward_inference(tok[:, 8:11], 8), gold["chunk_bf16"])
+    # greedy ids of the reference's generate loop (run in fp32): identical, except that a row may part ways at a
+    # step where the REFERENCE's own top-2 logits are within bf16 rounding of each other (recorded per call)
+    for c in gold["generate_cases"]:
+        prompts = [[1] + [int(x) for x in p.split()] for p in c["prompts"]]
+        stops = [[int(x) for x in s.split()] for s in c["stops"]] * 2
+        out, _, _ = m.generate_tokens(prompts, None, max_gen_len=c["max_gen_len"], eos_id=2, stop_sequences=stops)
+        min_prompt = min(len(q) for q in prompts)
+        for r, (g_, e_) in enumerate(zip(out, c["generated"])):
+            k = next((i for i, (x, y) in enumerate(zip(g_, e_)) if x != y), None)
+            if k is None:
+                assert len(g_) == len(e_)
+                continue
+            margin, mag = c["margins"][len(prompts[r]) + k - min_prompt][r].tolist()
+            print(f"row {r} diverges at generated token {k}: reference top-2 margin {margin:.4f} at logit {mag:.2f}")
+            assert margin <= 4 * 2.0 ** -8 * max(mag, 1.0), (r, k, margin, mag, g_, e_)
