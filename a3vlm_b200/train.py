@@ -4,6 +4,7 @@ fused all-reduce / global-norm clip / AdamW kernels instead of FSDP + apex Fused
 from __future__ import annotations
 
 import contextlib
+import math
 from typing import Optional
 
 import torch
@@ -78,3 +79,32 @@ def no_sync(llma):
         yield
     finally:
         llma.sync_grads = prev
+
+
+def adjust_learning_rate(optimizer, it, args) -> float:
+    """M/util/lr_sched.py:3-20 (per-iteration schedule used by engine_finetune.py:37-41): linear warm-up over
+    `args.warmup_iters`, half-cycle cosine from `args.lr` down to `args.min_lr` until `args.lr_decay_iters`,
+    `min_lr` afterwards; honours a per-group `lr_scale`.  Host arithmetic, kept for standalone use."""
+    if it < args.warmup_iters:
+        lr = args.lr * it / args.warmup_iters
+    elif it > args.lr_decay_iters:
+        lr = args.min_lr
+    else:
+        ratio = (it - args.warmup_iters) / (args.lr_decay_iters - args.warmup_iters)
+        assert 0 <= ratio <= 1
+        lr = args.min_lr + (args.lr - args.min_lr) * 0.5 * (1.0 + math.cos(math.pi * ratio))
+    for group in optimizer.param_groups:
+        group["lr"] = lr * group["lr_scale"] if "lr_scale" in group else lr
+    return lr
+
+
+def adjust_learning_rate_epoch(optimizer, epoch, args) -> float:
+    """M/util/lr_sched.py:23-35: the same shape over fractional epochs (warmup_epochs, epochs)."""
+    if epoch < args.warmup_epochs:
+        lr = args.lr * epoch / args.warmup_epochs
+    else:
+        lr = args.min_lr + (args.lr - args.min_lr) * 0.5 * \
+            (1.0 + math.cos(math.pi * (epoch - args.warmup_epochs) / (args.epochs - args.warmup_epochs)))
+    for group in optimizer.param_groups:
+        group["lr"] = lr * group["lr_scale"] if "lr_scale" in group else lr
+    return lr

@@ -18,6 +18,8 @@ names stubbed, and run its own classes / methods on CPU:
     model/accessory/model/meta.py              MetaModel.forward (pad trimming, shifted CE ignore_index 0),
                                                MetaModel.generate (force-feeding, stops, truncation),
                                                MetaModel.sample_top_p
+    model/accessory/util/lr_sched.py           adjust_learning_rate, adjust_learning_rate_epoch
+    model/accessory/util/misc.py               add_weight_decay (function source executed on its own)
 
   stubbed (stated here and in DESIGN.md section 2)
     fairscale ColumnParallelLinear / RowParallelLinear / ParallelEmbedding -> nn.Linear / nn.Embedding
@@ -39,6 +41,7 @@ names stubbed, and run its own classes / methods on CPU:
         space-separated token ids; `Tensor.cuda()` -> identity (no GPU in this container)
 """
 import importlib
+import importlib.util
 import os
 import sys
 import types
@@ -290,6 +293,37 @@ def main():
     torch.manual_seed(1234)
     out["topp_probs"], out["topp_p"] = probs, 0.75
     out["topp_tokens_seed1234"] = meta.sample_top_p(probs.clone(), 0.75)
+
+    # ---- host-side training arithmetic: util/lr_sched.py (imported as is) and misc.add_weight_decay (its
+    # function source executed on its own: the rest of misc.py needs FSDP / fairscale at import time)
+    import ast
+
+    spec = importlib.util.spec_from_file_location("ref_lr_sched", os.path.join(REF, "accessory", "util", "lr_sched.py"))
+    S = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(S)
+    sched_args = SimpleNamespace(lr=2e-5, min_lr=1e-6, warmup_iters=50, lr_decay_iters=1000, warmup_epochs=0.03, epochs=3)
+    opt = SimpleNamespace(param_groups=[{"lr": 0.0}, {"lr": 0.0, "lr_scale": 0.5}])
+    its = [0, 1, 25, 50, 51, 400, 999, 1000, 1001, 5000]
+    out["lr_args"] = vars(sched_args)
+    out["lr_iter"] = [(it, S.adjust_learning_rate(opt, it, sched_args), opt.param_groups[1]["lr"]) for it in its]
+    eps_ = [0.0, 0.01, 0.03, 0.5, 1.7, 3.0]
+    out["lr_epoch"] = [(e, S.adjust_learning_rate_epoch(opt, e, sched_args)) for e in eps_]
+    src = open(os.path.join(REF, "accessory", "util", "misc.py")).read()
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "add_weight_decay")
+    ns = {}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "misc.py:add_weight_decay", "exec"), ns)
+    holder = nn.Module()
+    names = [k for k in sd]  # every parameter name of the path, frozen ViT included (requires_grad False)
+    params = {}
+    for k in names:
+        prm = nn.Parameter(torch.zeros(1), requires_grad=not k.startswith("clip."))
+        params[k] = prm
+    holder.named_parameters = lambda: list(params.items())
+    groups = ns["add_weight_decay"](holder, 0.1)
+    ids = {id(p_): k for k, p_ in params.items()}
+    out["wd_no_decay"] = sorted(ids[id(p_)] for p_ in groups[0]["params"])
+    out["wd_decay"] = sorted(ids[id(p_)] for p_ in groups[1]["params"])
+    assert groups[0]["weight_decay"] == 0.0 and groups[1]["weight_decay"] == 0.1
 
     path = os.path.join(HERE, "reference_exec.pt")
     torch.save(out, path)

@@ -179,3 +179,46 @@ def test_cuda_decoder_matches_reference_run_in_bf16(gold, cfg):
             margin, mag = c["margins"][len(prompts[r]) + k - min_prompt][r].tolist()
             print(f"row {r} diverges at generated token {k}: reference top-2 margin {margin:.4f} at logit {mag:.2f}")
             assert margin <= 4 * 2.0 ** -8 * max(mag, 1.0), (r, k, margin, mag, g_, e_)
+
+
+def test_lr_schedule_matches_reference_lr_sched(gold):
+    from types import SimpleNamespace
+
+    from a3vlm_b200.train import adjust_learning_rate, adjust_learning_rate_epoch
+
+    args = SimpleNamespace(**gold["lr_args"])
+    opt = SimpleNamespace(param_groups=[{"lr": 0.0}, {"lr": 0.0, "lr_scale": 0.5}])
+    for it, lr, scaled in gold["lr_iter"]:
+        assert adjust_learning_rate(opt, it, args) == lr and opt.param_groups[0]["lr"] == lr
+        assert opt.param_groups[1]["lr"] == scaled
+    for ep, lr in gold["lr_epoch"]:
+        assert adjust_learning_rate_epoch(opt, ep, args) == lr
+
+
+def test_weight_decay_groups_match_reference_add_weight_decay(gold, cfg):
+    """misc.add_weight_decay run on the path's parameter names: the engine's decay / no-decay regions hold
+    exactly the same sets (incl. the reference's quirk that visual_proj.1 -- a LayerNorm -- IS decayed because
+    its name does not end in "norm.weight")."""
+    import a3vlm_oracle as O
+    from a3vlm_b200.engine import build_layout
+
+    a, v, _ = cfg
+    decay, nodecay, frozen, _ = build_layout(a, v)
+
+    def ref_names(layout):
+        D = a.dim
+        out = []
+        for n, _shape in layout:
+            if n.endswith(".wqkv"):
+                out += [n[:-4] + f"attention.{x}.weight" for x in ("wq", "wk", "wv")]
+            elif n.endswith(".w13"):
+                out += [n[:-3] + f"feed_forward.{x}.weight" for x in ("w1", "w3")]
+            else:
+                out.append(n)
+        return sorted(out)
+
+    assert ref_names(decay) == gold["wd_decay"]
+    assert ref_names(nodecay) == gold["wd_no_decay"]
+    assert "visual_proj.1.weight" in gold["wd_decay"] and "visual_proj.1.bias" in gold["wd_no_decay"]
+    assert all(O.is_no_decay(n) for n in gold["wd_no_decay"]) and not any(O.is_no_decay(n) for n in gold["wd_decay"])
+    assert not any(n.startswith("clip.") for n in gold["wd_decay"] + gold["wd_no_decay"])  # frozen tower: no group
