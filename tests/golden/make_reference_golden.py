@@ -15,6 +15,7 @@ names stubbed, and run its own classes / methods on CPU:
                                                forward / forward_inference / _allocate_kv_cache (text-only
                                                build), the image splice + logit slice of forward /
                                                forward_inference, clip_encode_image
+    model/accessory/model/LLM/llama_ens5_2images.py  forward_inference with image + depth_images (RGB-D splice)
     model/accessory/model/meta.py              MetaModel.forward (pad trimming, shifted CE ignore_index 0),
                                                MetaModel.generate (force-feeding, stops, truncation),
                                                MetaModel.sample_top_p
@@ -238,6 +239,28 @@ def main():
     out["img_prefill_fp32"] = ref.forward_inference(tok[:, :5], 0, fake_image).clone()
     out["img_cache_image_words"] = int(ref.cache_image_words)
     out["img_decode_fp32"] = ref.forward_inference(tok[:, 5:6], 5).clone()
+
+    # ---- RGB-D build (LLM/llama_ens5_2images.py:511-547): both streams spliced with their own tags; a lone RGB
+    # image is ignored at inference (:518)
+    L2 = importlib.import_module("accessory.model.LLM.llama_ens5_2images")
+    a_rgbd = O.ModelArgs(**{**vars(a), "max_seq_len": 128})  # 1 + 70 image words + text
+    ref2 = build_reference_decoder(L2, a_rgbd, sd, torch.float32)
+    g2 = torch.Generator().manual_seed(9)
+    depth_views = [torch.randn(2, n_tok, a.dim, generator=g2) for _ in range(n_views)]
+    tags = {k: torch.rand(1, 1, a.dim, generator=g2) for k in ("start_depth_img", "end_depth_img")}
+    ref2.start_img, ref2.end_img = nn.Parameter(sd["start_img"].float()), nn.Parameter(sd["end_img"].float())
+    ref2.start_depth_img, ref2.end_depth_img = nn.Parameter(tags["start_depth_img"]), nn.Parameter(tags["end_depth_img"])
+    ref2.visual_image_words = n_views * (n_tok + 2)
+    ref2.image_words = 2 * ref2.visual_image_words
+    rgb_marker, depth_marker = torch.zeros(2, 3, 4, 4), torch.ones(2, 3, 4, 4)
+    ref2.encode_image = lambda image: [t.clone() for t in (depth_views if bool(image.flatten()[0] == 1) else views)]
+    out["rgbd_depth_views"] = torch.stack(depth_views)
+    out["rgbd_tags"] = tags
+    out["rgbd_prefill_fp32"] = ref2.forward_inference(tok[:, :5], 0, rgb_marker, depth_marker).clone()
+    out["rgbd_cache_image_words"] = int(ref2.cache_image_words)
+    out["rgbd_decode_fp32"] = ref2.forward_inference(tok[:, 5:6], 5).clone()
+    out["rgbd_lone_rgb_prefill_fp32"] = ref2.forward_inference(tok[:, :5], 0, rgb_marker).clone()
+    out["rgbd_lone_cache_image_words"] = int(ref2.cache_image_words)
 
     # ---- clip_encode_image glue (llama_ens5.py:351-375) over a torch-primitive tower
     img = torch.randn(2, 3, v.image_size, v.image_size, generator=g)

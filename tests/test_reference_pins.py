@@ -99,6 +99,28 @@ def test_image_splice_logit_slice_and_decode_offset_match_reference(gold, cfg):
     close(orc.forward_inference(tok[:, 5:6], 5), gold["img_decode_fp32"], 2e-4)
 
 
+def test_rgbd_splice_matches_reference_2images(gold, cfg):
+    """LLM/llama_ens5_2images.py:511-547: BOS | RGB views | depth views (own tags) | text; decode offset counts
+    both streams; a lone RGB image is ignored at inference (:518)."""
+    import a3vlm_oracle as O
+
+    a, _, sd = cfg
+    v5 = O.VisionArgs(image_size=28, patch=14, width=128, layers=2, heads=2, mlp=256, views=5)
+    p = dict(sd)
+    p.update(gold["rgbd_tags"])
+    orc = O.OracleTransformer(O.ModelArgs(**{**vars(a), "max_seq_len": 128}), v5, p, act_dtype=torch.float32, rgbd=True)
+    rgb, depth = gold["img_views"], gold["rgbd_depth_views"]
+    rgb_marker, depth_marker = torch.zeros(2, 3, 4, 4), torch.ones(2, 3, 4, 4)
+    orc.encode_image = lambda image: torch.cat(list(depth if bool(image.flatten()[0] == 1) else rgb), dim=0)
+    tok = gold["tokens"]
+    assert orc.image_words == 70 and orc.visual_image_words == 35
+    close(orc.forward_inference(tok[:, :5], 0, rgb_marker, depth_marker), gold["rgbd_prefill_fp32"], 2e-4)
+    assert orc.cache_image_words == gold["rgbd_cache_image_words"] == 70
+    close(orc.forward_inference(tok[:, 5:6], 5), gold["rgbd_decode_fp32"], 2e-4)
+    close(orc.forward_inference(tok[:, :5], 0, rgb_marker), gold["rgbd_lone_rgb_prefill_fp32"], 2e-4)
+    assert orc.cache_image_words == gold["rgbd_lone_cache_image_words"] == 0
+
+
 def test_vit_tower_matches_reference_glue_over_torch_primitives(gold, cfg):
     """clip_encode_image (llama_ens5.py:351-375) executed over conv / LayerNorm / nn.MultiheadAttention."""
     import a3vlm_oracle as O
