@@ -47,16 +47,21 @@ def main():
     ropt = AdamW(ref, lr=1e-3, weight_decay=0.1)
     ok = True
     for step in range(3):
-        tok, lab, img = batch(rank + 10 * step)
+        # the last step accumulates two micro-batches per rank: the first inside no_sync() (update_grad=False,
+        # M/util/misc.py:311-313 -- no gradient exchange), the second exchanges the accumulated gradients
+        micro = 2 if step == 2 else 1
         dp.zero_grad(set_to_none=True)
-        loss, _ = dp(tok, lab, images=img)
-        norm = scaler(loss, opt, dp, clip_grad=0.5, update_grad=True)
-        # reference: every rank's batch on one replica, accumulated, each scaled by 1/world
+        for k in range(micro):
+            tok, lab, img = batch(rank + 10 * step + 100 * k)
+            loss, _ = dp(tok, lab, images=img)
+            norm = scaler(loss / micro, opt, dp, clip_grad=0.5, update_grad=(k == micro - 1))
+        # reference: every rank's batches on one replica, accumulated, each scaled by 1/(world * micro)
         ref.zero_grad(set_to_none=True)
         for r in range(world):
-            t2, l2, i2 = batch(r + 10 * step)
-            l, _ = ref(t2, l2, images=i2)
-            (l / world).backward()
+            for k in range(micro):
+                t2, l2, i2 = batch(r + 10 * step + 100 * k)
+                l, _ = ref(t2, l2, images=i2)
+                (l / (world * micro)).backward()
         ropt.step(max_norm=0.5)
         rnorm = ropt.grad_norm()
         step_ok = abs(norm.item() - rnorm.item()) <= 2e-2 * rnorm.item()

@@ -292,3 +292,22 @@ def test_resume_continues_the_optimiser_exactly(tmp_path):
         d = (got[k].float() - want[k].float()).abs()
         assert (d <= 2.0 ** -7 * want[k].float().abs()).all(), k
         assert (d == 0).float().mean() > 0.999, k
+
+
+def test_from_pretrained_refuses_what_it_does_not_implement(tmp_path):
+    """Loud errors instead of silent differences (no CUDA needed: all raised before the model is built)."""
+    from a3vlm_b200.model import MetaModel
+
+    with pytest.raises(ValueError, match="pretrained_path"):
+        MetaModel.from_pretrained([])
+    with pytest.raises(NotImplementedError, match="hf://"):
+        MetaModel.from_pretrained("hf://Alpha-VLLM/whatever")
+    with pytest.raises(NotImplementedError, match="quant"):
+        MetaModel.from_pretrained(str(tmp_path), llama_type="llama_b200", quant=True)
+    with pytest.raises(NotImplementedError, match="bf16"):
+        MetaModel.from_pretrained(str(tmp_path), llama_type="llama_b200", dtype=torch.float16)
+    with pytest.raises(ValueError, match="llama_type"):
+        MetaModel.from_pretrained(str(tmp_path))  # no meta.json to read it from
+    (tmp_path / "meta.json").write_text(json.dumps({"llama_type": "llama_ens5"}))
+    with pytest.raises(FileNotFoundError, match="tokenizer"):
+        MetaModel.from_pretrained(str(tmp_path))  # reference plugin name is mapped, but nothing to tokenise with

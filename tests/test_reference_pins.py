@@ -244,3 +244,22 @@ def test_weight_decay_groups_match_reference_add_weight_decay(gold, cfg):
     assert "visual_proj.1.weight" in gold["wd_decay"] and "visual_proj.1.bias" in gold["wd_no_decay"]
     assert all(O.is_no_decay(n) for n in gold["wd_no_decay"]) and not any(O.is_no_decay(n) for n in gold["wd_decay"])
     assert not any(n.startswith("clip.") for n in gold["wd_decay"] + gold["wd_no_decay"])  # frozen tower: no group
+
+
+@pytest.mark.gpu
+def test_cuda_vit_tower_matches_reference_glue(gold, cfg):
+    """The CUDA ViT tower (patchify + patch-embed GEMM + cls / pos / ln_pre + blocks + ln_post) against
+    clip_encode_image of the reference executed over torch.nn primitives (fp32): bf16 tolerance."""
+    from a3vlm_b200.model import MetaModel
+    from test_e2e_gpu import check
+
+    a, v, sd = cfg
+    m = MetaModel("llama_b200", dict(dim=a.dim, n_layers=a.n_layers, n_heads=a.n_heads, vocab_size=a.vocab_size,
+                                     multiple_of=a.multiple_of, image_size=v.image_size, vit_width=v.width,
+                                     vit_layers=v.layers, vit_heads=v.heads, vit_mlp=v.mlp), None, with_visual=True,
+                  max_seq_len=a.max_seq_len, max_batch_size=4)
+    m.llma.load_state_dict(sd)
+    eng = m.llma.engine
+    vw = eng._vit_workspace(2, False)
+    eng.vit_forward(gold["vit_image"].cuda(), vw)
+    check("cuda ViT vs reference glue", vw["feats"].view(2, v.tokens, v.width), gold["vit_tokens_fp32"], rel=1e-2, ulps=6)
