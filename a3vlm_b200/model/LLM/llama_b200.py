@@ -127,9 +127,12 @@ class _TrainFn(torch.autograd.Function):
             scale = 1.0
             dlogits = grad_out.reshape(ws.B * ws.T, -1).to(bf16).contiguous()
         hook = finish = None
-        if model.dp_group is not None and model.sync_grads:
-            hook, finish = eng.allreduce_hook(model.dp_group)
+        if model.dp_group is not None:
+            # the mean over the ranks is folded into every micro-step's gradient, also the ones accumulated
+            # inside no_sync() (FSDP divides the whole accumulated gradient when it finally reduces it)
             scale = scale / model.dp_world
+            if model.sync_grads:
+                hook, finish = eng.allreduce_hook(model.dp_group)
         eng.backward(ws, ctx.examples, dlogits, accumulate=accumulate, on_bucket=hook, scale=scale)
         if finish is not None:
             finish()

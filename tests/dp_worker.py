@@ -1,6 +1,7 @@
 """Worker for tests/test_dp_gpu.py (launched with torch.distributed.run, one rank per GPU): a tiny model
-takes one data-parallel fine-tune step (bucketed all-reduce + sharded AdamW + shard broadcasts) and is
-compared with a single-replica model that accumulates the SAME per-rank batches locally."""
+takes data-parallel fine-tune steps (per-chunk reduce-scatter of the gradients, sharded AdamW, all-gather of
+the updated weights; the last step accumulates two micro-batches, the first inside no_sync()) and is compared
+with a single-replica model that accumulates the SAME per-rank batches locally."""
 import os
 import sys
 
