@@ -35,4 +35,7 @@ res["rmsnorm_bwd"] = {"us": t, "bytes": b, "GBs": b / t / 1e3, "frac_hbm": b / t
 t = timeit(lambda s: ops.rmsnorm_fwd(s["x"], w, 1e-5, out=s["y"], rstd=s["rstd"]))
 b = 2 * rows * D * 2
 res["rmsnorm_fwd"] = {"us": t, "bytes": b, "GBs": b / t / 1e3, "frac_hbm": b / t / 1e3 / hbm}
+out = torch.empty(D, device=dev, dtype=bf)
+t = timeit(lambda s: ops.colsum_partials(part, out))
+res["colsum_partials_296x4096"] = {"us": t}
 print(json.dumps(res))
