@@ -1,87 +1,118 @@
-"""Tokenizer wrapper with the reference's interface (model/accessory/model/tokenizer.py:15-131):
-SentencePiece `.model` file or a HF tokenizer directory; `encode(s, bos, eos)`, `decode`,
-`encode_segment`, `encode_wo_prefix_space`, `n_words`, `bos_id`, `eos_id`, `save`.  CPU string work --
-not on the accelerated path; the reference's own class can be used instead unchanged."""
+"""Tokenizer front end with the reference's interface (model/accessory/model/tokenizer.py:15-131) for
+standalone use of `a3vlm_b200.model.MetaModel`: a SentencePiece `.model` file or a Hugging Face tokenizer
+directory behind `encode(s, bos, eos)`, `decode`, `encode_segment`, `encode_wo_prefix_space`, `n_words`,
+`bos_id`, `eos_id`, `save`.  CPU string work -- not on the accelerated path (BASELINE.json: "the (B,A,S)
+tokenizer/postprocess ... stay as-is"); inside the reference tree its own class is used unchanged."""
 from __future__ import annotations
 
 import os
-from pathlib import Path
-from typing import List
+from typing import Callable, List
+
+# characters that tokenise on their own: text glued behind one of them starts without a word-initial space
+_GLUE_PROBES = ("@", "\n", "\\", "=", ">", "`")
+
+
+class _SentencePieceBackend:
+    kind = "spm"
+
+    def __init__(self, path: str):
+        from sentencepiece import SentencePieceProcessor
+
+        if not os.path.isfile(path):
+            raise FileNotFoundError(path)
+        self.sp = SentencePieceProcessor(model_file=path)
+        if self.sp.vocab_size() != self.sp.get_piece_size():
+            raise ValueError("sentencepiece model: vocab_size != piece_size")
+        self.bos_id, self.eos_id = self.sp.bos_id(), self.sp.eos_id()
+
+    def ids(self, text: str) -> List[int]:
+        return self.sp.encode(text)
+
+    def text(self, ids: List[int]) -> str:
+        return self.sp.decode(ids)
+
+    def size(self) -> int:
+        return self.sp.vocab_size()
+
+    def save(self, directory: str) -> None:
+        with open(os.path.join(directory, "tokenizer.model"), "wb") as f:
+            f.write(self.sp.serialized_model_proto())
+
+
+class _HuggingFaceBackend:
+    kind = "transformers"
+
+    def __init__(self, path: str):
+        from transformers import AutoTokenizer
+
+        self.hf = AutoTokenizer.from_pretrained(path, trust_remote_code=True)
+        self.eos_id = self.hf.eos_token_id
+        if self.eos_id is None:
+            raise ValueError("the tokenizer defines no eos token")
+        self.bos_id = self.hf.bos_token_id if self.hf.bos_token_id is not None else self.eos_id
+
+    def ids(self, text: str) -> List[int]:
+        return self.hf.encode(text, truncation=False, add_special_tokens=False)
+
+    def text(self, ids: List[int]) -> str:
+        return self.hf.decode(ids)
+
+    def size(self) -> int:
+        return len(self.hf)
+
+    def save(self, directory: str) -> None:
+        self.hf.save_pretrained(directory)
+
+
+def _segment_needs_explicit_space(ids: Callable[[str], List[int]]) -> bool:
+    """Does a mid-sentence segment have to be written with its leading space (tokenizer.py:92-114)?  Llama's
+    SentencePiece model implies a word-initial space (False); byte-level BPE vocabularies do not (True)."""
+    whole, bare = ids("Hi my darling"), ids("my darling")
+    if whole[-len(bare):] == bare:
+        return False
+    spaced = ids(" my darling")
+    if whole[-len(spaced):] != spaced:
+        raise ValueError("cannot tell how this tokenizer treats word-initial spaces")
+    return True
 
 
 class Tokenizer:
     def __init__(self, model_path: str):
-        if model_path.endswith(".model"):
-            from sentencepiece import SentencePieceProcessor
-
-            self.tokenizer_type = "spm"
-            assert os.path.isfile(model_path), model_path
-            self.tokenizer = SentencePieceProcessor(model_file=model_path)
-            self.bos_id: int = self.tokenizer.bos_id()
-            self.eos_id: int = self.tokenizer.eos_id()
-            assert self.tokenizer.vocab_size() == self.tokenizer.get_piece_size()
-        else:
-            from transformers import AutoTokenizer
-
-            self.tokenizer_type = "transformers"
-            self.tokenizer = AutoTokenizer.from_pretrained(model_path, trust_remote_code=True)
-            self.bos_id = self.tokenizer.bos_token_id
-            if self.bos_id is None:
-                self.bos_id = self.tokenizer.eos_token_id
-            self.eos_id = self.tokenizer.eos_token_id
-            assert self.eos_id is not None
-        self._probe_tokenizer_style()
+        backend = _SentencePieceBackend if model_path.endswith(".model") else _HuggingFaceBackend
+        self._b = backend(model_path)
+        self.tokenizer_type = self._b.kind
+        self.tokenizer = getattr(self._b, "sp", None) or getattr(self._b, "hf")
+        self.bos_id: int = self._b.bos_id
+        self.eos_id: int = self._b.eos_id
+        self.need_space_before_segment = _segment_needs_explicit_space(self._b.ids)
 
     def encode(self, s: str, bos: bool, eos: bool) -> List[int]:
-        assert type(s) is str
-        if self.tokenizer_type == "transformers":
-            t = self.tokenizer.encode(s, truncation=False, add_special_tokens=False)
-        else:
-            t = self.tokenizer.encode(s)
-        if bos:
-            t = [self.bos_id] + t
-        if eos:
-            t = t + [self.eos_id]
-        return t
+        if type(s) is not str:
+            raise TypeError("Tokenizer.encode expects a str")
+        ids = self._b.ids(s)
+        return [self.bos_id] * bool(bos) + ids + [self.eos_id] * bool(eos)
 
     def encode_segment(self, s: str) -> List[int]:
+        """Token ids of `s` as it appears in the middle of a text, after a space."""
         s = s.lstrip(" ")
-        if self.need_space_before_segment:
-            return self.encode(" " + s, bos=False, eos=False)
-        return self.encode(s, bos=False, eos=False)
+        return self._b.ids(" " + s if self.need_space_before_segment else s)
 
     def encode_wo_prefix_space(self, s: str) -> List[int]:
+        """Token ids of `s` as it appears glued to the preceding character (no space in between)."""
         if self.need_space_before_segment:
-            return self.encode(s, bos=False, eos=False)
-        # glue the text behind characters that tokenise on their own and strip them again
-        for prefix in ["@", "\n", "\\", "=", ">", "`"]:
-            head = self.encode(prefix, bos=False, eos=False)
-            both = self.encode(prefix + s, bos=False, eos=False)
-            if both[: len(head)] == head:
+            return self._b.ids(s)
+        for probe in _GLUE_PROBES:
+            head, both = self._b.ids(probe), self._b.ids(probe + s)
+            if both[:len(head)] == head:
                 return both[len(head):]
         raise NotImplementedError(f"every probe prefix merges into {s!r} during tokenisation")
 
-    def _probe_tokenizer_style(self) -> None:
-        # Llama-style tokenizers imply a leading space; others need it spelled out (reference :92-114)
-        s1 = self.encode("Hi my darling", bos=False, eos=False)
-        s2 = self.encode("my darling", bos=False, eos=False)
-        if s1[-len(s2):] == s2:
-            self.need_space_before_segment = False
-        else:
-            s3 = self.encode(" my darling", bos=False, eos=False)
-            assert s1[-len(s3):] == s3
-            self.need_space_before_segment = True
-
     def decode(self, t: List[int]) -> str:
-        return self.tokenizer.decode(t)
+        return self._b.text(t)
 
     def save(self, save_dir: str) -> None:
-        if self.tokenizer_type == "transformers":
-            self.tokenizer.save_pretrained(save_dir)
-        else:
-            with open(Path(save_dir) / "tokenizer.model", "wb") as f:
-                f.write(self.tokenizer.serialized_model_proto())
+        self._b.save(save_dir)
 
     @property
     def n_words(self) -> int:
-        return self.tokenizer.vocab_size() if self.tokenizer_type == "spm" else len(self.tokenizer)
+        return self._b.size()

@@ -19,6 +19,7 @@ names stubbed, and run its own classes / methods on CPU:
     model/accessory/model/meta.py              MetaModel.forward (pad trimming, shifted CE ignore_index 0),
                                                MetaModel.generate (force-feeding, stops, truncation),
                                                MetaModel.sample_top_p
+    model/accessory/model/tokenizer.py         Tokenizer (SentencePiece branch) on tests/golden/toy_spm.model
     model/accessory/util/lr_sched.py           adjust_learning_rate, adjust_learning_rate_epoch
     model/accessory/util/misc.py               add_weight_decay (function source executed on its own)
 
@@ -347,6 +348,20 @@ def main():
     out["wd_no_decay"] = sorted(ids[id(p_)] for p_ in groups[0]["params"])
     out["wd_decay"] = sorted(ids[id(p_)] for p_ in groups[1]["params"])
     assert groups[0]["weight_decay"] == 0.0 and groups[1]["weight_decay"] == 0.1
+
+    # ---- Tokenizer (model/tokenizer.py:15-131), the real class on a tiny committed SentencePiece model
+    # (tests/golden/toy_spm.model, trained offline on a few sentences; identity normalisation keeps it ~2 KB)
+    del sys.modules["accessory.model.tokenizer"]  # drop the inert stub used for meta.py: import the real module
+    TK = importlib.import_module("accessory.model.tokenizer")
+    rt = TK.Tokenizer(os.path.join(HERE, "toy_spm.model"))
+    texts = ["Hi my darling", "the robot opens the drawer", " leading space", "###", "\n###", "rotate the door ### Assistant:", ""]
+    out["tok_cases"] = {
+        "n_words": rt.n_words, "bos_id": rt.bos_id, "eos_id": rt.eos_id, "need_space_before_segment": rt.need_space_before_segment,
+        "encode": [(t, b, e, rt.encode(t, b, e)) for t in texts for b, e in ((True, False), (False, True), (False, False))],
+        "encode_segment": [(t, rt.encode_segment(t)) for t in texts if t],
+        "encode_wo_prefix_space": [(t, rt.encode_wo_prefix_space(t)) for t in texts if t.strip()],
+        "decode": [(ids, rt.decode(ids)) for ids in ([85, 7, 69, 32], rt.encode("the robot opens the drawer", False, False))],
+    }
 
     path = os.path.join(HERE, "reference_exec.pt")
     torch.save(out, path)

@@ -263,3 +263,29 @@ def test_cuda_vit_tower_matches_reference_glue(gold, cfg):
     vw = eng._vit_workspace(2, False)
     eng.vit_forward(gold["vit_image"].cuda(), vw)
     check("cuda ViT vs reference glue", vw["feats"].view(2, v.tokens, v.width), gold["vit_tokens_fp32"], rel=1e-2, ulps=6)
+
+
+def test_tokenizer_wrapper_matches_reference_tokenizer_class(gold, tmp_path):
+    """a3vlm_b200.model.Tokenizer against the reference's Tokenizer class run on the same tiny SentencePiece
+    model (tests/golden/toy_spm.model): ids with / without bos / eos, mid-text segments, glued segments (the
+    stop-sequence encodings generate() uses, meta.py:440-441), decode, vocabulary size, save."""
+    from a3vlm_b200.model.tokenizer import Tokenizer
+
+    c = gold["tok_cases"]
+    t = Tokenizer(os.path.join(ROOT, "tests", "golden", "toy_spm.model"))
+    assert (t.n_words, t.bos_id, t.eos_id, t.need_space_before_segment) == (
+        c["n_words"], c["bos_id"], c["eos_id"], c["need_space_before_segment"])
+    assert t.tokenizer_type == "spm"
+    for text, bos, eos, ids in c["encode"]:
+        assert t.encode(text, bos, eos) == ids, (text, bos, eos)
+    for text, ids in c["encode_segment"]:
+        assert t.encode_segment(text) == ids, text
+    for text, ids in c["encode_wo_prefix_space"]:
+        assert t.encode_wo_prefix_space(text) == ids, text
+    for ids, text in c["decode"]:
+        assert t.decode(ids) == text
+    with pytest.raises(TypeError):
+        t.encode(["not", "a", "string"], True, False)
+    t.save(str(tmp_path))
+    again = Tokenizer(str(tmp_path / "tokenizer.model"))
+    assert again.encode("the robot opens the drawer", True, True) == t.encode("the robot opens the drawer", True, True)
