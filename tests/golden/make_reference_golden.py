@@ -20,6 +20,7 @@ names stubbed, and run its own classes / methods on CPU:
                                                MetaModel.generate (force-feeding, stops, truncation),
                                                MetaModel.sample_top_p
     model/accessory/model/tokenizer.py         Tokenizer (SentencePiece branch) on tests/golden/toy_spm.model
+    model/accessory/data/transform.py          get_transform (padded_resize / resized_center_crop / random_resized_crop)
     model/accessory/util/lr_sched.py           adjust_learning_rate, adjust_learning_rate_epoch
     model/accessory/util/misc.py               add_weight_decay (function source executed on its own)
 
@@ -170,6 +171,16 @@ class TorchViT(nn.Module):
                 b.c_fc.bias.copy_(sd[r + "mlp.c_fc.bias"].float())
                 b.c_proj.weight.copy_(sd[r + "mlp.c_proj.weight"].float())
                 b.c_proj.bias.copy_(sd[r + "mlp.c_proj.bias"].float())
+
+
+def synthetic_image(w, h):
+    """Deterministic RGB test card (gradients + a checker), identical wherever it is rebuilt."""
+    import numpy as np
+    from PIL import Image
+
+    y, x = np.mgrid[0:h, 0:w]
+    rgb = np.stack([(x * 255) // max(w - 1, 1), (y * 255) // max(h - 1, 1), ((x // 4 + y // 4) % 2) * 200 + 20], axis=-1)
+    return Image.fromarray(rgb.astype(np.uint8), "RGB")
 
 
 def tiny_cfg():
@@ -362,6 +373,17 @@ def main():
         "encode_wo_prefix_space": [(t, rt.encode_wo_prefix_space(t)) for t in texts if t.strip()],
         "decode": [(ids, rt.decode(ids)) for ids in ([85, 7, 69, 32], rt.encode("the robot opens the drawer", False, False))],
     }
+
+    # ---- image pre-processing (data/transform.py:37-79) on synthetic PIL images
+    spec = importlib.util.spec_from_file_location("ref_transform", os.path.join(REF, "accessory", "data", "transform.py"))
+    TR = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(TR)
+    out["transform_cases"] = []
+    for (w_, h_) in ((50, 37), (31, 64), (40, 40)):
+        pil = synthetic_image(w_, h_)
+        for kind in ("padded_resize", "resized_center_crop", "random_resized_crop"):
+            torch.manual_seed(7)
+            out["transform_cases"].append((w_, h_, kind, 28, TR.get_transform(kind, 28)(pil)))
 
     path = os.path.join(HERE, "reference_exec.pt")
     torch.save(out, path)

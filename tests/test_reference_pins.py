@@ -289,3 +289,17 @@ def test_tokenizer_wrapper_matches_reference_tokenizer_class(gold, tmp_path):
     t.save(str(tmp_path))
     again = Tokenizer(str(tmp_path / "tokenizer.model"))
     assert again.encode("the robot opens the drawer", True, True) == t.encode("the robot opens the drawer", True, True)
+
+
+def test_image_transform_matches_reference_get_transform(gold):
+    """a3vlm_b200.data.get_transform against the reference's data/transform.py run on the same synthetic
+    images: bit-identical tensors for all three pipelines (the random crop under the same torch seed)."""
+    import make_reference_golden as G
+    from a3vlm_b200.data import get_transform
+
+    for w, h, kind, size, ref in gold["transform_cases"]:
+        torch.manual_seed(7)
+        got = get_transform(kind, size)(G.synthetic_image(w, h))
+        assert got.shape == (3, size, size) and torch.equal(got, ref), (w, h, kind)
+    with pytest.raises(ValueError):
+        get_transform("no_such_pipeline")
