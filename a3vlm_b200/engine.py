@@ -40,8 +40,8 @@ def build_layout(args, vis):
     Returns (decay, nodecay, frozen, kpad).  Trainable order = decay + nodecay:
       visual_proj.{0,1}.weight, start/end_img | tok_embeddings | per layer: wqkv, wo, w13, w2 | output ||
       per layer: attention_norm, ffn_norm | norm | visual_proj.{0,1}.bias
-    i.e. in the order the forward consumes them (the sharded optimiser broadcasts updated shards in that
-    order while the next forward is already running).  wq|wk|wv and w1|w3 are adjacent rows of one
+    i.e. in the order the forward consumes them (the pipelined / sharded optimiser updates and all-gathers
+    the chunks in that order while the next forward is already running).  wq|wk|wv and w1|w3 are adjacent rows of one
     matrix, so the reference-named parameters are views.  `||` = decay / no-decay boundary."""
     D, V = args.dim, args.vocab_size
     F = ffn_hidden_dim(D, args.multiple_of, args.ffn_dim_multiplier)
@@ -257,7 +257,7 @@ class Engine:
         self.comm_stream = None
         # sharded optimiser (ZeRO-1 style, enable_sharded_optimizer): this rank's slice of the decay region
         self.shard_group, self.shard_world, self.shard_rank = None, 1, 0
-        # weight ranges still being written on a side stream (shard broadcasts, or the pipelined AdamW), in
+        # weight ranges still being written on a side stream (pipelined AdamW chunks, all-gathered chunks), in
         # forward-consumption order: (lo, hi, event).  wait_weights(upto) makes the compute stream wait for
         # those that start below `upto`.
         self._pending: List[Tuple[int, int, "torch.cuda.Event"]] = []

@@ -240,10 +240,12 @@ class Transformer(nn.Module):
         return [n for n, _ in self.named_modules() if n.startswith("clip.") or n.startswith("visual_proj.")]
 
     def enable_data_parallel(self, group=None, shard_optimizer: bool = True) -> None:
-        """Replica data parallelism: gradients are all-reduced (sum, 1/world folded into the
-        loss gradient) bucket by bucket on a side stream while the backward is still running.
-        shard_optimizer: split the fp32 AdamW state over the ranks (ZeRO-1) and broadcast the updated
-        bf16 weights behind the next forward (Engine.enable_sharded_optimizer)."""
+        """Replica data parallelism: the gradients are exchanged bucket by bucket (one per decoder
+        layer) on a side stream while the backward is still running, 1/world folded into the loss gradient.
+        shard_optimizer (default): rank r owns the r-th 1/N of every chunk -- the exchange is a reduce-scatter,
+        the fp32 AdamW state exists for the owned slices only, and the updated bf16 weights are all-gathered
+        chunk by chunk behind the next forward (Engine.enable_sharded_optimizer).  False: plain all-reduce and a
+        replicated optimiser."""
         import torch.distributed as dist
 
         self.dp_group = group if group is not None else dist.group.WORLD

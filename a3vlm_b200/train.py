@@ -20,7 +20,7 @@ class AdamW(torch.optim.Optimizer):
                  pipelined: Optional[bool] = None):
         """pipelined=True: the update (norm, clip, AdamW) runs on a side stream, chunk by chunk in the order
         the forward consumes the weights, underneath the NEXT step's forward (Engine.overlap_optimizer;
-        single replica -- with data parallelism the sharded optimiser pipelines its broadcasts instead).
+        with data parallelism the sharded optimiser always runs this way and all-gathers each chunk after it).
         Same arithmetic, bit for bit.  The model's own entry points (forward, forward_inference,
         state_dict, parameters / named_parameters, load_state_dict, checkpoint save / load) wait for the
         chunks they touch; code that reads a parameter tensor it kept a handle to must call

@@ -69,7 +69,7 @@ def main():
         if not step_ok:
             print(f"rank{rank} step{step}: grad norm {norm.item():.5f} vs single-replica {rnorm.item():.5f}", flush=True)
         ok &= step_ok
-        # the next forward consumes the broadcast shards; state_dict() waits for all of them
+        # the next forward consumes the all-gathered chunks; state_dict() waits for all of them
     got, want = dp.llma.state_dict(), ref.llma.state_dict()
     worst, over = 0.0, []
     for k in want:
@@ -85,7 +85,7 @@ def main():
             over.append((k, round(bad, 4)))
         assert (gk - wk).abs().max().item() <= 2 * 1e-3 * 3 + 2 ** -6 * wk.abs().max().item(), k  # never beyond 2*lr*steps
         worst = max(worst, bad)
-        # replicas must be IDENTICAL across ranks after the shard broadcasts
+        # replicas must be IDENTICAL across ranks after the weight all-gathers
         other = got[k].clone()
         dist.broadcast(other, src=0)
         same = bool(torch.equal(other, got[k]))
