@@ -309,12 +309,16 @@ class MetaModel(nn.Module):
         """meta.py:487-566: batch-1 generator yielding {"text", "end_of_content"}."""
         dev = self._device()
         args = self.llma.args
-        if image is not None:
-            image = image.to(dev)
         prompt_tokens = self.tokenizer.encode(prompt, bos=True, eos=False)
         max_seq_len = args.max_seq_len
         if image is not None:
             max_seq_len -= self.llma.image_words
+            if image.dim() == 4:
+                assert image.shape[0] == 1
+            else:
+                assert image.dim() == 3
+                image = image.unsqueeze(0)
+            image = image.to(dev)
         max_prompt_size = max_seq_len - max_gen_len
         prompt_tokens = prompt_tokens[-max_prompt_size:]
         prompt_size = len(prompt_tokens)
@@ -363,41 +367,48 @@ class MetaModel(nn.Module):
     # ------------------------------------------------------------------ scoring API (meta.py:265-377)
     @torch.inference_mode()
     def compute_logits(self, examples: List[Union[str, List[int]]], images=None, bos=True, eos=False):
-        """meta.py:265-304: per-example (T_i, V) logits of a padded batch."""
-        if self.tokenizer is not None:
-            examples = [self.tokenizer.encode(x, bos, eos) if isinstance(x, str) else x for x in examples]
-        l_seq_len = [len(x) for x in examples]
-        assert max(l_seq_len) <= self.llma.args.max_seq_len
+        """meta.py:265-304: fp32 (T_i, V) logits per example of a right-padded (pad id 0) batch."""
+        if isinstance(examples, str):
+            raise ValueError(f"{self.__class__}.compute_logits expects a batched LIST of examples, but str is given")
+        if isinstance(examples[0], str):
+            examples = [self.tokenizer.encode(x, bos, eos) for x in examples]
         dev = self._device()
+        if images is not None:
+            images = images.to(dev)
+        l_seq_len = [len(x) for x in examples]
         token_tensor = torch.full((len(examples), max(l_seq_len)), 0, device=dev, dtype=torch.long)
         for i, item in enumerate(examples):
-            token_tensor[i, :len(item)] = torch.tensor(item, device=dev).long()
-        logits = self.llma.forward(token_tensor, images)
-        return [lg[:n] for lg, n in zip(logits, l_seq_len)]
+            token_tensor[i, :len(item)] = torch.tensor(item, dtype=torch.long)
+        output = self.llma(token_tensor, images)
+        logits = output[0] if isinstance(output, tuple) else output
+        return [lg[:n].float() for lg, n in zip(logits, l_seq_len)]
 
     @torch.inference_mode()
-    def evaluate_examples(self, examples, contexts=None, images=None):
-        """meta.py:306-377: per-example log-likelihood / perplexity of the non-context part."""
-        if contexts is not None:
-            assert len(contexts) == len(examples)
-        if self.tokenizer is not None:
-            examples = [self.tokenizer.encode(x, True, True) if isinstance(x, str) else x for x in examples]
+    def evaluate_examples(self, examples, contexts=None, images=None, bos=True, eos=False) -> Dict[str, List]:
+        """meta.py:306-377: per example, over the part after its context, the log-likelihood, the reference's
+        "ppl" (which is the MEAN token loss, not its exponential -- kept as is), whether greedy decoding would
+        reproduce it (`max_equal`), and the logits themselves (`non_context_logits`)."""
+        if isinstance(examples, str):
+            raise ValueError(f"{self.__class__}.evaluate_examples expects a batched LIST of examples, but str is given")
+        if isinstance(examples[0], str):
+            examples = [self.tokenizer.encode(x, bos, eos) for x in examples]
             if contexts is not None:
-                contexts = [self.tokenizer.encode(x, True, False) if isinstance(x, str) else x for x in contexts]
-        if contexts is not None:
-            for c, e in zip(contexts, examples):
-                assert c == e[:len(c)], "contexts should be prefixes of examples"
-        l_logits = self.compute_logits(examples, images)
-        result = {"logits": l_logits, "log_likelihood": [], "ppl": []}
-        for i, (item, logits) in enumerate(zip(examples, l_logits)):
-            logits = logits.float()[:-1]
-            labels = torch.tensor(item, device=logits.device).long()[1:]
-            if contexts is not None:
-                n_ctx = len(contexts[i]) - 1
-                logits, labels = logits[n_ctx:], labels[n_ctx:]
-            ll = -torch.nn.functional.cross_entropy(logits, labels, reduction="sum").item()
-            result["log_likelihood"].append(ll)
-            result["ppl"].append(float(torch.exp(torch.tensor(-ll / max(len(labels), 1)))))
+                contexts = [self.tokenizer.encode(x, bos, False) for x in contexts]
+        if contexts is not None:  # every example must start with its context
+            assert all(list(e[:len(c)]) == list(c) for e, c in zip(examples, contexts))
+        logits = self.compute_logits(examples, images)
+        loss_func = torch.nn.CrossEntropyLoss(reduction="none", ignore_index=0)
+        result: Dict[str, List] = {"log_likelihood": [], "ppl": [], "max_equal": [], "non_context_logits": []}
+        for idx, item_logits in enumerate(logits):
+            start = 0 if contexts is None else len(contexts[idx]) - 1
+            assert start >= 0
+            item_logits = item_logits[start:-1]
+            labels = torch.tensor(list(examples[idx][start + 1:]), dtype=torch.long, device=item_logits.device)
+            loss = loss_func(item_logits, labels)
+            result["log_likelihood"].append(-loss.sum().item())
+            result["ppl"].append(loss.mean().item())
+            result["max_equal"].append((item_logits.argmax(dim=-1) == labels).all().item())
+            result["non_context_logits"].append(item_logits)
         return result
 
     def get_image_words(self):

@@ -18,7 +18,8 @@ names stubbed, and run its own classes / methods on CPU:
     model/accessory/model/LLM/llama_ens5_2images.py  forward_inference with image + depth_images (RGB-D splice)
     model/accessory/model/meta.py              MetaModel.forward (pad trimming, shifted CE ignore_index 0),
                                                MetaModel.generate (force-feeding, stops, truncation),
-                                               MetaModel.sample_top_p
+                                               MetaModel.sample_top_p, compute_logits, evaluate_examples,
+                                               stream_generate
     model/accessory/model/tokenizer.py         Tokenizer (SentencePiece branch) on tests/golden/toy_spm.model
     model/accessory/data/transform.py          get_transform (padded_resize / resized_center_crop / random_resized_crop)
     model/accessory/util/lr_sched.py           adjust_learning_rate, adjust_learning_rate_epoch
@@ -320,6 +321,21 @@ def main():
             gens.append(dict(c, generated=[[int(t) for t in r.split()] for r in res], margins=torch.stack(margins)))
         meta.llma.forward_inference = inner
         out["generate_cases"] = gens
+        # ---- scoring API (meta.py:265-377): compute_logits / evaluate_examples on token lists and on text
+        exs = [[1, 17, 33, 49, 80, 81], [1, 100, 101, 102], [1, 9, 10, 11, 12, 13, 14, 15]]
+        ctx = [[1, 17, 33], [1], [1, 9, 10, 11, 12]]
+        cl = meta.compute_logits(exs)
+        ev_all = meta.evaluate_examples(exs)
+        ev_ctx = meta.evaluate_examples(exs, ctx)
+        ev_txt = meta.evaluate_examples(["17 33 49", "100 101"], ["17", "100"], None, True, True)
+        strip = lambda r: {k: ([t.clone() for t in v_] if k == "non_context_logits" else list(v_)) for k, v_ in r.items()}
+        out["score_cases"] = dict(examples=exs, contexts=ctx, compute_logits=[t.clone() for t in cl], all=strip(ev_all),
+                                  ctx=strip(ev_ctx), txt=strip(ev_txt))
+        # ---- stream_generate (meta.py:487-566): greedy, a stop symbol that cuts the text, and a length-bound run
+        out["stream_cases"] = []
+        for prompt, max_gen, stops_ in (("17 33 49", 6, ()), ("100 101 102 103 104", 8, ("483 483",)), ("5 6", 5, ("999",))):
+            chunks = list(meta.stream_generate(prompt, None, max_gen, 0.0, 0.95, stops_))
+            out["stream_cases"].append(dict(prompt=prompt, max_gen_len=max_gen, stops=stops_, chunks=chunks))
     finally:
         torch.Tensor.cuda = cuda
 

@@ -303,3 +303,90 @@ def test_image_transform_matches_reference_get_transform(gold):
         assert got.shape == (3, size, size) and torch.equal(got, ref), (w, h, kind)
     with pytest.raises(ValueError):
         get_transform("no_such_pipeline")
+
+
+class _OracleLLM(torch.nn.Module):
+    """CPU stand-in for the inner model behind our MetaModel's host-side methods: the fp32 oracle."""
+
+    def __init__(self, orc):
+        super().__init__()
+        self.orc, self.args, self.image_words = orc, orc.args, 0
+        self.w = torch.nn.Parameter(torch.zeros(1))
+
+    def forward(self, tokens, image=None):
+        return self.orc.forward(tokens, image)
+
+    def forward_inference(self, tokens, start_pos, image=None):
+        return self.orc.forward_inference(tokens, start_pos, image)
+
+
+def test_scoring_api_matches_reference_compute_logits_and_evaluate_examples(gold, cfg):
+    """OUR MetaModel.compute_logits / evaluate_examples (host logic; the oracle supplies the logits) against the
+    reference's methods executed on its own decoder: same keys, context handling, "ppl" = mean token loss,
+    `max_equal`, text inputs tokenised with (bos, eos) for examples and (bos, False) for contexts."""
+    import a3vlm_oracle as O
+    import make_reference_golden as G
+    from a3vlm_b200.model.meta import MetaModel
+
+    a, _, sd = cfg
+    m = MetaModel.__new__(MetaModel)
+    torch.nn.Module.__init__(m)
+    m.llma = _OracleLLM(O.OracleTransformer(a, None, sd, act_dtype=torch.float32))
+    m.tokenizer = G.ToyTokenizer()
+    c = gold["score_cases"]
+    got = m.compute_logits(c["examples"])
+    assert [tuple(t.shape) for t in got] == [tuple(t.shape) for t in c["compute_logits"]]
+    for g_, r_ in zip(got, c["compute_logits"]):
+        assert g_.dtype == torch.float32
+        close(g_, r_, 2e-4)
+    runs = {"all": m.evaluate_examples(c["examples"]), "ctx": m.evaluate_examples(c["examples"], c["contexts"]),
+            "txt": m.evaluate_examples(["17 33 49", "100 101"], ["17", "100"], None, True, True)}
+    for name, res in runs.items():
+        ref = c[name]
+        assert set(res) == set(ref) == {"log_likelihood", "ppl", "max_equal", "non_context_logits"}
+        assert res["max_equal"] == ref["max_equal"]
+        for k in ("log_likelihood", "ppl"):
+            assert len(res[k]) == len(ref[k])
+            for x, y in zip(res[k], ref[k]):
+                assert abs(x - y) <= 1e-4 * max(1.0, abs(y)), (name, k, x, y)
+        for x, y in zip(res["non_context_logits"], ref["non_context_logits"]):
+            close(x, y, 2e-4)
+    with pytest.raises(AssertionError):
+        m.evaluate_examples([[1, 2, 3]], [[1, 5]])  # a context must be a prefix of its example
+    with pytest.raises(ValueError):
+        m.compute_logits("a single string")
+
+
+def test_stream_generate_matches_reference_stream_generate(gold, cfg):
+    """OUR MetaModel.stream_generate (host loop; the fp32 oracle supplies the logits and torch.argmax stands in
+    for the argmax kernel) yields the same chunk sequence as the reference's generator: plain greedy run, a stop
+    symbol that truncates the text and ends the stream, a run bounded by max_gen_len."""
+    import a3vlm_oracle as O
+    import make_reference_golden as G
+    from a3vlm_b200.model.meta import MetaModel
+
+    a, _, sd = cfg
+    m = MetaModel.__new__(MetaModel)
+    torch.nn.Module.__init__(m)
+    m.llma = _OracleLLM(O.OracleTransformer(a, None, sd, act_dtype=torch.float32))
+    m.tokenizer = G.ToyTokenizer()
+    m._argmax = lambda logits: torch.argmax(logits, dim=-1)
+    for c in gold["stream_cases"]:
+        got = list(m.stream_generate(c["prompt"], None, c["max_gen_len"], 0.0, 0.95, c["stops"]))
+        assert got == c["chunks"], (c["prompt"], got, c["chunks"])
+
+
+def test_metamodel_forward_host_path_matches_reference_loss(gold, cfg):
+    """OUR MetaModel.forward on its un-fused path (an inner model without `loss_forward`: trim trailing pad columns,
+    shift, CrossEntropyLoss(ignore_index=0)) against the reference's MetaModel.forward run on its own decoder."""
+    import a3vlm_oracle as O
+    from a3vlm_b200.model.meta import MetaModel
+
+    a, _, sd = cfg
+    m = MetaModel.__new__(MetaModel)
+    torch.nn.Module.__init__(m)
+    m.llma = _OracleLLM(O.OracleTransformer(a, None, sd, act_dtype=torch.float32))
+    m.criterion = torch.nn.CrossEntropyLoss(ignore_index=0)
+    loss, extra = m(gold["loss_examples"], gold["loss_labels"])
+    assert extra == {}
+    close(loss, gold["loss_fp32"], 1e-5, 1e-5)
