@@ -53,7 +53,12 @@ class NativeScalerWithGradNormCount:
     def __init__(self, args=None):
         pass
 
-    def __call__(self, loss, optimizer, model, parameters=None, clip_grad=None, update_grad=True):
+    def __call__(self, loss, optimizer, model, clip_grad=None, parameters=None, create_graph=False, update_grad=True):
+        """Same positional order as the reference (misc.py:302).  `clip_grad=None` disables clipping (the
+        reference clips at 1e8) but the pre-clip norm is still returned; `parameters` is accepted and unused,
+        as there."""
+        if create_graph:
+            raise NotImplementedError("second-order gradients are not built (the fine-tune loop never asks for them)")
         llma = getattr(model, "llma", model)
         if update_grad:
             loss.backward()
