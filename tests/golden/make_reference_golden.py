@@ -321,6 +321,19 @@ def main():
             gens.append(dict(c, generated=[[int(t) for t in r.split()] for r in res], margins=torch.stack(margins)))
         meta.llma.forward_inference = inner
         out["generate_cases"] = gens
+        # ---- generate with images (budget max_seq_len - image_words, image only in the prefill) and with
+        # sampling (temperature 0.8, top-p 0.9) under a fixed torch seed
+        meta_img = M.MetaModel.__new__(M.MetaModel)
+        nn.Module.__init__(meta_img)
+        meta_img.llma, meta_img.tokenizer = ref, ToyTokenizer()   # `ref`: the decoder with the patched encode_image above
+        res = meta_img.generate(["17 33 49", "100 101 102 103 104 105 106"], fake_image, None, 20, 0.0, 0.95, [])
+        out["generate_image_case"] = dict(prompts=["17 33 49", "100 101 102 103 104 105 106"], max_gen_len=20,
+                                          generated=[[int(t) for t in r.split()] for r in res])
+        torch.manual_seed(4321)
+        res = meta.generate(["17 33 49", "100 101 102 103 104"], None, None, 10, 0.8, 0.9, [])
+        out["generate_sampled_case"] = dict(prompts=["17 33 49", "100 101 102 103 104"], max_gen_len=10, temperature=0.8,
+                                            top_p=0.9, seed=4321, generated=[[int(t) for t in r.split()] for r in res])
+
         # ---- scoring API (meta.py:265-377): compute_logits / evaluate_examples on token lists and on text
         exs = [[1, 17, 33, 49, 80, 81], [1, 100, 101, 102], [1, 9, 10, 11, 12, 13, 14, 15]]
         ctx = [[1, 17, 33], [1], [1, 9, 10, 11, 12]]

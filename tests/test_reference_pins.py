@@ -390,3 +390,28 @@ def test_metamodel_forward_host_path_matches_reference_loss(gold, cfg):
     loss, extra = m(gold["loss_examples"], gold["loss_labels"])
     assert extra == {}
     close(loss, gold["loss_fp32"], 1e-5, 1e-5)
+
+
+def test_generate_with_images_and_with_sampling_match_reference(gold, cfg):
+    """(1) With images the reference shrinks the budget by image_words (meta.py:423-425) and feeds the image to
+    the prefill only; (2) with temperature > 0 the reference's loop draws through sample_top_p -- under the same
+    torch seed the oracle's loop consumes the generator identically, so the ids are equal."""
+    import a3vlm_oracle as O
+
+    a, _, sd = cfg
+    v5 = O.VisionArgs(image_size=28, patch=14, width=128, layers=2, heads=2, mlp=256, views=5)
+    orc = O.OracleTransformer(a, v5, sd, act_dtype=torch.float32)
+    views = gold["img_views"]
+    orc.encode_image = lambda image: torch.cat(list(views), dim=0)
+    c = gold["generate_image_case"]
+    prompts = [[1] + [int(x) for x in p.split()] for p in c["prompts"]]
+    out, toks, _ = O.generate_tokens(orc, prompts, images=torch.zeros(2, 3, 4, 4), max_gen_len=c["max_gen_len"], eos_id=2)
+    assert out == c["generated"]
+    assert toks.shape[1] == min(a.max_seq_len - 35, c["max_gen_len"] + 8)  # the budget the reference applied
+
+    txt = O.OracleTransformer(a, None, sd, act_dtype=torch.float32)
+    c = gold["generate_sampled_case"]
+    prompts = [[1] + [int(x) for x in p.split()] for p in c["prompts"]]
+    torch.manual_seed(c["seed"])
+    out, _, _ = O.generate_tokens(txt, prompts, max_gen_len=c["max_gen_len"], temperature=c["temperature"], top_p=c["top_p"], eos_id=2)
+    assert out == c["generated"]
