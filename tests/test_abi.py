@@ -63,3 +63,32 @@ def test_sass_is_blackwell_native():
     sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "UTCHMMA" in sass and "LDTM" in sass and "UTMALDG" in sass and "UTMAREDG" in sass
     assert " HMMA" not in sass
+
+
+def test_product_code_never_imports_the_oracle_or_a_cpu_fallback():
+    """The oracle is test infrastructure: nothing under a3vlm_b200/ may import, load or execute it (only tests/,
+    __graft_entry__.smoke() and bench.py's CPU-baseline / reference arm do), and no product module may import the
+    reference tree."""
+    import ast
+    import os
+
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "a3vlm_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(root):
+        for fn in files:
+            if not fn.endswith(".py"):
+                continue
+            path = os.path.join(dirpath, fn)
+            tree = ast.parse(open(path).read())
+            for node in ast.walk(tree):
+                names = []
+                if isinstance(node, ast.Import):
+                    names = [a.name for a in node.names]
+                elif isinstance(node, ast.ImportFrom):
+                    names = [node.module or ""]
+                elif isinstance(node, ast.Constant) and isinstance(node.value, str) and node.value.startswith("/root/reference"):
+                    names = [node.value]
+                for n in names:
+                    if "oracle" in n or n.startswith("accessory") or n.startswith("/root/reference"):
+                        offenders.append((os.path.relpath(path, root), n))
+    assert not offenders, offenders
