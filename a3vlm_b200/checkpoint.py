@@ -222,6 +222,27 @@ def load_into(targets: Dict[str, torch.Tensor], path_list: Union[str, Sequence[s
     return {"missing_keys": sorted(missing), "unexpected_keys": sorted(unexpected)}
 
 
+def check_vision_branch(path_list: Union[str, Sequence[str]], vit_width: int) -> None:
+    """A released reference checkpoint (`llama_ens5` / `llama_ens5_2images`) carries the four-encoder ensemble:
+    `qformer_proj.*`, ConvNeXt / DINOv2 towers and a 5632-wide `visual_proj.0.weight` (LLM/llama_ens5.py:303-333).
+    The llama_b200 plugins build the CLIP ViT-L/14 branch only, so such a checkpoint cannot be
+    mapped onto them: say so, instead of failing later with a generic shape mismatch."""
+    if isinstance(path_list, str):
+        path_list = [path_list]
+    for path in path_list:
+        fmt, mp = infer_checkpoint_format_and_mp_size(path)
+        shard = load_tensor_parallel_shard_state_dict(path, fmt, 0, mp)
+        bad = [k for k in shard if "qformer" in k or ".openclip_convnext_xxl." in k or ".dinov2_vitg14." in k]
+        vp = next((v for k, v in shard.items() if k.endswith("visual_proj.0.weight")), None)
+        if vp is not None and vp.dim() == 2 and vp.shape[1] != vit_width:
+            bad.append(f"visual_proj.0.weight of width {vp.shape[1]} (this build: {vit_width})")
+        if bad:
+            raise NotImplementedError(
+                f"{path}: checkpoint of the reference's four-encoder vision ensemble ({bad[0]}, {len(bad)} such entries); "
+                "llama_b200 implements the CLIP ViT-L/14 + visual_proj + Llama path only -- the ConvNeXt-XXL / DINOv2 / "
+                "Q-Former branches are out of scope (DESIGN.md section 7)")
+
+
 def _inner(model):
     return getattr(model, "llma", model)
 

@@ -436,13 +436,8 @@ extern "C" int a3_attn_bwd(const void* q, const void* k, const void* v, const vo
                                (uint64_t)width * 4, (uint64_t)T * width * 4, BW_HD, BW_Q, 1);
   if (rc) return rc;
 
-  static bool configured = false;
-  if (!configured) {
-    e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             BwdSmem::TOTAL);
-    if (e != cudaSuccess) return set_error(A3_ERR_CUDA, cudaGetErrorString(e));
-    configured = true;
-  }
+  rc = ensure_dyn_smem(reinterpret_cast<const void*>(&attn_bwd_kernel), BwdSmem::TOTAL);
+  if (rc) return rc;
   BwdParams p;
   p.lse = lse;
   p.delta = delta;

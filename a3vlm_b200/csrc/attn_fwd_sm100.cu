@@ -261,13 +261,7 @@ template <int HD>
 static int launch_attn_fwd(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                            const AttnParams& p, cudaStream_t stream) {
   using S = AttnSmem<HD>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<HD>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
-    if (e != cudaSuccess) return set_error(A3_ERR_CUDA, cudaGetErrorString(e));
-    configured = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&attn_fwd_kernel<HD>), S::TOTAL)) return rc;
   dim3 grid((p.Tq + ATT_BM - 1) / ATT_BM, p.H, p.B);
   attn_fwd_kernel<HD><<<grid, 128, S::TOTAL, stream>>>(tmQ, tmK, tmV, p);
   return check_launch("a3_attn_fwd");

@@ -5,7 +5,9 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <utility>
 
 namespace a3 {
 
@@ -27,6 +29,21 @@ int check_launch(const char* what) {
   return A3_OK;
 }
 
+int ensure_dyn_smem(const void* kernel, size_t bytes) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return set_error(A3_ERR_CUDA, "cudaGetDevice failed");
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> done;
+  std::lock_guard<std::mutex> lk(mu);
+  size_t& cur = done[std::make_pair(kernel, dev)];
+  if (bytes <= cur) return A3_OK;
+  const size_t want = bytes > 48 * 1024 ? bytes : 48 * 1024;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
+  if (e != cudaSuccess) return set_error(A3_ERR_CUDA, cudaGetErrorString(e));
+  cur = want;
+  return A3_OK;
+}
+
 static std::atomic<int> g_sm_limit{0};
 
 int num_sms() {
@@ -36,15 +53,15 @@ int num_sms() {
 }
 
 int device_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 148;
-    n = prop.multiProcessorCount;
+  static std::atomic<int> n[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int v = n[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
+    n[dev].store(v, std::memory_order_relaxed);
   }
-  return n;
+  return v;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,

@@ -11,6 +11,9 @@ namespace a3 {
 
 int set_error(int code, const char* msg);
 int check_launch(const char* what);
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per DEVICE: remembered per (kernel, current device),
+// so a process that drives several GPUs configures each of them (raised only, never lowered).
+int ensure_dyn_smem(const void* kernel, size_t bytes);
 int num_sms();     // SMs the persistent kernels size their grids for (a3_set_sm_limit)
 int device_sms();  // physical SM count
 

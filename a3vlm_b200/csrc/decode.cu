@@ -497,13 +497,7 @@ extern "C" int a3_linear_small_m(const void* X, const void* W, void* Y, int M, i
 template <int M>
 static int launch_decode_linear(const DecLinParams& p, cudaStream_t s) {
   const size_t smem = (size_t)M * p.K * 2;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(decode_linear_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(smem > 48 * 1024 ? smem : 48 * 1024));
-    if (e != cudaSuccess) return set_error(A3_ERR_CUDA, cudaGetErrorString(e));
-    configured = smem;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&decode_linear_kernel<M>), smem)) return rc;
   const int cols_per_block = LIN_WARPS * LIN_COLS_PER_WARP;
   int grid = (p.N + cols_per_block - 1) / cols_per_block;
   const int slots = num_sms() * 2;  // persistent: one resident wave (2 CTAs per SM), X staged once per CTA

@@ -209,13 +209,7 @@ template <int NB>
 static int launch_decode_gemm(const CUtensorMap& tmW, const CUtensorMap& tmX, const DgParams& p,
                               cudaStream_t stream) {
   using S = DgSmem<NB>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(decode_gemm_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         S::TOTAL);
-    if (e != cudaSuccess) return set_error(A3_ERR_CUDA, cudaGetErrorString(e));
-    configured = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&decode_gemm_kernel<NB>), S::TOTAL)) return rc;
   const int n_blocks = (p.N + DG_BM - 1) / DG_BM;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(n_blocks * p.splits);

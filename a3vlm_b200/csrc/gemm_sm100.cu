@@ -654,13 +654,7 @@ template <int BN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
                        cudaStream_t stream) {
   using S = GemmSmem<BN>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
-    if (e != cudaSuccess) return set_error(A3_ERR_CUDA, cudaGetErrorString(e));
-    configured = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&gemm_bf16_kernel<BN>), S::TOTAL)) return rc;
   const int m_blocks = (p.M + BM - 1) / BM, n_blocks = (p.N + BN - 1) / BN;
   const int tiles = m_blocks * n_blocks;
   const int grid = tiles < num_sms() ? tiles : num_sms();
@@ -671,13 +665,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
 static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
                         cudaStream_t stream) {
   using S = Gemm2Smem;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         S::TOTAL);
-    if (e != cudaSuccess) return set_error(A3_ERR_CUDA, cudaGetErrorString(e));
-    configured = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&gemm2_bf16_kernel), S::TOTAL)) return rc;
   const int m_blocks = (p.M + 2 * BM - 1) / (2 * BM);
   const int n_blocks = p.swiglu_F ? p.swiglu_F / S::BNH : (p.N + S::BN - 1) / S::BN;
   const int tiles = m_blocks * n_blocks;

@@ -373,13 +373,14 @@ argmax_kernel(const float* __restrict__ logits, long long ld, int V, long long* 
 
 // ------------------------------------------------------------------ optimiser
 constexpr int SUMSQ_BLOCKS = 1184;  // 148 SMs x 8
-__device__ float g_sumsq_partial[SUMSQ_BLOCKS];
-__device__ unsigned int g_sumsq_done = 0;
 
 // out[0] += sum(g^2).  Fixed grid, partials combined by the last CTA in index order -> the result
-// is deterministic (no float atomics).
+// is deterministic (no float atomics).  The partials and the arrival counter live in CALLER-OWNED
+// scratch (A3_SUMSQ_SCRATCH_BYTES, zeroed once; the counter resets itself), so launches in flight on
+// different streams never share state as long as each stream has its own scratch.
 __global__ void __launch_bounds__(256)
-sumsq_kernel(const __nv_bfloat16* __restrict__ g, long long n, float* __restrict__ out) {
+sumsq_kernel(const __nv_bfloat16* __restrict__ g, long long n, float* __restrict__ out,
+             float* __restrict__ g_sumsq_partial, unsigned int* __restrict__ done_ctr) {
   __shared__ float red[32];
   __shared__ bool last;
   float s = 0.f;
@@ -400,7 +401,7 @@ sumsq_kernel(const __nv_bfloat16* __restrict__ g, long long n, float* __restrict
   if (threadIdx.x == 0) {
     g_sumsq_partial[blockIdx.x] = s;
     __threadfence();
-    const unsigned int t = atomicAdd(&g_sumsq_done, 1u);
+    const unsigned int t = atomicAdd(done_ctr, 1u);
     last = (t == gridDim.x - 1);
   }
   __syncthreads();
@@ -412,7 +413,7 @@ sumsq_kernel(const __nv_bfloat16* __restrict__ g, long long n, float* __restrict
     t = block_sum_m(t, red);
     if (threadIdx.x == 0) {
       out[0] += t;
-      g_sumsq_done = 0;
+      *done_ctr = 0;
     }
   }
 }
@@ -610,13 +611,18 @@ extern "C" int a3_argmax(const float* logits, long long ld, int B, int V, long l
   return check_launch("a3_argmax");
 }
 
-extern "C" int a3_sumsq_bf16(const void* g, long long n, float* out, void* stream) {
+extern "C" int a3_sumsq_bf16(const void* g, long long n, float* out, void* scratch, void* stream) {
+  static_assert((SUMSQ_BLOCKS + 1) * 4 <= A3_SUMSQ_SCRATCH_BYTES, "scratch too small");
   if (n <= 0) return A3_OK;
   if (reinterpret_cast<uintptr_t>(g) & 15) return set_error(A3_ERR_ARG, "a3_sumsq_bf16: 16-byte alignment");
+  if (!scratch || (reinterpret_cast<uintptr_t>(scratch) & 3))
+    return set_error(A3_ERR_ARG, "a3_sumsq_bf16: scratch (A3_SUMSQ_SCRATCH_BYTES, zero-initialised) required");
   long long blocks = ((n >> 3) + 255) / 256;
   if (blocks > SUMSQ_BLOCKS) blocks = SUMSQ_BLOCKS;
   if (blocks < 1) blocks = 1;
-  sumsq_kernel<<<(int)blocks, 256, 0, ST(stream)>>>(BF(g), n, out);
+  float* part = reinterpret_cast<float*>(scratch);
+  sumsq_kernel<<<(int)blocks, 256, 0, ST(stream)>>>(BF(g), n, out, part,
+                                                     reinterpret_cast<unsigned int*>(part + SUMSQ_BLOCKS));
   return check_launch("a3_sumsq_bf16");
 }
 

@@ -53,11 +53,15 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
 __global__ void __launch_bounds__(ROW_THREADS)
 rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                    __nv_bfloat16* __restrict__ y, float* __restrict__ rstd_out, int D,
-                   long long ldx, long long ldy, float eps) {
+                   long long ldx, long long ldy, float eps, int group_rows, long long group_stride) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // a PDL successor may start prefetching weights
   __shared__ float red[32];
   const int row = blockIdx.x;
-  const __nv_bfloat16* xr = x + row * ldx;
+  // grouped input rows (the text rows of every sample of a [B][L][D] stream): row r of the output is row
+  // r % group_rows of group r / group_rows
+  const __nv_bfloat16* xr = group_rows > 0
+                                ? x + (row / group_rows) * group_stride + (row % group_rows) * ldx
+                                : x + row * ldx;
   const int nchunks = D >> 3;
   float xv[MAX_CHUNKS][8];
   float ss = 0.f;
@@ -109,31 +113,37 @@ __global__ void __launch_bounds__(ROW_THREADS, NCH <= 2 ? 2 : 1)
 rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                    const __nv_bfloat16* __restrict__ w, const float* __restrict__ rstd_in,
                    __nv_bfloat16* __restrict__ dx, float* __restrict__ dw_partial, int rows, int D,
-                   int add_to_dx) {
+                   int add_to_dx, int group_rows, long long group_stride) {
   __shared__ float red[32];
   const int nchunks = D >> 3;
   float dw[NCH][8];
   uint4 xp[NCH], gp[NCH];
+  // x / dx rows may be grouped (see rmsnorm_fwd_kernel); dy and rstd are dense [rows][D]
+  auto xoff = [&](int r) -> long long {
+    return group_rows > 0 ? (long long)(r / group_rows) * group_stride + (long long)(r % group_rows) * D
+                          : (long long)r * D;
+  };
 #pragma unroll
   for (int i = 0; i < NCH; ++i) {
     const int c = threadIdx.x + i * ROW_THREADS;
 #pragma unroll
     for (int j = 0; j < 8; ++j) dw[i][j] = 0.f;
     if (c < nchunks && (int)blockIdx.x < rows) {
-      xp[i] = *reinterpret_cast<const uint4*>(x + (long long)blockIdx.x * D + c * 8);
+      xp[i] = *reinterpret_cast<const uint4*>(x + xoff(blockIdx.x) + c * 8);
       gp[i] = *reinterpret_cast<const uint4*>(dy + (long long)blockIdx.x * D + c * 8);
     }
   }
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
     const int nrow = row + gridDim.x;
-    __nv_bfloat16* dr = dx + (long long)row * D;
+    __nv_bfloat16* dr = dx + xoff(row);
+    const long long nxo = nrow < rows ? xoff(nrow) : 0;
     uint4 xn[NCH], gn[NCH], pv[NCH];
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
       const int c = threadIdx.x + i * ROW_THREADS;
       if (c < nchunks) {
         if (nrow < rows) {
-          xn[i] = *reinterpret_cast<const uint4*>(x + (long long)nrow * D + c * 8);
+          xn[i] = *reinterpret_cast<const uint4*>(x + nxo + c * 8);
           gn[i] = *reinterpret_cast<const uint4*>(dy + (long long)nrow * D + c * 8);
         }
         if (add_to_dx) pv[i] = *reinterpret_cast<const uint4*>(dr + c * 8);
@@ -457,29 +467,33 @@ static int check_rowshape(const char* what, int rows, int D) {
 }
 
 extern "C" int a3_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int rows, int D,
-                              long long ldx, long long ldy, float eps, void* stream) {
+                              long long ldx, long long ldy, float eps, int group_rows,
+                              long long group_stride, void* stream) {
   if (check_rowshape("a3_rmsnorm_fwd: D must be a multiple of 8 and <= 8192", rows, D)) return A3_ERR_ARG;
   if (rows == 0) return A3_OK;
-  if ((ldx & 7) || (ldy & 7)) return set_error(A3_ERR_ARG, "a3_rmsnorm_fwd: ld % 8 != 0");
-  rmsnorm_fwd_kernel<<<rows, ROW_THREADS, 0, ST(stream)>>>(BF(x), BF(w), BFM(y), rstd, D, ldx, ldy, eps);
+  if ((ldx & 7) || (ldy & 7) || (group_stride & 7) || group_rows < 0)
+    return set_error(A3_ERR_ARG, "a3_rmsnorm_fwd: ld % 8 != 0");
+  rmsnorm_fwd_kernel<<<rows, ROW_THREADS, 0, ST(stream)>>>(BF(x), BF(w), BFM(y), rstd, D, ldx, ldy, eps,
+                                                           group_rows, group_stride);
   return check_launch("a3_rmsnorm_fwd");
 }
 
 extern "C" int a3_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd,
                               void* dx, float* dw_partial, int nparts, int rows, int D,
-                              int add_to_dx, void* stream) {
+                              int add_to_dx, int group_rows, long long group_stride, void* stream) {
   if (check_rowshape("a3_rmsnorm_bwd: D must be a multiple of 8 and <= 8192", rows, D)) return A3_ERR_ARG;
   if (nparts <= 0) return set_error(A3_ERR_ARG, "a3_rmsnorm_bwd: nparts <= 0");
+  if ((group_stride & 7) || group_rows < 0) return set_error(A3_ERR_ARG, "a3_rmsnorm_bwd: group_stride % 8 != 0");
   const int nch = (D / 8 + ROW_THREADS - 1) / ROW_THREADS;
   if (nch <= 1)
     rmsnorm_bwd_kernel<1><<<nparts, ROW_THREADS, 0, ST(stream)>>>(BF(dy), BF(x), BF(w), rstd, BFM(dx),
-                                                                  dw_partial, rows, D, add_to_dx);
+                                                                  dw_partial, rows, D, add_to_dx, group_rows, group_stride);
   else if (nch == 2)
     rmsnorm_bwd_kernel<2><<<nparts, ROW_THREADS, 0, ST(stream)>>>(BF(dy), BF(x), BF(w), rstd, BFM(dx),
-                                                                  dw_partial, rows, D, add_to_dx);
+                                                                  dw_partial, rows, D, add_to_dx, group_rows, group_stride);
   else
     rmsnorm_bwd_kernel<4><<<nparts, ROW_THREADS, 0, ST(stream)>>>(BF(dy), BF(x), BF(w), rstd, BFM(dx),
-                                                                  dw_partial, rows, D, add_to_dx);
+                                                                  dw_partial, rows, D, add_to_dx, group_rows, group_stride);
   return check_launch("a3_rmsnorm_bwd");
 }
 

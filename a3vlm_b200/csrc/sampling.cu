@@ -276,13 +276,8 @@ extern "C" int a3_sample_top_p(const float* logits, long long ld, int B, int V, 
   if (V <= 0 || !(temperature > 0.f)) return set_error(A3_ERR_ARG, "a3_sample_top_p: V > 0 and temperature > 0");
   const size_t smem = (size_t)V * sizeof(float);
   if (smem > 200 * 1024) return set_error(A3_ERR_UNSUPPORTED, "a3_sample_top_p: V > 51200 (row must fit shared memory)");
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(sample_top_p_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(sample_top_p_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
-      return set_error(A3_ERR_CUDA, "a3_sample_top_p: cannot reserve shared memory");
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&sample_top_p_kernel<true>), 200 * 1024)) return rc;
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&sample_top_p_kernel<false>), 200 * 1024)) return rc;
   if (V <= SAMPLE_THREADS * SAMPLE_ITEMS)
     sample_top_p_kernel<true><<<B, SAMPLE_THREADS, smem, ST(stream)>>>(logits, ld, V, temperature, top_p, u, out);
   else

@@ -97,3 +97,82 @@ class BucketReduceScatter:
         for h in self.handles:
             h.wait()
         self.handles = []
+
+
+def self_check(group=None, steps: int = 3) -> dict:
+    """Correctness of the data-parallel fine-tune step on the live process group (bench.py prints the result
+    at N > 1 so the multi-GPU path carries evidence wherever it is timed): a tiny model takes `steps` sharded
+    DP steps (reduce-scatter of the gradients, owned-slice AdamW, all-gather of the weights; the last step
+    accumulates two micro-batches, the first inside no_sync()) next to a single replica that accumulates the
+    SAME per-rank batches locally.  Returns {"ok", "worst_mismatch", "grad_norm_rel_err", "replicas_identical",
+    "world"}.  `worst_mismatch` = largest fraction of elements of any parameter that ends further than bf16
+    resolution from the single-replica run (Adam's sign-like first steps flip where a gradient is rounding
+    noise: the two runs sum the ranks' bf16 gradients in different places); a lost update or exchange is ~1.0."""
+    from .model import MetaModel
+    from .train import AdamW, NativeScalerWithGradNormCount
+
+    group = group if group is not None else dist.group.WORLD
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    cfg = dict(dim=256, n_layers=3, n_heads=2, vocab_size=512, multiple_of=128, image_size=28, vit_width=128,
+               vit_layers=2, vit_heads=2, vit_mlp=256)
+
+    def build():
+        m = MetaModel("llama_b200", cfg, None, with_visual=True, max_seq_len=64, max_batch_size=4)
+        m.llma.reset_parameters(seed=31)
+        with torch.no_grad():  # sharper logits: gradients well above rounding noise
+            m.llma.engine.param_views()["output.weight"].mul_(4.0)
+        return m
+
+    def batch(r):
+        g = torch.Generator().manual_seed(100 + r)
+        tok = torch.randint(3, 512, (2, 12), generator=g)
+        tok[:, 0] = 1
+        lab = tok.clone()
+        lab[:, :5] = 0
+        return tok.cuda(), lab.cuda(), torch.randn(2, 3, 28, 28, generator=g).cuda()
+
+    dp = build()
+    dp.llma.enable_data_parallel(group)
+    opt = AdamW(dp, lr=1e-3, weight_decay=0.1)
+    scaler = NativeScalerWithGradNormCount()
+    ref = build()
+    ropt = AdamW(ref, lr=1e-3, weight_decay=0.1)
+    norm_err = 0.0
+    for step in range(steps):
+        micro = 2 if step == steps - 1 else 1
+        dp.zero_grad(set_to_none=True)
+        for k in range(micro):
+            tok, lab, img = batch(rank + 10 * step + 100 * k)
+            loss, _ = dp(tok, lab, images=img)
+            norm = scaler(loss / micro, opt, dp, clip_grad=0.5, update_grad=(k == micro - 1))
+        ref.zero_grad(set_to_none=True)
+        for r in range(world):
+            for k in range(micro):
+                t2, l2, i2 = batch(r + 10 * step + 100 * k)
+                l, _ = ref(t2, l2, images=i2)
+                (l / (world * micro)).backward()
+        ropt.step(max_norm=0.5)
+        rnorm = ropt.grad_norm()
+        norm_err = max(norm_err, abs(norm.item() - rnorm.item()) / max(rnorm.item(), 1e-12))
+    got, want = dp.llma.state_dict(), ref.llma.state_dict()
+    worst, identical, ok = 0.0, True, norm_err <= 2e-2
+    for k in want:
+        if k.startswith("clip."):
+            continue
+        gk, wk = got[k].float(), want[k].float()
+        bad = ((gk - wk).abs() > 1e-5 + 2 ** -6 * wk.abs()).float().mean().item()
+        ok &= bad <= (0.03 if wk.numel() >= 4096 else 0.08)
+        ok &= (gk - wk).abs().max().item() <= 2 * 1e-3 * steps + 2 ** -6 * wk.abs().max().item()  # never beyond 2*lr*steps
+        worst = max(worst, bad)
+        other = got[k].clone()
+        dist.broadcast(other, src=dist.get_global_rank(group, 0), group=group)
+        identical &= bool(torch.equal(other, got[k]))
+    ok &= identical
+    flag = torch.tensor([1.0 if ok else 0.0, -worst, -norm_err, 1.0 if identical else 0.0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    del dp, ref, opt, ropt
+    torch.cuda.empty_cache()
+    return {"ok": bool(flag[0].item()), "worst_mismatch": -flag[1].item(), "grad_norm_rel_err": -flag[2].item(),
+            "replicas_identical": bool(flag[3].item()), "world": world, "steps": steps,
+            "what": "tiny model: sharded DP steps (reduce-scatter grads, owned-slice AdamW, all-gather weights, last step "
+                    "with a no_sync accumulation micro-step) vs one replica accumulating the same per-rank batches"}

@@ -169,19 +169,29 @@ class Workspace:
         self.B, self.T, self.W, self.L, self.M = B, T, W, L, M
         e = lambda *s, dt=bf16: torch.empty(*s, device=dev, dtype=dt)
         keep = NL if train else 1
+        # Activation recompute (the reference checkpoints every TransformerBlock, M/main_finetune.py:268-276):
+        #   0  keep everything the backward reads (fastest; 7B at batch 8 needs ~28 GB)
+        #   1  selective: the norm outputs xn / hn (+ rstd) and the gate output y are rebuilt in the backward
+        #      from x / h / gu by three HBM-bound row kernels per layer (-25 % activation memory)
+        #   2  full block recompute as in the reference: only the block inputs x[i] are kept, the backward
+        #      re-runs the block's forward (without its last GEMM) into one layer's worth of scratch
+        self.recompute = rc = (eng.recompute if train else 0)
+        self.generation = 0  # bumped by every forward_train into this workspace (stale-backward guard)
+        k_sel = 1 if rc >= 1 else keep   # xn, hn, y, rstd
+        k_blk = 1 if rc >= 2 else keep   # qkv, o, h, gu, lse
         self.x = [e(M, D) for _ in range(keep + 1)]
-        self.xn = [e(M, D) for _ in range(keep)]
-        self.qkv = [e(M, 3 * D) for _ in range(keep)]
-        self.o = [e(M, D) for _ in range(keep)]
-        self.h = [e(M, D) for _ in range(keep)]
-        self.hn = [e(M, D) for _ in range(keep)]
-        self.gu = [e(M, 2 * F) for _ in range(keep)]
-        # swiglu output: kept per layer when training (the w2 wgrad needs it; recomputing costs a
-        # 441 MB pass per layer), one scratch buffer otherwise
-        self.y = [e(M, F) for _ in range(keep)]
-        self.lse = [e(B, a.n_heads, L, dt=torch.float32) for _ in range(keep)]
-        self.rstd1 = [e(M, dt=torch.float32) for _ in range(keep)]
-        self.rstd2 = [e(M, dt=torch.float32) for _ in range(keep)]
+        self.xn = [e(M, D) for _ in range(k_sel)]
+        self.qkv = [e(M, 3 * D) for _ in range(k_blk)]
+        self.o = [e(M, D) for _ in range(k_blk)]
+        self.h = [e(M, D) for _ in range(k_blk)]
+        self.hn = [e(M, D) for _ in range(k_sel)]
+        self.gu = [e(M, 2 * F) for _ in range(k_blk)]
+        # swiglu output: kept per layer when training without recompute (the w2 wgrad needs it), one
+        # scratch buffer otherwise
+        self.y = [e(M, F) for _ in range(k_sel)]
+        self.lse = [e(B, a.n_heads, L, dt=torch.float32) for _ in range(k_blk)]
+        self.rstd1 = [e(M, dt=torch.float32) for _ in range(k_sel)]
+        self.rstd2 = [e(M, dt=torch.float32) for _ in range(k_sel)]
         if train:
             R = B * T
             self.fn = e(R, D)
@@ -200,7 +210,6 @@ class Workspace:
             self.dq_acc = e(M, D, dt=torch.float32)
             self.delta = e(B, a.n_heads, L, dt=torch.float32)
             self.nparts = 2 * eng.n_sms  # rmsnorm_bwd runs 2 CTAs/SM: one resident wave
-            self.part = e(max(B, 1) * self.nparts, D, dt=torch.float32)
             self.part2 = e(self.nparts, D, dt=torch.float32)
             self.tag_grad = e(2, D, dt=torch.float32)
         if W:
@@ -264,6 +273,8 @@ class Engine:
         # pipelined optimiser step (single replica / unsharded state): sumsq + AdamW run on a side stream,
         # chunk by chunk in forward-consumption order, underneath the NEXT step's ViT + decoder forward
         self.overlap_optimizer = False
+        # activation recompute level for the training workspaces (Workspace): 0 none, 1 selective, 2 per block
+        self.recompute = 0
         self.overlap_adamw_blocks_per_sm = 4  # measured: 4 CTAs/SM 275.8-277.5 ms/step, 1: 279.9, 16: 279.4, in line: 281-285
         self.opt_stream = None
         self.norm_ready = None
@@ -352,7 +363,7 @@ class Engine:
         return ws
 
     def workspace(self, B: int, T: int, W: int, train: bool) -> Workspace:
-        key = (B, T, W, train)
+        key = (B, T, W, train, self.recompute if train else 0)
         ws = self._ws.get(key)
         if ws is None:
             # one live shape per mode: drop workspaces of other shapes (they are GBs at 7B)
@@ -415,7 +426,7 @@ class Engine:
 
     # ------------------------------------------------------------------------------------ decoder layer
     def _layer_fwd(self, i, x, xn, qkv, o, h, hn, gu, y, out, lse, rstd1, rstd2, B, L, pos0=0,
-                   kv=None):
+                   kv=None, skip_out=False):
         a, w, D = self.args, self.w.views, self.args.dim
         p = f"layers.{i}."
         ops.rmsnorm_fwd(x, w[p + "attention_norm.weight"], a.norm_eps, out=xn, rstd=rstd1)
@@ -438,7 +449,8 @@ class Engine:
         else:
             ops.gemm(hn, w[p + "w13"], gu)
             ops.swiglu_fwd(gu, y)
-        ops.gemm(y, w[p + "feed_forward.w2.weight"], out, residual=h)
+        if not skip_out:  # the backward's block recompute already holds the block output x[i + 1]
+            ops.gemm(y, w[p + "feed_forward.w2.weight"], out, residual=h)
 
     # ------------------------------------------------------------------------------------ training forward
     def forward_train(self, examples: torch.Tensor, image: Optional[torch.Tensor], labels=None,
@@ -451,23 +463,27 @@ class Engine:
         # the training forward splices the RGB stream only, also in the RGB-D build (M/model/meta.py:251)
         W = self.visual_image_words if image is not None else 0
         ws = self.workspace(B, T, W, True)
+        ws.generation += 1
         L, D = ws.L, a.dim
         if L > 2 * a.max_seq_len:
             raise ValueError("sequence longer than the RoPE table (2 * max_seq_len)")
-        examples = examples.contiguous()
+        # the backward scatters into the embedding by these ids: keep the dense copy with the workspace (a
+        # trimmed `examples[:, :k]` view handed to the kernels as a bare pointer would be read with the wrong stride)
+        examples = ws.examples = examples.contiguous()
         img = self.vit_forward(image, ws.vit) if W else None
         self.wait_weights(self._range("tok_embeddings.weight")[1])
         ops.embed_splice(examples, w["tok_embeddings.weight"], img, w["start_img"] if W else None,
                          w["end_img"] if W else None, ws.x[0], B, T, self.vis.tokens if W else 0, D, self.views)
+        ks, kb = (lambda i: 0 if ws.recompute >= 1 else i), (lambda i: 0 if ws.recompute >= 2 else i)
         for i in range(a.n_layers):
             self.wait_weights(self._range(f"layers.{i}.feed_forward.w2.weight")[1])
-            self._layer_fwd(i, ws.x[i], ws.xn[i], ws.qkv[i], ws.o[i], ws.h[i], ws.hn[i], ws.gu[i], ws.y[i],
-                            ws.x[i + 1], ws.lse[i], ws.rstd1[i], ws.rstd2[i], B, L)
+            self._layer_fwd(i, ws.x[i], ws.xn[ks(i)], ws.qkv[kb(i)], ws.o[kb(i)], ws.h[kb(i)], ws.hn[ks(i)],
+                            ws.gu[kb(i)], ws.y[ks(i)], ws.x[i + 1], ws.lse[kb(i)], ws.rstd1[ks(i)],
+                            ws.rstd2[ks(i)], B, L)
         self.wait_weights()
         xf = ws.x[a.n_layers].view(B, L, D)
-        for b in range(B):  # final norm on the text rows only (llama_ens5.py:485-486)
-            ops.rmsnorm_fwd(xf[b, W:], w["norm.weight"], a.norm_eps, out=ws.fn[b * T:(b + 1) * T],
-                            rstd=ws.rstd_f[b * T:(b + 1) * T])
+        # final norm on the text rows only (llama_ens5.py:485-486): one grouped launch over [B][T] rows
+        ops.rmsnorm_fwd(xf[:, W:], w["norm.weight"], a.norm_eps, out=ws.fn, rstd=ws.rstd_f)
         ops.gemm(ws.fn, w["output.weight"], ws.logits)
         if labels is not None:
             ops.shift_labels(labels, ws.shift, ws.count)
@@ -486,6 +502,7 @@ class Engine:
         a, w, g = self.args, self.w.views, self.g.views
         B, T, W, L, M, D, F = ws.B, ws.T, ws.W, ws.L, ws.M, a.dim, self.ffn_dim
         NL, acc = a.n_layers, accumulate
+        examples = examples.contiguous()  # see forward_train: never index a strided view through a bare pointer
         wg = lambda dy, x, out: ops.gemm(dy, x, out, a_mn=True, b_mn=True, accumulate=acc)   # dW = dy^T x
         dg = lambda dy, wt, out: ops.gemm(dy, wt, out, b_mn=True)                             # dx = dy W
         np_ = ws.nparts
@@ -497,32 +514,39 @@ class Engine:
             on_bucket(*next(bk))
         ws.d.zero_()
         xf, dv = ws.x[NL].view(B, L, D), ws.d.view(B, L, D)
-        for b in range(B):
-            ops.rmsnorm_bwd(ws.dfn[b * T:(b + 1) * T], xf[b, W:], w["norm.weight"], ws.rstd_f[b * T:(b + 1) * T],
-                            dv[b, W:], ws.part[b * np_:(b + 1) * np_])
-        ops.colsum_partials(ws.part[:B * np_], g["norm.weight"], accumulate=acc)
+        ops.rmsnorm_bwd(ws.dfn, xf[:, W:], w["norm.weight"], ws.rstd_f, dv[:, W:], ws.part2)
+        ops.colsum_partials(ws.part2, g["norm.weight"], accumulate=acc)
         d, t = ws.d, ws.dtmp
+        rc = ws.recompute
         for i in reversed(range(NL)):
             p = f"layers.{i}."
-            wg(d, ws.y[i], g[p + "feed_forward.w2.weight"])
+            ks, kb = (0 if rc >= 1 else i), (0 if rc >= 2 else i)
+            if rc >= 2:    # the reference's per-block activation checkpoint: re-run the block (minus its last GEMM)
+                self._layer_fwd(i, ws.x[i], ws.xn[0], ws.qkv[0], ws.o[0], ws.h[0], ws.hn[0], ws.gu[0], ws.y[0],
+                                None, ws.lse[0], ws.rstd1[0], ws.rstd2[0], B, L, skip_out=True)
+            elif rc == 1:  # selective: rebuild the norm outputs and the gate output (three row kernels)
+                ops.swiglu_fwd(ws.gu[i], ws.y[0])
+                ops.rmsnorm_fwd(ws.h[i], w[p + "ffn_norm.weight"], a.norm_eps, out=ws.hn[0], rstd=ws.rstd2[0])
+                ops.rmsnorm_fwd(ws.x[i], w[p + "attention_norm.weight"], a.norm_eps, out=ws.xn[0], rstd=ws.rstd1[0])
+            wg(d, ws.y[ks], g[p + "feed_forward.w2.weight"])
             if self.fuse_dswiglu:  # gate backward fused behind the w2 dgrad: dy stays in TMEM / registers
-                ops.gemm_dswiglu(d, w[p + "feed_forward.w2.weight"], ws.gu[i], ws.dgu)
+                ops.gemm_dswiglu(d, w[p + "feed_forward.w2.weight"], ws.gu[kb], ws.dgu)
             else:
                 dg(d, w[p + "feed_forward.w2.weight"], ws.dy)
-                ops.swiglu_bwd(ws.gu[i], ws.dy, ws.dgu)
-            wg(ws.dgu, ws.hn[i], g[p + "w13"])
+                ops.swiglu_bwd(ws.gu[kb], ws.dy, ws.dgu)
+            wg(ws.dgu, ws.hn[ks], g[p + "w13"])
             dg(ws.dgu, w[p + "w13"], t)
-            ops.rmsnorm_bwd(t, ws.h[i], w[p + "ffn_norm.weight"], ws.rstd2[i], d, ws.part2, add_to_dx=True)
+            ops.rmsnorm_bwd(t, ws.h[kb], w[p + "ffn_norm.weight"], ws.rstd2[ks], d, ws.part2, add_to_dx=True)
             ops.colsum_partials(ws.part2, g[p + "ffn_norm.weight"], accumulate=acc)
-            wg(d, ws.o[i], g[p + "attention.wo.weight"])
+            wg(d, ws.o[kb], g[p + "attention.wo.weight"])
             dg(d, w[p + "attention.wo.weight"], t)
-            qkv, dqkv = ws.qkv[i], ws.dqkv
-            ops.attn_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], ws.o[i], t, ws.lse[i], ws.delta, ws.dq_acc,
+            qkv, dqkv = ws.qkv[kb], ws.dqkv
+            ops.attn_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], ws.o[kb], t, ws.lse[kb], ws.delta, ws.dq_acc,
                          dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], B, a.n_heads, L, self.head_dim,
                          self.scale, True, rope=self.rope)  # backward of RoPE fused into the dq / dk stores
-            wg(dqkv, ws.xn[i], g[p + "wqkv"])
+            wg(dqkv, ws.xn[ks], g[p + "wqkv"])
             dg(dqkv, w[p + "wqkv"], t)
-            ops.rmsnorm_bwd(t, ws.x[i], w[p + "attention_norm.weight"], ws.rstd1[i], d, ws.part2, add_to_dx=True)
+            ops.rmsnorm_bwd(t, ws.x[i], w[p + "attention_norm.weight"], ws.rstd1[ks], d, ws.part2, add_to_dx=True)
             ops.colsum_partials(ws.part2, g[p + "attention_norm.weight"], accumulate=acc)
             if on_bucket:
                 on_bucket(*next(bk))

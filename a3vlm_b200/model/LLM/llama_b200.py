@@ -108,7 +108,9 @@ class _TrainFn(torch.autograd.Function):
     def forward(ctx, model: "Transformer", examples, image, labels, anchor):
         eng = model.engine
         ws, logits = eng.forward_train(examples, image, labels)
-        ctx.model, ctx.ws, ctx.examples, ctx.fused = model, ws, examples, labels is not None
+        # ws.examples: the dense copy of the ids the forward used (a trimmed column view would be mis-strided)
+        ctx.model, ctx.ws, ctx.examples, ctx.fused = model, ws, ws.examples, labels is not None
+        ctx.generation = ws.generation
         if labels is not None:
             return ws.loss[0].clone()
         B, T = examples.shape
@@ -118,6 +120,13 @@ class _TrainFn(torch.autograd.Function):
     def backward(ctx, grad_out):
         model, ws = ctx.model, ctx.ws
         eng = model.engine
+        if ws.generation != ctx.generation:
+            # the engine keeps ONE activation workspace per shape: a later forward (another micro-batch, or a
+            # no_grad evaluation through loss_forward) has overwritten what this backward would read
+            raise RuntimeError(
+                "llama_b200: backward() after another forward of the same shape -- the activation workspace is "
+                "reused, so run forward -> backward per micro-batch (gradients accumulate across backward calls; "
+                "this is the order of M/engine_finetune.py:44-68)")
         params = model._trainable
         accumulate = params[0].grad is not None  # zero_grad(set_to_none=True) -> overwrite
         if ctx.fused:
@@ -252,6 +261,15 @@ class Transformer(nn.Module):
         self.dp_world = dist.get_world_size(self.dp_group)
         if shard_optimizer and self.dp_world > 1:
             self.engine.enable_sharded_optimizer(self.dp_group)
+
+    def set_activation_recompute(self, level: int) -> None:
+        """The reference's `--checkpointing` (M/main_finetune.py:268-276 wraps every TransformerBlock in an
+        activation checkpoint).  0: keep all activations (default); 1: selective -- norm outputs and the gate
+        output are rebuilt in the backward by row kernels; 2: per-block recompute as in the reference (only the
+        block inputs are kept, the backward re-runs each block's forward).  Same gradients bit for bit."""
+        if level not in (0, 1, 2):
+            raise ValueError("activation recompute level must be 0, 1 or 2")
+        self.engine.recompute = int(level)
 
     def state_dict(self, *args, **kwargs):
         self.engine.wait_weights()  # a pending weight exchange / pipelined update must land first

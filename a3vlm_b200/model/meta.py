@@ -121,6 +121,9 @@ class MetaModel(nn.Module):
                 raise ValueError("Cannot determine llama_type")
             with open(mj, "r") as f:
                 llama_type = json.load(f)["llama_type"]
+        if llama_type in ("llama_ens5", "llama_ens5_2images"):
+            # a checkpoint written by the reference's own plugin: loadable only if it was built ViT-only
+            ckpt.check_vision_branch(pretrained_path, 1024)
         llama_type = {"llama_ens5": "llama_b200", "llama_ens5_2images": "llama_b200_2images"}.get(llama_type, llama_type)
         if llama_config is None:
             cj = os.path.join(last, "config.json")

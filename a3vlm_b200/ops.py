@@ -129,21 +129,37 @@ def decode_gemm(x, w, out, residual=None, out_fp32=False):
 
 # ----------------------------------------------------------------------------------------- norms
 def rmsnorm_fwd(x, w, eps, out=None, rstd=None):
-    rows, D = x.shape
+    """x [rows][D] (row stride honoured), or [G][R][D] with x.stride(2) == 1: the G groups of R rows are
+    normalised by one launch into dense out [G*R][D] (the text rows of every sample of a [B][L][D] stream)."""
+    if x.dim() == 3:
+        G, R, D = x.shape
+        assert x.stride(2) == 1
+        rows, ldx, group_rows, group_stride = G * R, x.stride(1), R, x.stride(0)
+    else:
+        rows, D = x.shape
+        ldx, group_rows, group_stride = x.stride(0), 0, 0
     if out is None:
         out = torch.empty(rows, D, device=x.device, dtype=bf16)
-    rc = _L().a3_rmsnorm_fwd(_p(x), _p(w), _p(out), _p(rstd), rows, D, x.stride(0), out.stride(0),
-                             float(eps), _st())
+    rc = _L().a3_rmsnorm_fwd(_p(x), _p(w), _p(out), _p(rstd), rows, D, ldx, out.stride(0),
+                             float(eps), group_rows, group_stride, _st())
     _lib.check(rc, "a3_rmsnorm_fwd")
     return out
 
 
 def rmsnorm_bwd(dy, x, w, rstd, dx, dw_partial, add_to_dx=False):
-    rows, D = x.shape
-    assert x.is_contiguous() and dy.is_contiguous() and dx.is_contiguous()
+    """x / dx [rows][D] contiguous, or both [G][R][D] views with dense rows inside a group (same strides);
+    dy and rstd are dense over the G*R rows."""
+    if x.dim() == 3:
+        G, R, D = x.shape
+        assert x.stride() == dx.stride() and x.stride(2) == 1 and x.stride(1) == D and dy.is_contiguous()
+        rows, group_rows, group_stride = G * R, R, x.stride(0)
+    else:
+        rows, D = x.shape
+        assert x.is_contiguous() and dy.is_contiguous() and dx.is_contiguous()
+        group_rows = group_stride = 0
     nparts = dw_partial.shape[0]
     rc = _L().a3_rmsnorm_bwd(_p(dy), _p(x), _p(w), _p(rstd), _p(dx), _p(dw_partial), nparts, rows, D,
-                             int(add_to_dx), _st())
+                             int(add_to_dx), group_rows, group_stride, _st())
     _lib.check(rc, "a3_rmsnorm_bwd")
     return dx
 
@@ -363,8 +379,24 @@ def generate_step(tokens, prompt_len, next_token, cur_pos, stop_tokens, stop_off
 
 
 # ----------------------------------------------------------------------------------------- optimiser
-def sumsq_bf16(g, out):
-    _lib.check(_L().a3_sumsq_bf16(_p(g), g.numel(), _p(out), _st()), "a3_sumsq_bf16")
+SUMSQ_SCRATCH_BYTES = 8192  # A3_SUMSQ_SCRATCH_BYTES
+_sumsq_scratch = {}
+
+
+def sumsq_scratch(device) -> torch.Tensor:
+    """A zeroed scratch buffer for a3_sumsq_bf16 (partials + arrival counter)."""
+    return torch.zeros(SUMSQ_SCRATCH_BYTES // 4, device=device, dtype=torch.float32)
+
+
+def sumsq_bf16(g, out, scratch=None):
+    """out[0] += sum(g^2).  Without `scratch` one buffer per (device, current stream) is kept here, so
+    calls on different streams never share the kernel's partial sums."""
+    if scratch is None:
+        key = (g.device, torch.cuda.current_stream(g.device).cuda_stream)
+        scratch = _sumsq_scratch.get(key)
+        if scratch is None:
+            scratch = _sumsq_scratch[key] = sumsq_scratch(g.device)
+    _lib.check(_L().a3_sumsq_bf16(_p(g), g.numel(), _p(out), _p(scratch), _st()), "a3_sumsq_bf16")
 
 
 def set_adamw_blocks_per_sm(n: int) -> None:

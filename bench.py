@@ -99,11 +99,13 @@ class ClockSampler:
 _CPU_REF_CACHE = {}
 
 
-def cpu_reference_sample(cfg, S, T, sample_layers=2, repeats=1):
+def cpu_reference_sample(cfg, S, T, sample_layers=2, repeats=1, detail=None):
     """Times the oracle restatement (PyTorch eager, bf16 linears on the host cores) on a bounded sample
     of the workload: batch 1, full ViT forward, `sample_layers` decoder layers fwd+bwd, LM head + loss
     fwd+bwd, clip + AdamW on what was trained; the decoder time is extrapolated linearly to n_layers.
-    Returns (seconds per image, cores, description).  Weights / inputs are built once and cached."""
+    Returns (seconds per image EXTRAPOLATED to full depth, cores, description).  `detail` (dict) receives the
+    measured pieces: wall seconds of the sample itself and its forward+backward / optimiser split.
+    Weights / inputs are built once and cached."""
     import torch
 
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -137,18 +139,59 @@ def cpu_reference_sample(cfg, S, T, sample_layers=2, repeats=1):
         t0 = time.perf_counter()
         loss = O.meta_forward_loss(m, tok, lab, img)
         loss.backward()
+        t1 = time.perf_counter()
         live = [k for k in train if sd[k].grad is not None]
         grads = {k: sd[k].grad for k in live}
         O.adamw_step({k: master[k] for k in live}, grads, state, 1, 2e-5, 0.0, 8.0)  # clip 8 + AdamW, as our step
-        return time.perf_counter() - t0
+        t2 = time.perf_counter()
+        return t2 - t0, t1 - t0, t2 - t1
 
-    t_small = min(run(a_small) for _ in range(repeats))
-    t_zero = min(run(a_zero) for _ in range(repeats))
+    r_small = min((run(a_small) for _ in range(repeats)), key=lambda r: r[0])
+    r_zero = min((run(a_zero) for _ in range(repeats)), key=lambda r: r[0])
+    t_small, t_zero = r_small[0], r_zero[0]
     per_layer = max(t_small - t_zero, 0.0) / sample_layers
     full = t_zero + per_layer * cfg["n_layers"]
+    if detail is not None:
+        detail.update(sample_wall_s=t_small + t_zero, t_zero_s=t_zero, t_layers_s=t_small - t_zero,
+                      fwd_bwd_zero_s=r_zero[1], fwd_bwd_small_s=r_small[1], opt_zero_s=r_zero[2], opt_small_s=r_small[2],
+                      sample_layers=sample_layers, n_layers=cfg["n_layers"], extrapolated_s_per_image=full)
     sample = (f"oracle (torch eager, bf16 linears) batch 1, {S}px + {T} tok: ViT fwd + head/loss fwd+bwd + their clip/AdamW = {t_zero:.2f}s, "
               f"{sample_layers} decoder layers fwd+bwd+AdamW = {t_small - t_zero:.2f}s, extrapolated x{cfg['n_layers']}/{sample_layers}")
     return full, cores, sample
+
+
+def cpu_reference_full_depth_check(cfg, S, T, sample_layers=2):
+    """Validates the linear extrapolation ONCE: a full-depth (n_layers) batch-1 forward + backward of the oracle,
+    timed directly.  The n_layers blocks cycle through the `sample_layers` sampled blocks' weight tensors (aliases:
+    a 7B / 13B replica plus its gradients does not have to be materialised on the host; each block's ~0.4-0.6 GB of
+    weights exceeds the CPU caches, so the timing is that of distinct weights; gradients of the aliased blocks
+    accumulate, one extra add per block).  The optimiser is excluded (its fp32 state for the full model does not fit
+    host memory) -- compare with the sample's forward+backward extrapolation."""
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import a3vlm_oracle as O
+
+    key = (json.dumps(cfg, sort_keys=True), S, T, sample_layers)
+    a_small, a_zero, v, sd, tok, lab, img, train, master, state = _CPU_REF_CACHE[key]
+    a_full = O.ModelArgs(**{**cfg, "max_seq_len": 2048})
+    full_sd = dict(sd)
+    for i in range(cfg["n_layers"]):
+        for k in list(sd):
+            if k.startswith("layers.0."):
+                full_sd[f"layers.{i}." + k[len("layers.0."):]] = sd[f"layers.{i % sample_layers}." + k[len("layers.0."):]]
+    for k in train:
+        sd[k].requires_grad_(True)
+        sd[k].grad = None
+    m = O.OracleTransformer(a_full, v, full_sd, native_linear=True)
+    t0 = time.perf_counter()
+    loss = O.meta_forward_loss(m, tok, lab, img)
+    t1 = time.perf_counter()
+    loss.backward()
+    t2 = time.perf_counter()
+    for k in train:
+        sd[k].grad = None
+    return {"forward_s": t1 - t0, "forward_backward_s": t2 - t0}
 
 
 def run_reference(args, cfg):
@@ -158,20 +201,38 @@ def run_reference(args, cfg):
     S, T = args.image_size, args.text_len
     for _ in range(min(args.warmup, 1)):
         cpu_reference_sample(cfg, S, T)
-    times = []
+    times, walls, det = [], [], {}
     t_start = time.perf_counter()
     for _ in range(args.steps):
-        full, cores, sample = cpu_reference_sample(cfg, S, T)
+        w0 = time.perf_counter()
+        full, cores, sample = cpu_reference_sample(cfg, S, T, detail=det)
+        walls.append(time.perf_counter() - w0)
         times.append(full)
-        if time.perf_counter() - t_start > 240:
+        if time.perf_counter() - t_start > 200:
             break
     sec = statistics.mean(times)
     val = 1.0 / sec
+    # one direct full-depth forward + backward to validate the extrapolation (outside the timed steps)
+    check = None
+    try:
+        fd = cpu_reference_full_depth_check(cfg, S, T)
+        nl, sl = cfg["n_layers"], det["sample_layers"]
+        extrap_fb = det["fwd_bwd_zero_s"] + (det["fwd_bwd_small_s"] - det["fwd_bwd_zero_s"]) / sl * nl
+        check = {"measured_full_depth_forward_backward_s": fd["forward_backward_s"], "measured_full_depth_forward_s": fd["forward_s"],
+                 "extrapolated_forward_backward_s": extrap_fb, "ratio_measured_over_extrapolated": fd["forward_backward_s"] / extrap_fb,
+                 "how": f"batch 1, {nl} decoder blocks cycling through the {sl} sampled blocks' weights (aliases), optimiser excluded"}
+    except Exception as e:  # e.g. not enough host memory for the activations
+        check = {"error": repr(e)[:200]}
     fl = flops_per_sample(cfg, S, T)
+    # ms_per_step is the MEASURED wall time of one step of this arm (= one bounded sample); `value` is that sample
+    # extrapolated linearly to the full decoder depth and stated as images/s -- see `extrapolation`
     line = {"impl": "reference", "metric": "images/sec (336x336 + 256-tok prompt) fwd+bwd", "value": val, "unit": "images/s",
-            "n_gpus": args.gpus, "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3,
+            "n_gpus": args.gpus, "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": statistics.mean(walls) * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(args, cfg, fl, 1),
+            "value_is": "EXTRAPOLATED: seconds per image = t(ViT + head + their AdamW) + n_layers/sample_layers * t(sampled decoder "
+                        "layers fwd+bwd+AdamW), batch 1, scaled linearly to the batch; ms_per_step is the measured sample",
+            "extrapolation": {**det, "extrapolated_ms_per_image": sec * 1e3, "full_depth_check": check},
             "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -185,7 +246,7 @@ def workload_config(args, cfg, fl, n):
             "global_batch": args.batch * n, "text_len": args.text_len, "seq_len": fl["L"], "image_size": args.image_size,
             "parallelism": f"dp{n}", "optimizer": ("sharded over the ranks (reduce-scatter grads, all-gather weights), pipelined under the next forward" if n > 1
                           else "pipelined under the next forward" if getattr(args, "overlap_opt", 0) else "in line"),
-            "l2_policy": "working set (13.5 GB weights + activations) >> 126 MB L2, no flush needed",
+            "l2_policy": "working set (>= 13.5 GB of weights + activations) >> 126 MB L2, no flush needed",
             "tflop_per_image": fl["total"] / 1e12}
 
 
@@ -201,6 +262,10 @@ def main():
     ap.add_argument("--text-len", type=int, default=256)
     ap.add_argument("--image-size", type=int, default=336)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--recompute", type=int, default=-1, choices=[-1, 0, 1, 2],
+                    help="activation recompute (M/main_finetune.py:268-276): 0 none, 1 selective, 2 per block, -1 = the "
+                         "lowest level whose estimated footprint fits the device")
+    ap.add_argument("--no-dp-check", action="store_true", help="skip the data-parallel correctness self-check at N > 1")
     ap.add_argument("--overlap-opt", type=int, default=int(os.environ.get("A3_OVERLAP_OPT", "1")),
                     help="1: pipelined optimiser step (sumsq + AdamW on a side stream underneath the next step's forward)")
     ap.add_argument("--ncu", action="store_true",
@@ -238,9 +303,38 @@ def main():
     fl = flops_per_sample(cfg, S, T)
     pk = peaks()
 
+    # ---- memory plan (bytes): bf16 weights + bf16 grads + fp32 master/m/v (sharded over the ranks) + activations
+    D, NL, V, F, L = cfg["dim"], cfg["n_layers"], cfg["vocab_size"], fl["F"], fl["L"]
+    n_params = V * D * 2 + NL * (4 * D * D + 3 * D * F) + 1024 * D
+    M_rows = B * L
+    act_layer = {0: (8 * M_rows * D + 3 * M_rows * F) * 2, 1: (6 * M_rows * D + 2 * M_rows * F) * 2, 2: M_rows * D * 2}
+    one_layer = (8 * M_rows * D + 3 * M_rows * F) * 2
+    bwd_ws = (2 * M_rows * D + 3 * M_rows * F + 3 * M_rows * D) * 2 + M_rows * D * 4 + 2 * B * T * V * 2
+    fixed = n_params * (2 + 2) + n_params * 12 // world + bwd_ws + (3 << 30)  # + ViT, NCCL buffers, context
+    total_mem = torch.cuda.get_device_properties(dev).total_memory
+    plan = {lv: fixed + NL * act_layer[lv] + (one_layer if lv else 0) for lv in (0, 1, 2)}
+    recompute = args.recompute
+    if recompute < 0:
+        recompute = next((lv for lv in (0, 1, 2) if plan[lv] < 0.90 * total_mem), 2)
+    if plan[recompute] > 0.98 * total_mem:
+        if rank == 0:
+            print(json.dumps({"metric": "images/sec (336x336 + 256-tok prompt) fwd+bwd", "unavailable":
+                              f"llama-{args.model} at batch {B}, L {L} needs ~{plan[recompute] / 2**30:.0f} GiB per GPU at N={world} "
+                              f"(recompute level {recompute}); device has {total_mem / 2**30:.0f} GiB -- use more GPUs (the optimiser "
+                              f"state is sharded over the ranks)", "n_gpus": world}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    dp_check = None
+    if world > 1 and not args.no_dp_check:
+        from a3vlm_b200 import dp as _dp
+
+        dp_check = _dp.self_check()  # outside the timed region, tiny model, every rank takes part
+
     model = MetaModel("llama_b200", {**cfg, "image_size": S}, None, with_visual=True, max_seq_len=2048)
     model.llma.reset_parameters(seed=2 + 0)  # identical replicas on every rank
     eng = model.llma.engine
+    model.llma.set_activation_recompute(recompute)
     eng.overlap_optimizer = bool(args.overlap_opt)  # no effect with the sharded optimiser (N > 1)
     if world > 1:
         model.llma.enable_data_parallel()
@@ -377,14 +471,16 @@ def main():
         torch.cuda.synchronize()
         tot_ms = sum(e0.elapsed_time(e1) for e0, e1, _, _ in recs)
         tot_fl = sum(f for _, _, f, _ in recs)
+        by = {}
+        for e0, e1, f, key in recs:
+            t = by.setdefault(key, [0, 0.0, 0.0])
+            t[0] += 1; t[1] += e0.elapsed_time(e1); t[2] += f
+        by_shape = [{"M": k[0], "N": k[1], "K": k[2], "a_mn": k[3], "b_mn": k[4], "launches": n, "ms": round(ms_, 3),
+                     "tflops": round(f / ms_ / 1e9, 1)} for k, (n, ms_, f) in sorted(by.items(), key=lambda kv: -kv[1][1])]
         if os.environ.get("A3_BENCH_GEMM_DETAIL"):
-            by = {}
-            for e0, e1, f, key in recs:
-                t = by.setdefault(key, [0, 0.0, 0.0])
-                t[0] += 1; t[1] += e0.elapsed_time(e1); t[2] += f
-            for key, (n, ms_, f) in sorted(by.items(), key=lambda kv: -kv[1][1]):
-                print(f"gemm M{key[0]} N{key[1]} K{key[2]} a_mn{key[3]} b_mn{key[4]}: n={n} total {ms_:.2f} ms, "
-                      f"{f / ms_ / 1e9:.0f} TFLOP/s", file=sys.stderr)
+            for r in by_shape:
+                print(f"gemm M{r['M']} N{r['N']} K{r['K']} a_mn{r['a_mn']} b_mn{r['b_mn']}: n={r['launches']} total {r['ms']:.2f} ms, "
+                      f"{r['tflops']:.0f} TFLOP/s", file=sys.stderr)
         ach = tot_fl / (tot_ms / 1e3) / 1e12
         traffic = None
         tp = os.path.join(ROOT, "profiles", "r01e_gemm_traffic.json")  # ncu dram bytes of the same launches
@@ -394,7 +490,8 @@ def main():
                 "unit": "TFLOP/s", "frac": ach / pk["bf16"], "peak_source": pk["src"] + " (burst; sustained %s)" % pk["bf16_sustained"],
                 "launches_per_step": len(recs), "avg_launch_ms": tot_ms / len(recs), "gemm_ms_per_step": tot_ms,
                 "gemm_share_of_step": tot_ms / ms_step, "flops_per_launch": tot_fl / len(recs), "traffic": traffic,
-                "traffic_note": "ncu dram__bytes_read+write per GEMM launch (profiles/r01e_gemm_traffic.json), bytes"}
+                "traffic_note": "ncu dram__bytes_read+write per GEMM launch (profiles/r01e_gemm_traffic.json), bytes",
+                "by_shape": by_shape[:12]}
 
     if rank != 0:
         if world > 1:
@@ -415,7 +512,16 @@ def main():
             "step_tflops_per_gpu": step_tflops, "step_frac_of_bf16_peak": step_tflops / pk["bf16"],
             "forward": {"ms": ms_fwd, "tflops": fwd_tflops, "frac_of_bf16_peak": fwd_tflops / pk["bf16"],
                         "what": "ViT + projector + LLM forward + LM head + CE at batch %d" % B},
-            "loss": float(loss_t.item()), "e2e_last_loss": last_loss}
+            "loss": float(loss_t.item()), "e2e_last_loss": last_loss,
+            "memory": {"peak_allocated_gib": torch.cuda.max_memory_allocated(dev) / 2 ** 30, "device_gib": total_mem / 2 ** 30,
+                       "planned_gib": plan[recompute] / 2 ** 30, "activation_recompute": recompute,
+                       "recompute_levels": "0 none / 1 selective (norm + gate outputs) / 2 per block (M/main_finetune.py:268-276)"},
+            "dp_check": dp_check,
+            "parity": "tests/ (-m gpu): bit-exact for integer / index work and greedy ids (tie-aware, tests/test_fullsize_greedy_gpu.py); "
+                      "fp32-output kernels rtol 1e-3 / atol 1e-4*sqrt(K); bf16 tensors within 1-2 bf16 ulp per op and, end to end, "
+                      "rel-L2 <= 1-3e-2 with |cuda - fp32 model| <= 1.25 |oracle_bf16 - fp32 model| (the north star's rtol 1e-3 is "
+                      "below bf16 spacing 2^-8); training keeps a bf16 residual stream where the reference's autocast promotes it "
+                      "to fp32 (DESIGN.md section 2)"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -109,12 +109,18 @@ int a3_decode_gemm(const void* X, const void* W, void* Y, int M, int N, int K, l
  * LayerNorm: nn.LayerNorm eps 1e-5 of the ViT (ln_pre / ln_1 / ln_2 / ln_post) and of
  * visual_proj[1] (llama_ens5.py:330-333): fp32 statistics, output bf16.
  * ------------------------------------------------------------------------------------------- */
+/* group_rows > 0: the input rows are grouped -- output row r reads x + (r / group_rows) * group_stride +
+ * (r % group_rows) * ldx (elements).  One launch then normalises the text rows [W, L) of every sample of a
+ * [B][L][D] residual stream (final norm on h[:, image_words:], llama_ens5.py:485-486).  0: dense rows. */
 int a3_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int rows, int D,
-                   long long ldx, long long ldy, float eps, void* stream);
+                   long long ldx, long long ldy, float eps, int group_rows, long long group_stride,
+                   void* stream);
 /* dx = d/dx of the above given dy; dw_partial [nparts][D] fp32 (caller sums over parts with
- * a3_colsum_partials).  add_to_dx != 0: dx += (residual stream gradient fused). */
+ * a3_colsum_partials).  add_to_dx != 0: dx += (residual stream gradient fused).  x and dx are dense
+ * [rows][D], or grouped like a3_rmsnorm_fwd's input (row stride D inside a group); dy, rstd are dense. */
 int a3_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx,
-                   float* dw_partial, int nparts, int rows, int D, int add_to_dx, void* stream);
+                   float* dw_partial, int nparts, int rows, int D, int add_to_dx, int group_rows,
+                   long long group_stride, void* stream);
 int a3_layernorm_fwd(const void* x, const void* w, const void* b, void* y, float* mean,
                      float* rstd, int rows, int D, long long ldx, long long ldy, float eps,
                      void* stream);
@@ -260,11 +266,15 @@ int a3_generate_step(long long* tokens, long long ld_tokens, const int* prompt_l
 
 /* ---------------------------------------------------------------------------------------------
  * Optimiser (main_finetune.py:284-285, util/misc.py:586-599, util/clip_grad.py:187-193).
- * sumsq: out[0] += sum(g^2) over n bf16 gradients (fp32 accumulate).  adamw: one fused pass over
+ * sumsq: out[0] += sum(g^2) over n bf16 gradients (fp32 accumulate, deterministic).  `scratch` is
+ * A3_SUMSQ_SCRATCH_BYTES of caller-owned device memory, zeroed once before first use (the kernel leaves
+ * it ready for the next call); calls that may be in flight concurrently (different streams) must use
+ * different scratch buffers.  adamw: one fused pass over
  * a flat range -- g = bf16 grad * clip_coef(*norm_sq), m,v fp32, master fp32, shadow bf16 weight.
  * clip: coef = min(1, max_norm / (sqrt(norm_sq) + 1e-6)); max_norm <= 0 disables clipping.
  * ------------------------------------------------------------------------------------------- */
-int a3_sumsq_bf16(const void* g, long long n, float* out, void* stream);
+#define A3_SUMSQ_SCRATCH_BYTES 8192
+int a3_sumsq_bf16(const void* g, long long n, float* out, void* scratch, void* stream);
 /* Grid of a3_adamw in CTAs per SM (default 16; 1-2 when the update runs on a side stream underneath
  * the next step's forward, so that its CTAs co-reside with the persistent GEMM CTAs). */
 int a3_set_adamw_blocks_per_sm(int n);

@@ -263,12 +263,19 @@ class OracleTransformer:
     (ConvNeXt / DINOv2 / Q-Former branches are out of scope), single-view."""
 
     def __init__(self, args: ModelArgs, vis: Optional[VisionArgs], params: Dict[str, torch.Tensor],
-                 act_dtype=bf16, native_linear: bool = False, rgbd: bool = False):
+                 act_dtype=bf16, native_linear: bool = False, rgbd: bool = False, stream_dtype=None):
         """rgbd=True restates LLM/llama_ens5_2images.py: a second (depth) image stream with its own
-        start / end tags, image_words doubled (:335-344)."""
+        start / end tags, image_words doubled (:335-344).
+        stream_dtype=torch.float32 (with act_dtype bf16) restates the reference's TRAINING numerics under CUDA
+        autocast with fp32 master weights (M/util/tensor_type.py:60-66, M/engine_finetune.py:44-49): embedding rows
+        and the nn.LayerNorm output of visual_proj are fp32, so the residual stream (`h = x + linear(...)`, fp32 +
+        bf16 -> fp32) and the RMSNorm outputs stay fp32, while every Linear still runs on bf16 operands and rounds
+        its output to bf16.  Default (None = act_dtype): the bf16 stream of the inference path, which
+        is what the CUDA path keeps in training too."""
         self.args, self.vis, self.p = args, vis, params
         self.rgbd = rgbd
         self.act_dtype, self.native = act_dtype, native_linear
+        self.stream_dtype = act_dtype if stream_dtype is None else stream_dtype
         self.head_dim = args.dim // args.n_heads
         self.n_kv_heads = args.n_heads if args.n_kv_heads is None else args.n_kv_heads
         self.freqs_cis = precompute_freqs_cis(self.head_dim, args.max_seq_len * 2, args.rope_theta,
@@ -334,12 +341,12 @@ class OracleTransformer:
             image = torch.cat([image_g] + parts, dim=0)
         feats = self.clip_encode_image(image)
         y = self._lin(feats, "visual_proj.0", bias=True)
-        return layernorm(y, self.p["visual_proj.1.weight"], self.p["visual_proj.1.bias"], 1e-5)
+        return layernorm(y.to(self.stream_dtype), self.p["visual_proj.1.weight"], self.p["visual_proj.1.bias"], 1e-5)
 
     def _wrap_views(self, image: torch.Tensor, start: str, end: str) -> torch.Tensor:
         B = image.shape[0]
         views = list(torch.chunk(self.encode_image(image), self.vis.views))  # :457 one (B, N, D) per view
-        st, en = self._cast(self.p[start]).expand(B, -1, -1), self._cast(self.p[end]).expand(B, -1, -1)
+        st, en = self.p[start].to(self.stream_dtype).expand(B, -1, -1), self.p[end].to(self.stream_dtype).expand(B, -1, -1)
         toks = torch.cat([torch.cat((st, v, en), dim=1) for v in views], dim=1)  # :471-477
         assert toks.shape[1] == self.visual_image_words, f"{toks.shape[1]} v.s. {self.visual_image_words}"  # :478
         return toks
@@ -379,7 +386,7 @@ class OracleTransformer:
         return h + self._lin(y, p + "feed_forward.w2")  # :238
 
     def _embed(self, tokens: torch.Tensor) -> torch.Tensor:
-        return self._cast(F.embedding(tokens, self.p["tok_embeddings.weight"]))
+        return F.embedding(tokens, self.p["tok_embeddings.weight"]).to(self.stream_dtype)
 
     # ---- training forward: LLM/llama_ens5.py:461-487
     def forward(self, examples: torch.Tensor, image: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -221,3 +221,21 @@ def test_generation_plan_matches_oracle_restatement():
         assert plan["stop_flat"].tolist() == [2, 38, 19, 7] and plan["stop_offsets"].tolist() == [0, 1, 3, 4]
         if calls:
             assert calls[0] == ((len(c["prompts"]), plan["start_pos"]), 0)
+
+
+def test_reference_ensemble_checkpoint_is_refused_clearly(tmp_path):
+    """a released llama_ens5 checkpoint (Q-Former + 5632-wide visual_proj) must raise an explicit
+    unsupported-encoder error, not a generic shape mismatch deep in the loader."""
+    import torch
+    from a3vlm_b200 import checkpoint as ckpt
+
+    d = tmp_path / "ens"
+    d.mkdir()
+    torch.save({"model": {"llma.visual_proj.0.weight": torch.zeros(8, 5632), "llma.qformer_proj.weight": torch.zeros(4, 4),
+                          "llma.tok_embeddings.weight": torch.zeros(16, 8)}}, d / "consolidated.00-of-01.model.pth")
+    with pytest.raises(NotImplementedError, match="four-encoder"):
+        ckpt.check_vision_branch(str(d), 1024)
+    ok = tmp_path / "vit_only"
+    ok.mkdir()
+    torch.save({"model": {"llma.visual_proj.0.weight": torch.zeros(8, 1024)}}, ok / "consolidated.00-of-01.model.pth")
+    ckpt.check_vision_branch(str(ok), 1024)

@@ -415,3 +415,52 @@ def test_generate_with_images_and_with_sampling_match_reference(gold, cfg):
     torch.manual_seed(c["seed"])
     out, _, _ = O.generate_tokens(txt, prompts, max_gen_len=c["max_gen_len"], temperature=c["temperature"], top_p=c["top_p"], eos_id=2)
     assert out == c["generated"]
+
+
+def test_reference_metamodel_reaches_the_real_plugin():
+    """The literal one-line stub of INTEGRATION.md (`accessory/model/LLM/llama_b200.py` re-exporting our
+    ModelArgs / Transformer), resolved by the reference's UNMODIFIED MetaModel.__init__ through its importlib seam
+    (meta.py:30-32): the reference builds our ModelArgs from its JSON config and calls our real constructor,
+    which refuses to build without a CUDA device -- there is no CPU fallback behind the seam.  Runs where
+    /root/reference exists (this container); the GPU half is tests/test_seam_gpu.py."""
+    import importlib
+    import json
+    import tempfile
+    import types
+
+    if not os.path.isdir("/root/reference/model"):
+        pytest.skip("reference tree not present")
+    if torch.cuda.is_available():
+        pytest.skip("CPU-side half of the seam proof")
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_seam_trace as MS
+    from a3vlm_b200 import _lib
+    from a3vlm_b200.model.LLM import llama_b200 as ours
+
+    M = MS.install_seam(ours.Transformer)
+    stub = types.ModuleType("accessory.model.LLM.llama_b200")
+    exec("from a3vlm_b200.model.LLM.llama_b200 import ModelArgs, Transformer  # noqa: F401", stub.__dict__)
+    sys.modules["accessory.model.LLM.llama_b200"] = stub
+    assert importlib.import_module("accessory.model.LLM.llama_b200").Transformer is ours.Transformer
+    seen = {}
+    real_init = ours.Transformer.__init__
+
+    def spy(self, args, with_visual=False):
+        seen["args"], seen["with_visual"] = args, with_visual
+        return real_init(self, args, with_visual=with_visual)
+
+    ours.Transformer.__init__ = spy
+    try:
+        with tempfile.TemporaryDirectory() as td:
+            cfg = os.path.join(td, "params.json")
+            json.dump(MS.seam_cfg(), open(cfg, "w"))
+            with pytest.raises(_lib.A3Error, match="no CPU fallback"):
+                M.MetaModel("llama_b200", cfg, os.path.join(td, "tokenizer.model"), with_visual=True, max_seq_len=64)
+    finally:
+        ours.Transformer.__init__ = real_init
+    assert isinstance(seen["args"], ours.ModelArgs) and seen["with_visual"] is True
+    assert (seen["args"].dim, seen["args"].max_seq_len, seen["args"].max_batch_size, seen["args"].vocab_size) == (256, 64, 32, 512)
+    # and the recorded trace the GPU half replays was made from the same constructor arguments
+    tr = torch.load(os.path.join(ROOT, "tests", "golden", "reference_seam_trace.pt"), weights_only=False)
+    import dataclasses
+    assert tr["ctor"]["model_args"] == dataclasses.asdict(seen["args"])
