@@ -101,7 +101,7 @@ def test_7b_greedy_32_tokens_full_size():
     assert prefix >= min(first_tie, NG), (prefix, first_tie, got, ref)
 
     # ---------------- part 2: peaked LM head, margin >= 10x noise, token-exact free running
-    gamma, alpha = 0.004, 0.25
+    gamma, alpha = 0.02, 0.25
     views = model.llma.engine.param_views()
     perm = torch.randperm(32000, generator=torch.Generator().manual_seed(7))
     with torch.no_grad():
