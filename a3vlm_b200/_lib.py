@@ -13,7 +13,8 @@ from typing import Dict, List, Tuple
 
 _ROOT = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(os.path.dirname(_ROOT), "include", "a3vlm_b200.h")
-LIB_PATH = os.path.join(_ROOT, "lib", "liba3vlm_b200.so")
+# A3_LIB_PATH: development aid for A/B-testing an alternative build of the same library (never a different backend)
+LIB_PATH = os.environ.get("A3_LIB_PATH") or os.path.join(_ROOT, "lib", "liba3vlm_b200.so")
 
 
 class A3LibraryError(RuntimeError):

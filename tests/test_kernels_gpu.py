@@ -251,7 +251,9 @@ def attn_ref(q, k, v, causal, scale):
 
 @pytest.mark.parametrize("B,H,Tq,Tk,hd,causal", [
     (2, 2, 128, 128, 128, 1), (1, 3, 200, 200, 128, 1), (2, 2, 835, 835, 128, 1),
-    (1, 2, 70, 300, 128, 1), (2, 4, 257, 257, 64, 0), (1, 16, 577, 577, 64, 0), (1, 2, 5, 5, 128, 1)])
+    (1, 2, 70, 300, 128, 1), (2, 4, 257, 257, 64, 0), (1, 16, 577, 577, 64, 0), (1, 2, 5, 5, 128, 1),
+    (2, 2, 256, 256, 128, 1), (1, 1, 129, 129, 128, 1), (1, 2, 1603, 1603, 128, 1), (1, 3, 300, 300, 64, 0),
+    (2, 2, 384, 384, 128, 0), (1, 2, 3, 700, 128, 1), (1, 2, 300, 1000, 128, 1), (3, 2, 64, 64, 64, 1)])
 def test_attn_fwd(ops, B, H, Tq, Tk, hd, causal):
     torch.manual_seed(Tq + hd)
     W = H * hd
@@ -267,6 +269,26 @@ def test_attn_fwd(ops, B, H, Tq, Tk, hd, causal):
                             v.float().reshape(B, Tk, H, hd), causal, scale)
     close_bf16(o.reshape(B, Tq, H, hd), ref, rtol=2 ** -6, atol=6e-3)  # P is rounded to bf16 before PV
     torch.testing.assert_close(lse, lse_ref, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("mag", [4.0, 12.0])
+def test_attn_fwd_growing_maxima(ops, mag):
+    """Scores with a large spread whose row maxima keep growing along the keys (later keys are scaled up), so the
+    lazy-rescale path of the warp-specialised kernel (running maximum moves only past 2^8, O rescaled by the
+    correction warps) is exercised tile after tile."""
+    torch.manual_seed(int(mag))
+    B, H, T, hd = 2, 2, 700, 128
+    W = H * hd
+    q, v = rnd(B * T, W), rnd(B * T, W)
+    ramp = torch.linspace(0.2, mag, T, device=dev()).repeat(B)[:, None]
+    k = (rnd(B * T, W).float() * ramp).to(torch.bfloat16)
+    lse = torch.empty(B, H, T, device=dev())
+    for causal in (1, 0):
+        o = ops.attn_fwd(q, k, v, B, H, T, T, hd, 1 / math.sqrt(hd), causal, lse=lse)
+        ref, lse_ref = attn_ref(q.float().reshape(B, T, H, hd), k.float().reshape(B, T, H, hd),
+                                v.float().reshape(B, T, H, hd), causal, 1 / math.sqrt(hd))
+        close_bf16(o.reshape(B, T, H, hd), ref, rtol=2 ** -6, atol=6e-3)
+        torch.testing.assert_close(lse, lse_ref, rtol=1e-4, atol=2e-4)
 
 
 @pytest.mark.parametrize("B,H,T,causal", [(1, 2, 128, 1), (2, 2, 200, 1), (1, 2, 835, 1), (1, 1, 64, 0)])

@@ -114,7 +114,15 @@ def test_activation_recompute_is_bit_identical(level):
     finally:
         m.llma.set_activation_recompute(0)
     assert torch.equal(l0, l1)
-    assert torch.equal(g0, g1), (g0.float() - g1.float()).abs().max()
+    # bit-identical everywhere except the token-embedding gradient: its scatter-add uses bf16 atomics
+    # (a3_embed_splice_bwd), so rows of tokens that occur more than once in the batch are summed in a
+    # timing-dependent order and may differ by one bf16 rounding between ANY two runs, recompute or not
+    lo, n, _ = eng.w.offsets["tok_embeddings.weight"]
+    keep = torch.ones_like(g0, dtype=torch.bool)
+    keep[lo:lo + n] = False
+    assert torch.equal(g0[keep], g1[keep]), (g0[keep].float() - g1[keep].float()).abs().max()
+    e0, e1 = g0[lo:lo + n].float(), g1[lo:lo + n].float()
+    assert bool(((e0 - e1).abs() <= 2.0 ** -7 * e0.abs().clamp_min(1e-30)).all()), (e0 - e1).abs().max()
     assert held1 < held0 and held1 == (7 if level == 2 else 3 + 4 * a.n_layers)
 
 
