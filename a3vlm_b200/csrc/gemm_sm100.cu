@@ -357,8 +357,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp walks the loop, one elected lane issues) =====================
+    {
+      const bool leader = elect_one();
+      const uint32_t smem0 = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -367,31 +369,43 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int m0 = mb * BM, n0 = nb * BN;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * S::STAGE_BYTES;
-          uint8_t* sb = sa + S::A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], p.a_rows * (BK * 2) + S::B_BYTES);
+          const uint32_t sa = smem0 + stage * S::STAGE_BYTES;
+          const uint32_t sb = sa + S::A_BYTES;
           const int k0 = kb * BK;
-          if (!p.a_mn) {
-            tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0);  // box {64 k, a_rows (128) rows}
-          } else {
+          if (leader) {
+            mbar_arrive_expect_tx(&full_bar[stage], p.a_rows * (BK * 2) + S::B_BYTES);
+            if (!p.a_mn) {
+              tma_load_2d_s(sa, &tmA, &full_bar[stage], k0, m0);  // box {64 k, a_rows (128) rows}
+            } else {
 #pragma unroll
-            for (int c = 0; c < BM / 64; ++c)  // box {64 m, 64 k-rows} per 64-wide chunk
-              tma_load_2d(sa + c * (BK * 128), &tmA, &full_bar[stage], m0 + c * 64, k0);
-          }
-          if (!p.b_mn) {
-            tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);  // box {64 k, BN rows}
-          } else {
+              for (int c = 0; c < BM / 64; ++c)  // box {64 m, 64 k-rows} per 64-wide chunk
+                tma_load_2d_s(sa + c * (BK * 128), &tmA, &full_bar[stage], m0 + c * 64, k0);
+            }
+            if (!p.b_mn) {
+              tma_load_2d_s(sb, &tmB, &full_bar[stage], k0, n0);  // box {64 k, BN rows}
+            } else {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c)
-              tma_load_2d(sb + c * (BK * 128), &tmB, &full_bar[stage], n0 + c * 64, k0);
+              for (int c = 0; c < BN / 64; ++c)
+                tma_load_2d_s(sb + c * (BK * 128), &tmB, &full_bar[stage], n0 + c * 64, k0);
+            }
           }
+          __syncwarp();
           if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (single thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer =====================
+    // The whole warp runs the (warp-uniform) loop and the waits; one elected lane issues the tcgen05
+    // instructions.  With a `lane == 0` branch around the loop every operand of UTCHMMA / UTCBAR lives in
+    // per-thread registers and the compiler wraps each instruction in an ELECT / R2UR / BRA.U.ANY waterfall
+    // loop (~80-100 issue cycles per MMA, close to the 128 cycles the MMA itself takes); here the operands
+    // are provably uniform (kernel parameters, loop counters, broadcast shuffles) and descriptors are a base
+    // plus an immediate.
+    {
+      const bool leader = elect_one();
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t smem0 = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
       const uint32_t idesc = make_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
       // Descriptor template per operand; only the start-address field changes per stage / k-step.
       const uint32_t a_lbo = p.a_mn ? BK * 128 : 16, b_lbo = p.b_mn ? BK * 128 : 16;
@@ -404,23 +418,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&tmem_empty[acc_stage], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc_stage * BN;
+        const uint32_t d_tmem = tm + acc_stage * BN;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint32_t sa = smem0 + stage * S::STAGE_BYTES;
           const uint32_t sb = sa + S::A_BYTES;
           const uint64_t adesc = make_smem_desc_sw128(sa, a_lbo, 1024);
           const uint64_t bdesc = make_smem_desc_sw128(sb, b_lbo, 1024);
+          if (leader) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            umma_bf16(d_tmem, adesc + k * a_kstep, bdesc + k * b_kstep, idesc,
-                      (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              umma_bf16(d_tmem, adesc + k * a_kstep, bdesc + k * b_kstep, idesc,
+                        (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs retire
+            if (kb == k_blocks - 1) umma_commit(&tmem_full[acc_stage]);  // accumulator ready for the epilogue
           }
-          umma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs retire
+          __syncwarp();
           if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc_stage]);  // accumulator ready for the epilogue
         if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
       }
     }
@@ -528,8 +545,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
+    // ===================== TMA producer (both CTAs; whole warp walks the loop, one elected lane issues) =====================
+    {
+      const bool issuer = elect_one();
+      const uint32_t smem0 = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
@@ -540,32 +559,38 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int n0 = p.swiglu_F ? nb * BNH + rank * p.swiglu_F : nb * BN + rank * BNH;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * S::STAGE_BYTES;
-          uint8_t* sb = sa + S::A_BYTES;
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);
+          const uint32_t sa = smem0 + stage * S::STAGE_BYTES;
+          const uint32_t sb = sa + S::A_BYTES;
           const uint32_t fb = mapa_u32(&full_bar[stage], 0);
           const int k0 = kb * BK;
-          if (!p.a_mn) {
-            tma_load_2d_2sm(sa, &tmA, fb, k0, m0);
-          } else {
+          if (issuer) {
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);
+            if (!p.a_mn) {
+              tma_load_2d_2sm_s(sa, &tmA, fb, k0, m0);
+            } else {
 #pragma unroll
-            for (int c = 0; c < BM / 64; ++c)
-              tma_load_2d_2sm(sa + c * (BK * 128), &tmA, fb, m0 + c * 64, k0);
-          }
-          if (!p.b_mn) {
-            tma_load_2d_2sm(sb, &tmB, fb, k0, n0);
-          } else {
+              for (int c = 0; c < BM / 64; ++c)
+                tma_load_2d_2sm_s(sa + c * (BK * 128), &tmA, fb, m0 + c * 64, k0);
+            }
+            if (!p.b_mn) {
+              tma_load_2d_2sm_s(sb, &tmB, fb, k0, n0);
+            } else {
 #pragma unroll
-            for (int c = 0; c < BNH / 64; ++c)
-              tma_load_2d_2sm(sb + c * (BK * 128), &tmB, fb, n0 + c * 64, k0);
+              for (int c = 0; c < BNH / 64; ++c)
+                tma_load_2d_2sm_s(sb + c * (BK * 128), &tmB, fb, n0 + c * 64, k0);
+            }
           }
+          __syncwarp();
           if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA, single thread) =====================
-    if (leader && lane == 0) {
+    // ===================== MMA issuer (leader CTA; whole warp, one elected lane issues) =====================
+    if (leader) {
+      const bool issuer = elect_one();
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t smem0 = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
       const uint32_t idesc = make_idesc_bf16(2 * BM, BN, p.a_mn, p.b_mn);
       const uint32_t a_lbo = p.a_mn ? BK * 128 : 16, b_lbo = p.b_mn ? BK * 128 : 16;
       const uint32_t a_kstep = p.a_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
@@ -577,23 +602,26 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         mbar_wait(&tmem_empty[acc_stage], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc_stage * BN;
+        const uint32_t d_tmem = tm + acc_stage * BN;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint32_t sa = smem0 + stage * S::STAGE_BYTES;
           const uint32_t sb = sa + S::A_BYTES;
           const uint64_t adesc = make_smem_desc_sw128(sa, a_lbo, 1024);
           const uint64_t bdesc = make_smem_desc_sw128(sb, b_lbo, 1024);
+          if (issuer) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            umma_bf16_2sm(d_tmem, adesc + k * a_kstep, bdesc + k * b_kstep, idesc,
-                          (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              umma_bf16_2sm(d_tmem, adesc + k * a_kstep, bdesc + k * b_kstep, idesc,
+                            (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit_2sm(&empty_bar[stage], 3);  // frees this stage in both CTAs
+            if (kb == k_blocks - 1) umma_commit_2sm(&tmem_full[acc_stage], 3);
           }
-          umma_commit_2sm(&empty_bar[stage], 3);  // frees this stage in both CTAs
+          __syncwarp();
           if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit_2sm(&tmem_full[acc_stage], 3);
         if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
       }
     }
