@@ -108,11 +108,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // broadcast shuffles make the TMEM / shared-memory bases provably warp-uniform: the elected lane of warp 0
+  // then issues UTCHMMA / UTMALDG from uniform registers (a `tid == 0` branch makes the compiler wrap every
+  // such instruction in an ELECT / R2UR / BRA.U.ANY waterfall loop, ~100 issue cycles per MMA)
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
   constexpr uint32_t C_S = 0, C_DP = 64, C_DQ = 128, C_DV = 256, C_DK = 384;
+  const bool warp0 = (threadIdx.x >> 5) == 0;  // warp-uniform
 
-  const uint32_t sb = smem_u32(smem);
+  const uint32_t sb = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
   const uint32_t sK = sb + S::OFF_K, sV = sb + S::OFF_V, sQ = sb + S::OFF_Q, sDO = sb + S::OFF_DO,
                  sP = sb + S::OFF_P, sDS = sb + S::OFF_DS;
   constexpr uint32_t idesc_sdp = make_idesc_bf16(128, BW_Q, 0, 0);   // [keys x q]
@@ -180,20 +184,26 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   };
 
   if (n_iter > 0) {
-    if (tid == 0) {
-      mbar_arrive_expect_tx(kv_full, 2 * S::KV_BYTES);
+    if (warp0) {
+      if (elect_one()) {
+        mbar_arrive_expect_tx(kv_full, 2 * S::KV_BYTES);
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        tma_load_3d(smem + S::OFF_K + c * (BW_KEYS * 128), &tmK, kv_full, h * BW_HD + c * 64, key0, b);
-        tma_load_3d(smem + S::OFF_V + c * (BW_KEYS * 128), &tmV, kv_full, h * BW_HD + c * 64, key0, b);
+        for (int c = 0; c < 2; ++c) {
+          tma_load_3d(smem + S::OFF_K + c * (BW_KEYS * 128), &tmK, kv_full, h * BW_HD + c * 64, key0, b);
+          tma_load_3d(smem + S::OFF_V + c * (BW_KEYS * 128), &tmV, kv_full, h * BW_HD + c * 64, key0, b);
+        }
+        load_q(i_start);
       }
-      load_q(i_start);
+      __syncwarp();
       mbar_wait(kv_full, 0);
       mbar_wait(&q_full[i_start & 1], 0);
       tc_fence_after();
-      issue_sdp(i_start);
-      umma_commit(sdp_bar);
-      if (n_iter > 1) load_q(i_start + 1);
+      if (elect_one()) {
+        issue_sdp(i_start);
+        umma_commit(sdp_bar);
+        if (n_iter > 1) load_q(i_start + 1);
+      }
+      __syncwarp();
     }
     load_stats(i_start);
   }
@@ -245,27 +255,34 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                        pack_bf16x2(dv[6], dv[7]));
       }
     }
-    if (tid == 0) bulk_wait_group_read0();  // the previous tile's reduce has drained the dQ staging
+    if (warp0 && elect_one()) bulk_wait_group_read0();  // the previous tile's reduce has drained the dQ staging
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (warp0) {
       tc_fence_after();
-      issue_grads(i, it == 0);
-      umma_commit(grad_bar);
+      if (elect_one()) {
+        issue_grads(i, it == 0);
+        umma_commit(grad_bar);
+      }
+      __syncwarp();
       if (it + 1 < n_iter) {
         mbar_wait(&q_full[(i + 1) & 1], ((it + 1) >> 1) & 1);
         tc_fence_after();
-        issue_sdp(i + 1);
-        umma_commit(sdp_bar);
+        if (elect_one()) {
+          issue_sdp(i + 1);
+          umma_commit(sdp_bar);
+        }
+        __syncwarp();
       }
     }
-    __syncwarp();
     // dQ^T readout: lanes = head dims, columns = queries -> coalesced fp32 reductions
     mbar_wait(grad_bar, it & 1);
     tc_fence_after();
-    if (tid == 0 && it + 2 < n_iter) load_q(i + 2);  // stage st is free: its MMAs have retired
-    __syncwarp();
+    if (warp0) {
+      if (it + 2 < n_iter && elect_one()) load_q(i + 2);  // stage st is free: its MMAs have retired
+      __syncwarp();
+    }
     {
       float* stage = reinterpret_cast<float*>(smem + S::OFF_DQ) + warp * 32 + lane;  // column d
       uint32_t dq[16];
@@ -278,12 +295,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc_fence_before();
     fence_proxy_async_smem();
     __syncthreads();
-    if (tid == 0 && !(p.debug_skip & 1)) {
-      tma_reduce_add_3d(&tmDQ, smem + S::OFF_DQ, h * BW_HD, qbase, b);  // rows >= T are clipped
-      bulk_commit_group();
+    if (warp0) {
+      if (!(p.debug_skip & 1) && elect_one()) {
+        tma_reduce_add_3d(&tmDQ, smem + S::OFF_DQ, h * BW_HD, qbase, b);  // rows >= T are clipped
+        bulk_commit_group();
+      }
+      __syncwarp();
     }
   }
-  if (tid == 0) bulk_wait_group0();
+  if (warp0 && elect_one()) bulk_wait_group0();
 
   // ---- epilogue: dV, dK -> bf16
   if (n_iter > 0) {

@@ -92,47 +92,62 @@ decode_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // producer and issuer warps run warp-uniform with one elected lane issuing, so UTMALDG / UTCHMMA take their
+  // operands from uniform registers (no ELECT / R2UR waterfall loop per instruction; the MMAs here are 8-32 cycles)
   if (warp == 0) {
-    if (lane == 0) {
-      // first ring pass: weights now, activations after the previous kernel has finished
-      const int first = min(nkb, S::STAGES);
+    const bool leader = elect_one();
+    const uint32_t smem0 = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+    // first ring pass: weights now, activations after the previous kernel has finished
+    const int first = min(nkb, S::STAGES);
+    if (leader) {
       for (int i = 0; i < first; ++i) {
         mbar_arrive_expect_tx(&full_bar[i], S::W_BYTES + S::X_BYTES);
-        tma_load_2d(smem + i * S::STAGE_BYTES, &tmW, &full_bar[i], (kb_begin + i) * DG_BK, n0);
-      }
-      asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-      asm volatile("griddepcontrol.wait;" ::: "memory");
-      for (int i = 0; i < first; ++i)
-        tma_load_2d(smem + i * S::STAGE_BYTES + S::W_BYTES, &tmX, &full_bar[i], (kb_begin + i) * DG_BK, 0);
-      int stage = 0;
-      uint32_t phase = 1;  // the first pass filled every slot once
-      for (int i = first; i < nkb; ++i) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sw = smem + stage * S::STAGE_BYTES;
-        mbar_arrive_expect_tx(&full_bar[stage], S::W_BYTES + S::X_BYTES);
-        tma_load_2d(sw, &tmW, &full_bar[stage], (kb_begin + i) * DG_BK, n0);
-        tma_load_2d(sw + S::W_BYTES, &tmX, &full_bar[stage], (kb_begin + i) * DG_BK, 0);
-        if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+        tma_load_2d_s(smem0 + i * S::STAGE_BYTES, &tmW, &full_bar[i], (kb_begin + i) * DG_BK, n0);
       }
     }
+    __syncwarp();
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (leader) {
+      for (int i = 0; i < first; ++i)
+        tma_load_2d_s(smem0 + i * S::STAGE_BYTES + S::W_BYTES, &tmX, &full_bar[i], (kb_begin + i) * DG_BK, 0);
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 1;  // the first pass filled every slot once
+    for (int i = first; i < nkb; ++i) {
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      const uint32_t sw = smem0 + stage * S::STAGE_BYTES;
+      if (leader) {
+        mbar_arrive_expect_tx(&full_bar[stage], S::W_BYTES + S::X_BYTES);
+        tma_load_2d_s(sw, &tmW, &full_bar[stage], (kb_begin + i) * DG_BK, n0);
+        tma_load_2d_s(sw + S::W_BYTES, &tmX, &full_bar[stage], (kb_begin + i) * DG_BK, 0);
+      }
+      __syncwarp();
+      if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+    }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(DG_BM, NB < 16 ? 16 : NB, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int i = 0; i < nkb; ++i) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t sw = smem_u32(smem + stage * S::STAGE_BYTES);
-        const uint64_t adesc = make_smem_desc_sw128(sw, 16, 1024);
-        const uint64_t bdesc = make_smem_desc_sw128(sw + S::W_BYTES, 16, 1024);
+    const bool leader = elect_one();
+    const uint32_t smem0 = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+    constexpr uint32_t idesc = make_idesc_bf16(DG_BM, NB < 16 ? 16 : NB, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int i = 0; i < nkb; ++i) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint32_t sw = smem0 + stage * S::STAGE_BYTES;
+      const uint64_t adesc = make_smem_desc_sw128(sw, 16, 1024);
+      const uint64_t bdesc = make_smem_desc_sw128(sw + S::W_BYTES, 16, 1024);
+      if (leader) {
 #pragma unroll
         for (int k = 0; k < DG_BK / 16; ++k)
-          umma_bf16(tmem_base, adesc + k * 2, bdesc + k * 2, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          umma_bf16(tm, adesc + k * 2, bdesc + k * 2, idesc, (i > 0 || k > 0) ? 1u : 0u);
         umma_commit(&empty_bar[stage]);
-        if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+        if (i == nkb - 1) umma_commit(acc_full);
       }
-      umma_commit(acc_full);
+      __syncwarp();
+      if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
     }
   }
 
