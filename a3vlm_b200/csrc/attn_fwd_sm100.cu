@@ -520,38 +520,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
-// Reports the alignment of the dynamic shared-memory window for a launch with `bytes` of it (one warp).
-__global__ void fa_smem_probe_kernel(unsigned int* out) {
-  extern __shared__ __align__(1024) uint8_t probe_smem[];
-  if (threadIdx.x == 0) *out = smem_u32(probe_smem) & 1023u;
-}
-
-// Once per device: the kernels place 128-byte-swizzled tiles at fixed offsets of the dynamic shared-memory
-// base and have no room for alignment slack at head_dim 128 (5 x 32 KB ring + 64 KB Q = 224 of 227 KB).
-static int fa_check_smem_alignment() {
-  static int state[64];  // 0 unknown, 1 aligned, 2 misaligned
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return set_error(A3_ERR_CUDA, "cudaGetDevice failed");
-  if (state[dev] == 0) {
-    unsigned int* d = nullptr;
-    unsigned int h = 1;
-    if (cudaMalloc(&d, sizeof(unsigned int)) != cudaSuccess) return set_error(A3_ERR_CUDA, "a3_attn_fwd: probe allocation failed");
-    fa_smem_probe_kernel<<<1, 32, 1024>>>(d);
-    cudaError_t e = cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost);
-    cudaFree(d);
-    if (e != cudaSuccess) return set_error(A3_ERR_CUDA, cudaGetErrorString(e));
-    state[dev] = h == 0 ? 1 : 2;
-  }
-  if (state[dev] == 2)
-    return set_error(A3_ERR_UNSUPPORTED, "a3_attn_fwd: dynamic shared memory is not 1024-byte aligned on this device / driver");
-  return A3_OK;
-}
-
 template <int HD>
 static int launch_attn_fwd(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                            const FaParams& p, cudaStream_t stream) {
   using S = FaSmem<HD>;
-  if (int rc = fa_check_smem_alignment()) return rc;
+  if (int rc = check_dyn_smem_alignment("a3_attn_fwd")) return rc;
   if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&attn_fwd_kernel<HD>), S::TOTAL)) return rc;
   const int grid = p.n_items < num_sms() ? p.n_items : num_sms();
   attn_fwd_kernel<HD><<<grid, FA_THREADS, S::TOTAL, stream>>>(tmQ, tmK, tmV, p);

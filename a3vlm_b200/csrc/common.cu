@@ -44,6 +44,36 @@ int ensure_dyn_smem(const void* kernel, size_t bytes) {
   return A3_OK;
 }
 
+// Reports the alignment of the dynamic shared-memory window of a launch (one thread).
+__global__ void smem_probe_kernel(unsigned int* out) {
+  extern __shared__ __align__(1024) uint8_t probe_smem[];
+  *out = static_cast<unsigned int>(__cvta_generic_to_shared(probe_smem)) & 1023u;
+}
+
+int check_dyn_smem_alignment(const char* who) {
+  static std::atomic<int> state[64];  // 0 unknown, 1 aligned, 2 misaligned
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return set_error(A3_ERR_CUDA, "cudaGetDevice failed");
+  int st = state[dev].load(std::memory_order_relaxed);
+  if (st == 0) {
+    unsigned int* d = nullptr;
+    unsigned int h = 1;
+    if (cudaMalloc(&d, sizeof(unsigned int)) != cudaSuccess) return set_error(A3_ERR_CUDA, "shared-memory probe: allocation failed");
+    smem_probe_kernel<<<1, 1, 1024>>>(d);
+    cudaError_t e = cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return set_error(A3_ERR_CUDA, cudaGetErrorString(e));
+    st = h == 0 ? 1 : 2;
+    state[dev].store(st, std::memory_order_relaxed);
+  }
+  if (st == 2) {
+    char buf[160];
+    std::snprintf(buf, sizeof(buf), "%s: dynamic shared memory is not 1024-byte aligned on this device / driver", who);
+    return set_error(A3_ERR_UNSUPPORTED, buf);
+  }
+  return A3_OK;
+}
+
 static std::atomic<int> g_sm_limit{0};
 
 int num_sms() {

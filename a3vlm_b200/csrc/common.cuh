@@ -14,6 +14,10 @@ int check_launch(const char* what);
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per DEVICE: remembered per (kernel, current device),
 // so a process that drives several GPUs configures each of them (raised only, never lowered).
 int ensure_dyn_smem(const void* kernel, size_t bytes);
+// The attention kernels place 128-byte-swizzled tiles at fixed offsets of the dynamic shared-memory base and have
+// no room for alignment slack (224 of the 227 KB are tiles).  Probed once per device with a one-thread kernel
+// (the first call synchronises); A3_ERR_UNSUPPORTED if the base is not 1024-byte aligned.
+int check_dyn_smem_alignment(const char* who);
 int num_sms();     // SMs the persistent kernels size their grids for (a3_set_sm_limit)
 int device_sms();  // physical SM count
 

@@ -122,8 +122,9 @@ def test_activation_recompute_is_bit_identical(level):
     keep[lo:lo + n] = False
     assert torch.equal(g0[keep], g1[keep]), (g0[keep].float() - g1[keep].float()).abs().max()
     e0, e1 = g0[lo:lo + n].float(), g1[lo:lo + n].float()
-    # (a few bf16 roundings of the larger operand: the order of up to B * T partial sums differs)
-    assert bool(((e0 - e1).abs() <= 2.0 ** -6 * torch.maximum(e0.abs(), e1.abs()) + 1e-30).all()), (e0 - e1).abs().max()
+    # (a few bf16 roundings at the magnitude of the CONTRIBUTIONS -- partial sums of opposite sign may cancel, so
+    # the bound is relative to the largest entry of the table, not to the element itself)
+    assert bool(((e0 - e1).abs() <= 2.0 ** -6 * e0.abs().max()).all()), ((e0 - e1).abs().max(), e0.abs().max())
     assert held1 < held0 and held1 == (7 if level == 2 else 3 + 4 * a.n_layers)
 
 
