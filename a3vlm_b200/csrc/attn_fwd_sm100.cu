@@ -107,10 +107,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* p_half = bars + 14;        // [2]  softmax group s (4 warps) -> MMA_s: keys [0,64) of P_s(j) are in TMEM
   uint64_t* p_full = bars + 16;        // [2]  softmax group s (4 warps) -> MMA_s: all of P_s(j)
   uint64_t* pv_done = bars + 18;       // [2]  MMA_s (commit) -> softmax group s (rescale) / epilogue: PV_s(j) retired
-  uint64_t* fin = bars + 20;           // [2][2] softmax group s (4 warps) -> epilogue: l, m of the item final; by item
+  uint64_t* fin = bars + 20;           // [2][2] softmax group s (128 threads) -> epilogue: l, m of the item final; by item
                                        //      parity, because a softmax group may finish the NEXT item (one key
                                        //      tile: its only S needs no O) before the epilogue has seen this one
-  uint64_t* o_free = bars + 24;        // [2]  epilogue (4 warps) -> MMA_s: O_s of the item has been read out
+  uint64_t* o_free = bars + 24;        // [2]  epilogue (128 threads) -> MMA_s / softmax s: O_s, l, m of the item have been read
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -150,9 +150,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&p_half[i], 4);
       mbar_init(&p_full[i], 4);
       mbar_init(&pv_done[i], 1);
-      mbar_init(&fin[2 * i], 4);
-      mbar_init(&fin[2 * i + 1], 4);
-      mbar_init(&o_free[i], 4);
+      mbar_init(&fin[2 * i], FA_BM);      // every softmax thread releases its own l, m
+      mbar_init(&fin[2 * i + 1], FA_BM);
+      mbar_init(&o_free[i], FA_BM);       // every epilogue thread, after it has read l, m and its O row
     }
     for (int i = 0; i < NS; ++i) {
       mbar_init(&kv_full[i], 1);
@@ -286,8 +286,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (c_item > 0) mbar_wait(&o_free[s], (c_item - 1) & 1);
       s_l[s * FA_BM + t] = l_run;
       s_m[s * FA_BM + t] = m_use;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&fin[2 * s + (c_item & 1)]);
+      mbar_arrive(&fin[2 * s + (c_item & 1)]);
       ++c_item;
     }
   } else if (warp < 12) {
@@ -334,8 +333,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
           if (c == HD / 32 - 1 && n > 0) {  // O_s is in registers: the next item's first PV_s may overwrite it
             tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&o_free[s]);
+            mbar_arrive(&o_free[s]);
           }
           if (row_ok) {
 #pragma unroll

@@ -278,6 +278,7 @@ cross_entropy_kernel(__nv_bfloat16* __restrict__ logits, long long ld,
                      const long long* __restrict__ labels, float* __restrict__ row_loss,
                      const int* __restrict__ count, int V, float grad_scale, int want_grad) {
   __shared__ float red[32];
+  __shared__ float s_label_logit;
   const int row = blockIdx.x;
   __nv_bfloat16* lr = logits + row * ld;
   const long long label = labels[row];
@@ -304,10 +305,18 @@ cross_entropy_kernel(__nv_bfloat16* __restrict__ logits, long long ld,
     ld8(lr + c * 8, v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) sum += __expf(v[j] - mx);
+    // the label's logit is captured HERE, by the thread that owns its chunk: the gradient pass below overwrites the
+    // row in place, so reading lr[label] after the reduction races with that store (found by compute-sanitizer:
+    // the loss came out 1 % off when the instrumented timing let the store win)
+    if (c == static_cast<int>(label >> 3)) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j == static_cast<int>(label & 7)) s_label_logit = v[j];
+    }
   }
-  sum = block_sum_m(sum, red);
+  sum = block_sum_m(sum, red);  // (block barriers inside: s_label_logit is visible afterwards)
   const float lse = mx + logf(sum);
-  if (threadIdx.x == 0) row_loss[row] = lse - __bfloat162float(lr[label]);
+  if (threadIdx.x == 0) row_loss[row] = lse - s_label_logit;
   if (want_grad) {
     const float scale = grad_scale / (float)max(*count, 1);
     const float inv = 1.f / sum;

@@ -483,14 +483,14 @@ def main():
                       f"{r['tflops']:.0f} TFLOP/s", file=sys.stderr)
         ach = tot_fl / (tot_ms / 1e3) / 1e12
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "r01e_gemm_traffic.json")  # ncu dram bytes of the same launches
+        tp = os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")  # ncu dram bytes of the same launches
         if os.path.exists(tp) and (B, T, S, args.model) == (8, 256, 336, "7b"):
             traffic = json.load(open(tp))["dram_bytes_per_launch"]
         roof = {"bound": "tensor", "kernel": "gemm2_bf16_kernel / gemm_bf16_kernel (tcgen05 cta_group::2 / ::1, TMEM, TMA; incl. fused gated-SiLU epilogues)", "achieved": ach, "peak": pk["bf16"],
                 "unit": "TFLOP/s", "frac": ach / pk["bf16"], "peak_source": pk["src"] + " (burst; sustained %s)" % pk["bf16_sustained"],
                 "launches_per_step": len(recs), "avg_launch_ms": tot_ms / len(recs), "gemm_ms_per_step": tot_ms,
                 "gemm_share_of_step": tot_ms / ms_step, "flops_per_launch": tot_fl / len(recs), "traffic": traffic,
-                "traffic_note": "ncu dram__bytes_read+write per GEMM launch (profiles/r01e_gemm_traffic.json), bytes",
+                "traffic_note": "ncu dram__bytes_read+write per GEMM launch (profiles/r02_gemm_traffic.json), bytes",
                 "by_shape": by_shape[:12]}
 
     if rank != 0:
