@@ -154,6 +154,15 @@ int make_tmap_3d_bf16(CUtensorMap* tm, const void* ptr, uint64_t dim0, uint64_t 
   return encode(tm, ptr, 3, dims, strides, box);
 }
 
+int make_tmap_4d_bf16(CUtensorMap* tm, const void* ptr, const uint64_t (&dims)[4], const uint64_t (&strides_bytes)[3],
+                      const uint32_t (&box)[4], int swizzle32) {
+  cuuint64_t d[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t st[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
+  cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+  return encode(tm, ptr, 4, d, st, bx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                swizzle32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
 int make_tmap_3d_f32_linear(CUtensorMap* tm, const void* ptr, uint64_t dim0, uint64_t dim1,
                             uint64_t dim2, uint64_t stride1_bytes, uint64_t stride2_bytes,
                             uint32_t box0, uint32_t box1, uint32_t box2) {

@@ -29,6 +29,11 @@ int make_tmap_3d_bf16(CUtensorMap* tm, const void* ptr, uint64_t dim0, uint64_t 
                       uint64_t dim2, uint64_t stride1_bytes, uint64_t stride2_bytes,
                       uint32_t box0, uint32_t box1, uint32_t box2);
 
+// 4-D bf16 tensor map with 128-byte (or 32-byte) swizzle (dims[0] contiguous; strides of dims 1..3 in bytes,
+// multiples of 16; box origins must be 16-byte aligned in dim 0).
+int make_tmap_4d_bf16(CUtensorMap* tm, const void* ptr, const uint64_t (&dims)[4], const uint64_t (&strides_bytes)[3],
+                      const uint32_t (&box)[4], int swizzle32 = 0);
+
 // 3-D fp32 tensor map without swizzle (row-major smem box), used for TMA reduce-add stores.
 int make_tmap_3d_f32_linear(CUtensorMap* tm, const void* ptr, uint64_t dim0, uint64_t dim1,
                             uint64_t dim2, uint64_t stride1_bytes, uint64_t stride2_bytes,

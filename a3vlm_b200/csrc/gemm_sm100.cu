@@ -60,6 +60,19 @@ struct GemmParams {
   // k-block; the remaining rows of the 128-row MMA tile read stale shared memory and their
   // accumulator rows are never stored.
   int a_rows;
+  // im2col-free patch embedding (single-CTA kernel, a3_vit_patch_embed): A is never materialised.  The "A" tensor
+  // map is a 4-D view of the bf16 image whose rows were cast with every patch column on a 16-element pitch
+  // (a3_vit_pad_cast), {x: 16 g, ky: patch, py: grid, channel-of-image: 3B}, 32-byte swizzle.  One TMA box
+  // {16 x, 1 ky, 8 py, 1} lands as one 8-row x 32-byte atom of a K-major SW32 operand: row = patch (px fixed, 8 py),
+  // 16 k = the kx of one kernel row (kx >= patch is zero padding in both operands; ky >= patch is out of bounds of
+  // the map: zero fill).  (Measured: with a swizzle mode TMA puts every inner box row on its own swizzle-span line,
+  // so a {16, 4, 8} box does NOT give 128-byte K rows; the 32-byte mode with one kernel row per box does.)  A stage
+  // holds four such [128 rows][32 B] sub-tiles, one per k-step of the MMA, whose A descriptor is SW32 while B (the
+  // weights) stays SW128.  A 128-row tile = 16 x 4 boxes per k-block;
+  // k-block kb covers channel kb / 4, kernel rows 4 (kb % 4) .. +3.  Rows are ordered (image, px, py-group, py) and
+  // the epilogue writes accumulator row r to output row image * g^2 + py * g + px.
+  int patch_g;      // grid side g (0: off)
+  int patch_p;      // patch size (<= 16)
 };
 
 template <int BN>
@@ -327,7 +340,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int m_blocks = (p.M + BM - 1) / BM;
+  // patch mode: accumulator rows run over (image, px, py-group, 8 py), i.e. M is padded to whole groups
+  const int m_rows = p.patch_g ? (p.M / (p.patch_g * p.patch_g)) * p.patch_g * ((p.patch_g + 7) >> 3) * 8 : p.M;
+  const int m_blocks = (m_rows + BM - 1) / BM;
   const int n_blocks = (p.N + BN - 1) / BN;
   const int k_blocks = (p.K + BK - 1) / BK;
   const int num_tiles = m_blocks * n_blocks;
@@ -374,7 +389,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int k0 = kb * BK;
           if (leader) {
             mbar_arrive_expect_tx(&full_bar[stage], p.a_rows * (BK * 2) + S::B_BYTES);
-            if (!p.a_mn) {
+            if (p.patch_g) {
+              const int gpp = (p.patch_g + 7) >> 3;         // 8-row py groups per patch column
+              const int gpi = p.patch_g * gpp;              // groups per image
+#pragma unroll 2
+              for (int r8 = 0; r8 < BM / 8; ++r8) {
+                const int G = (m0 >> 3) + r8;
+                const int img = G / gpi, rem = G - img * gpi;
+                const int px = rem / gpp, pyg = rem - px * gpp;
+                // groups past the last image have channel coordinate >= 3B: zero fill, byte count unchanged
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)  // sub-tile kk = kernel row 4 (kb % 4) + kk: [128 rows][32 B], atom r8
+                  tma_load_4d_s(sa + kk * (BM * 32) + r8 * 256, &tmA, &full_bar[stage], px * 16, (kb & 3) * 4 + kk,
+                                pyg * 8, img * 3 + (kb >> 2));
+              }
+            } else if (!p.a_mn) {
               tma_load_2d_s(sa, &tmA, &full_bar[stage], k0, m0);  // box {64 k, a_rows (128) rows}
             } else {
 #pragma unroll
@@ -424,12 +453,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tc_fence_after();
           const uint32_t sa = smem0 + stage * S::STAGE_BYTES;
           const uint32_t sb = sa + S::A_BYTES;
-          const uint64_t adesc = make_smem_desc_sw128(sa, a_lbo, 1024);
+          // patch mode: A is four SW32 sub-tiles of [128 rows][32 bytes], one per k-step
+          const uint64_t adesc = p.patch_g ? make_smem_desc_sw32(sa, 256) : make_smem_desc_sw128(sa, a_lbo, 1024);
+          const uint32_t a_step = p.patch_g ? (BM * 32) >> 4 : a_kstep;
           const uint64_t bdesc = make_smem_desc_sw128(sb, b_lbo, 1024);
           if (leader) {
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
-              umma_bf16(d_tmem, adesc + k * a_kstep, bdesc + k * b_kstep, idesc,
+              umma_bf16(d_tmem, adesc + k * a_step, bdesc + k * b_kstep, idesc,
                         (kb > 0 || k > 0) ? 1u : 0u);
             }
             umma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs retire
@@ -450,7 +481,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int mb, nb;
       tile_coords(tile, m_blocks, n_blocks, p.group_m, mb, nb);
-      const int row = mb * BM + ew * 32 + lane;
+      int row = mb * BM + ew * 32 + lane;
+      if (p.patch_g) {  // (image, px, py-group, py) -> image * g^2 + py * g + px; rows of padded groups are dropped
+        const int g = p.patch_g, gpp = (g + 7) >> 3, gpi = g * gpp;
+        const int G = row >> 3, img = G / gpi, rem = G - img * gpi;
+        const int px = rem / gpp, py = (rem - px * gpp) * 8 + (row & 7);
+        row = py < g ? (img * g + py) * g + px : p.M;
+      }
       const int n0 = nb * BN;
       mbar_wait(&tmem_full[acc_stage], acc_phase);
       tc_fence_after();
@@ -782,6 +819,7 @@ extern "C" int a3_gemm_bf16(const void* A, const void* B, void* C, int M, int N,
   p.group_m = gm_env > 0 ? gm_env : 16;
   p.swiglu_F = 0; p.C2 = nullptr; p.ldc2 = 0; p.dswiglu_gu = nullptr; p.ldgu = 0;
   p.a_rows = a_rows;
+  p.patch_g = 0; p.patch_p = 0;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (pair) return launch_gemm2(tmA, tmB, p, s);
   if (bn == 32) return launch_gemm<32>(tmA, tmB, p, s);
@@ -793,7 +831,7 @@ static void init_params(a3::GemmParams& p, int M, int N, int K) {
   p.C = nullptr; p.bias = nullptr; p.residual = nullptr; p.rope = nullptr; p.ldc = 0; p.ldr = 0;
   p.rope_cols = 0; p.rope_period = 1; p.rope_pos0 = 0; p.M = M; p.N = N; p.K = K; p.a_mn = 0; p.b_mn = 0;
   p.act = 0; p.out_fp32 = 0; p.accumulate = 0; p.alpha = 1.f; p.group_m = 16; p.swiglu_F = 0; p.C2 = nullptr;
-  p.ldc2 = 0; p.dswiglu_gu = nullptr; p.ldgu = 0; p.a_rows = a3::BM;
+  p.ldc2 = 0; p.dswiglu_gu = nullptr; p.ldgu = 0; p.a_rows = a3::BM; p.patch_g = 0; p.patch_p = 0;
 }
 
 extern "C" int a3_gemm_swiglu_bf16(const void* X, const void* W13, void* GU, void* Y, int M, int F, int K,
@@ -840,4 +878,47 @@ extern "C" int a3_gemm_dswiglu_bf16(const void* D, const void* W2, const void* G
   p.dswiglu_gu = reinterpret_cast<const __nv_bfloat16*>(GU); p.ldgu = ldgu;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   return pair ? launch_gemm2(tmA, tmB, p, s) : launch_gemm<256>(tmA, tmB, p, s);
+}
+
+/* im2col-free patch embedding: out[B * g^2][D] = conv(image, w) with kernel = stride = patch, no bias
+ * (open_clip conv1, reference LLM/llama_ens5.py:354-357).  image: the output of a3_vit_pad_cast, bf16
+ * [B][3][S][g][16]; w: [D][3 * 16 * 16] bf16, the (D, 3, patch, patch) kernel zero-padded to 16 x 16 windows
+ * (k = c * 256 + ky * 16 + kx). */
+extern "C" int a3_vit_patch_embed(const void* image, const void* w, void* out, int B, int S, int patch, int D,
+                                  long long ldo, void* stream) {
+  using namespace a3;
+  if (B <= 0) return A3_OK;
+  if (!image || !w || !out) return set_error(A3_ERR_ARG, "a3_vit_patch_embed: null operand");
+  if (patch <= 0 || patch > 16 || S % patch || (D & 7) || (ldo & 7) ||
+      ((reinterpret_cast<uintptr_t>(image) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(out)) & 15))
+    return set_error(A3_ERR_ARG, "a3_vit_patch_embed: patch <= 16, S % patch == 0, D % 8 == 0, 16-byte aligned pointers");
+  const int g = S / patch;
+  CUtensorMap tmA, tmB;
+  const uint64_t rowb = (uint64_t)g * 16 * 2;  // bytes of one padded pixel row
+  const uint64_t dims[4] = {(uint64_t)g * 16, (uint64_t)patch, (uint64_t)g, (uint64_t)3 * B};
+  const uint64_t strides[3] = {rowb, (uint64_t)patch * rowb, (uint64_t)S * rowb};
+  const uint32_t box[4] = {16, 1, 8, 1};
+  int rc = make_tmap_4d_bf16(&tmA, image, dims, strides, box, /*swizzle32=*/1);
+  if (rc != A3_OK) return rc;
+  const int K = 3 * 256;
+  const int bn = D <= 128 ? 128 : 256;
+  rc = encode_operand_map(&tmB, w, D, K, K, 0, bn);
+  if (rc != A3_OK) return rc;
+  GemmParams p;
+  init_params(p, B * g * g, D, K);
+  p.C = out; p.ldc = ldo;
+  p.patch_g = g; p.patch_p = patch;
+  // grid: tiles over the group-padded rows
+  const int m_rows = B * g * ((g + 7) / 8) * 8;
+  const int tiles = ((m_rows + BM - 1) / BM) * ((D + bn - 1) / bn);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (bn == 128) {
+    if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(&gemm_bf16_kernel<128>), GemmSmem<128>::TOTAL)) return e;
+    gemm_bf16_kernel<128><<<grid, 384, GemmSmem<128>::TOTAL, st>>>(tmA, tmB, p);
+  } else {
+    if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(&gemm_bf16_kernel<256>), GemmSmem<256>::TOTAL)) return e;
+    gemm_bf16_kernel<256><<<grid, 384, GemmSmem<256>::TOTAL, st>>>(tmA, tmB, p);
+  }
+  return check_launch("a3_vit_patch_embed");
 }

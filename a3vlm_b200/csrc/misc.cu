@@ -576,6 +576,66 @@ extern "C" int a3_vit_patchify(const void* image, int image_is_fp32, void* A, in
   return check_launch("a3_vit_patchify");
 }
 
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+  const long long n8 = n >> 3;
+  for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < n8; c += (long long)gridDim.x * blockDim.x) {
+    const float4 a = reinterpret_cast<const float4*>(in)[2 * c], b = reinterpret_cast<const float4*>(in)[2 * c + 1];
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    st8(out + c * 8, v);
+  }
+  if (blockIdx.x == 0)
+    for (long long i = (n8 << 3) + threadIdx.x; i < n; i += blockDim.x) out[i] = __float2bfloat16_rn(in[i]);
+}
+
+// NCHW image (fp32 or bf16) -> bf16 rows in which every `patch`-pixel group starts on a 16-element (32-byte)
+// boundary: out[(b, c)][y][px][16], kx >= patch zero.  This is the autocast cast of the conv input; the padding is
+// what lets a TMA box start at an arbitrary patch column (TMA needs a 16-byte aligned inner coordinate -- a raw
+// row of 14-pixel patches is 28-byte periodic: measured, cp.async.bulk.tensor traps on it).
+template <typename T>
+__global__ void vit_pad_cast_kernel(const T* __restrict__ in, __nv_bfloat16* __restrict__ out, int S, int patch,
+                                    long long rows) {
+  const int g = S / patch;
+  const long long total = rows * g;  // one thread per (row, px): 16 outputs
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / g;
+    const int px = (int)(i - r * g);
+    const T* src = in + r * S + px * patch;
+    float lo[8], hi[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      lo[k] = k < patch ? (float)src[k] : 0.f;
+      hi[k] = k + 8 < patch ? (float)src[k + 8] : 0.f;
+    }
+    __nv_bfloat16* dst = out + i * 16;
+    st8(dst, lo);
+    st8(dst + 8, hi);
+  }
+}
+
+extern "C" int a3_vit_pad_cast(const void* image, int image_is_fp32, void* out, int B, int S, int patch, void* stream) {
+  if (patch <= 0 || patch > 16 || S % patch) return set_error(A3_ERR_ARG, "a3_vit_pad_cast: patch <= 16, S % patch == 0");
+  if (B <= 0) return A3_OK;
+  const long long rows = (long long)B * 3 * S, total = rows * (S / patch);
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
+  if (image_is_fp32)
+    vit_pad_cast_kernel<float><<<(int)blocks, 256, 0, ST(stream)>>>(reinterpret_cast<const float*>(image), BFM(out), S, patch, rows);
+  else
+    vit_pad_cast_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, ST(stream)>>>(BF(image), BFM(out), S, patch, rows);
+  return check_launch("a3_vit_pad_cast");
+}
+
+extern "C" int a3_cast_f32_bf16(const float* in, void* out, long long n, void* stream) {
+  if (n <= 0) return A3_OK;
+  if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15)
+    return set_error(A3_ERR_ARG, "a3_cast_f32_bf16: 16-byte aligned pointers");
+  long long blocks = ((n >> 3) + 255) / 256;
+  if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
+  if (blocks < 1) blocks = 1;
+  cast_f32_bf16_kernel<<<(int)blocks, 256, 0, ST(stream)>>>(in, BFM(out), n);
+  return check_launch("a3_cast_f32_bf16");
+}
+
 extern "C" int a3_vit_assemble_lnpre(const void* patch_out, const void* cls, const void* pos,
                                      const void* ln_w, const void* ln_b, void* x, int B, int Np, int D,
                                      float eps, void* stream) {

@@ -65,7 +65,8 @@ def build_layout(args, vis):
     if vis is not None:
         v, c = vis, "clip.visual."
         Wv = v.width
-        kpad = (3 * v.patch * v.patch + 7) // 8 * 8
+        # conv1 re-laid for the im2col-free patch embedding: every (c) window zero-padded to 16 x 16 -> K = 768
+        kpad = 3 * 16 * 16
         nodecay += [("visual_proj.0.bias", (D,)), ("visual_proj.1.bias", (D,))]
         frozen += [(c + "conv1.weight", (Wv, 3, v.patch, v.patch)), (c + "conv1_padded", (Wv, kpad)),
                    (c + "class_embedding", (Wv,)), (c + "positional_embedding", (v.tokens, Wv)),
@@ -336,14 +337,17 @@ class Engine:
         self.weights_changed()
 
     def weights_changed(self) -> None:
-        """Re-derive the kernel-side layouts from the reference-named weights (conv1 flattened to
-        K-major [1024][588 -> 592 zero-padded]) and invalidate fp32 masters."""
+        """Re-derive the kernel-side layouts from the reference-named weights (conv1 as a K-major [1024][768]
+        matrix, k = c * 256 + ky * 16 + kx, the 14 x 14 windows zero-padded to 16 x 16 for the TMA patch loader)
+        and invalidate fp32 masters."""
         if self.fz is not None:
             c = "clip.visual."
             v = self.vis
+            if v.patch > 16:
+                raise NotImplementedError("patch sizes above 16 are not built (CLIP ViT-L/14)")
             pad = self.fz.views[c + "conv1_padded"]
             pad.zero_()
-            pad[:, :3 * v.patch * v.patch] = self.fz.views[c + "conv1.weight"].reshape(v.width, -1)
+            pad.view(v.width, 3, 16, 16)[:, :, :v.patch, :v.patch] = self.fz.views[c + "conv1.weight"]
         self.master = None
 
     # ------------------------------------------------------------------------------------ workspaces
@@ -351,7 +355,7 @@ class Engine:
         v, D, dev = self.vis, self.args.dim, self.device
         g2, N, Wv = v.grid * v.grid, v.tokens, v.width
         e = lambda *s, dt=bf16: torch.empty(*s, device=dev, dtype=dt)
-        ws = {"A": e(B * g2, self.kpad), "po": e(B * g2, Wv), "x": e(B * N, Wv), "y": e(B * N, Wv),
+        ws = {"img16": e(B, 3, v.image_size, v.grid * 16), "po": e(B * g2, Wv), "x": e(B * N, Wv), "y": e(B * N, Wv),
               "qkv": e(B * N, 3 * Wv), "o": e(B * N, Wv), "fc": e(B * N, v.mlp), "feats": e(B * N, Wv),
               "pre": e(B * N, D), "tok": e(B * N, D), "mean": e(B * N, dt=torch.float32),
               "rstd": e(B * N, dt=torch.float32)}
@@ -395,13 +399,14 @@ class Engine:
             im = im.contiguous()
             if self.views == 5:  # [global bicubic | TL | TR | BL | BR] x B, view-major (llama_ens5.py:383-385)
                 ops.build_views(im, vw["views"][s * 5 * B0:(s + 1) * 5 * B0], B0, v.image_size)
-            else:
-                ops.vit_patchify(im, vw["A"][s * B0 * g2:(s + 1) * B0 * g2], B0, v.image_size, v.patch, self.kpad)
+            else:  # the autocast cast of the conv input, patch columns on a 16-element pitch for the TMA loader
+                ops.vit_pad_cast(im, vw["img16"][s * B0:(s + 1) * B0], B0, v.image_size, v.patch)
         B = len(streams) * self.views * B0
         if self.views == 5:
-            ops.vit_patchify(vw["views"], vw["A"], B, v.image_size, v.patch, self.kpad)
+            ops.vit_pad_cast(vw["views"], vw["img16"], B, v.image_size, v.patch)
         act = ops.ACT_QUICKGELU if v.quick_gelu else ops.ACT_GELU
-        ops.gemm(vw["A"], f[c + "conv1_padded"], vw["po"])
+        # conv1 without im2col: 4-D TMA boxes over the NCHW pixels land in the UMMA layout (a3_vit_patch_embed)
+        ops.vit_patch_embed(vw["img16"], f[c + "conv1_padded"], vw["po"], B, v.image_size, v.patch)
         ops.vit_assemble_lnpre(vw["po"], f[c + "class_embedding"], f[c + "positional_embedding"],
                                f[c + "ln_pre.weight"], f[c + "ln_pre.bias"], vw["x"], B, g2, Wv, v.ln_eps)
         x, y, qkv, o, fc = vw["x"], vw["y"], vw["qkv"], vw["o"], vw["fc"]

@@ -121,9 +121,7 @@ class MetaModel(nn.Module):
                 raise ValueError("Cannot determine llama_type")
             with open(mj, "r") as f:
                 llama_type = json.load(f)["llama_type"]
-        if llama_type in ("llama_ens5", "llama_ens5_2images"):
-            # a checkpoint written by the reference's own plugin: loadable only if it was built ViT-only
-            ckpt.check_vision_branch(pretrained_path, 1024)
+        from_reference_plugin = llama_type in ("llama_ens5", "llama_ens5_2images")
         llama_type = {"llama_ens5": "llama_b200", "llama_ens5_2images": "llama_b200_2images"}.get(llama_type, llama_type)
         if llama_config is None:
             cj = os.path.join(last, "config.json")
@@ -145,6 +143,9 @@ class MetaModel(nn.Module):
             # its config.json and loads without one; otherwise as the reference (meta.py:189-193)
             if tokenizer_path is None and not any(c.get("vocab_size", -1) > 0 for c in cfgs):
                 raise FileNotFoundError("No tokenizer available")
+        if from_reference_plugin:
+            # a checkpoint written by the reference's own plugin: loadable only if it was built ViT-only
+            ckpt.check_vision_branch(pretrained_path, 1024)
         with torch.cuda.device(torch.device(device) if str(device) != "cuda" else torch.cuda.current_device()):
             model = cls(llama_type, cfgs, tokenizer_path, with_visual, max_seq_len, max_batch_size=max_batch_size)
         print(f"Loading pretrained weights from {pretrained_path} ...")

@@ -317,6 +317,29 @@ def vit_patchify(image, out, B, S, patch, Kpad):
     return out
 
 
+def vit_pad_cast(image, out, B, S, patch):
+    """NCHW fp32 / bf16 image -> bf16 [B][3][S][S/patch][16] (patch columns on a 16-element pitch) for vit_patch_embed."""
+    assert image.is_contiguous() and image.dtype in (torch.float32, bf16) and out.dtype == bf16 and out.is_contiguous()
+    assert out.numel() == B * 3 * S * (S // patch) * 16
+    rc = _L().a3_vit_pad_cast(_p(image), int(image.dtype == torch.float32), _p(out), B, S, patch, _st())
+    _lib.check(rc, "a3_vit_pad_cast")
+    return out
+
+
+def vit_patch_embed(image_padded, w768, out, B, S, patch):
+    """conv1 (kernel = stride = patch) as one tcgen05 GEMM fed by 4-D TMA boxes over the padded bf16 image."""
+    assert image_padded.dtype == bf16 and image_padded.is_contiguous() and w768.is_contiguous() and out.stride(1) == 1
+    rc = _L().a3_vit_patch_embed(_p(image_padded), _p(w768), _p(out), B, S, patch, w768.shape[0], out.stride(0), _st())
+    _lib.check(rc, "a3_vit_patch_embed")
+    return out
+
+
+def cast_f32_bf16(x, out):
+    assert x.dtype == torch.float32 and x.is_contiguous() and out.dtype == bf16 and out.is_contiguous()
+    _lib.check(_L().a3_cast_f32_bf16(_p(x), _p(out), x.numel(), _st()), "a3_cast_f32_bf16")
+    return out
+
+
 def vit_assemble_lnpre(patch_out, cls, pos, ln_w, ln_b, out, B, Np, D, eps):
     rc = _L().a3_vit_assemble_lnpre(_p(patch_out), _p(cls), _p(pos), _p(ln_w), _p(ln_b), _p(out), B, Np,
                                     D, float(eps), _st())

@@ -222,6 +222,17 @@ int a3_build_views(const void* image, int image_is_fp32, float* views, int B, in
  * x[b,1+p] = patch_out[b,p] + pos[1+p]; then ln_pre -> y (bf16). */
 int a3_vit_patchify(const void* image, int image_is_fp32, void* A, int B, int S, int patch, int Kpad,
                     void* stream);
+/* im2col-free patch embedding (the conv1 of llama_ens5.py:354-357 as ONE tcgen05 GEMM whose A operand is loaded by
+ * 4-D TMA boxes straight from the image into the UMMA shared-memory layout; no patch matrix in HBM).
+ * a3_vit_pad_cast: the autocast cast of the NCHW image (fp32 or bf16) to bf16 [B][3][S][g][16], every patch column on
+ * a 16-element pitch (kx >= patch zero) -- TMA needs 16-byte aligned box origins, raw 14-pixel patches are 28 bytes.
+ * a3_vit_patch_embed: image = that buffer; w [D][768] bf16 = the (D, 3, patch, patch) kernel zero-padded to 16 x 16
+ * windows, k = c * 256 + ky * 16 + kx; out [B * (S/patch)^2][ldo] bf16, rows in (image, py, px) order like
+ * a3_vit_patchify's.  a3_cast_f32_bf16: plain fp32 -> bf16 cast of an array. */
+int a3_vit_pad_cast(const void* image, int image_is_fp32, void* out, int B, int S, int patch, void* stream);
+int a3_vit_patch_embed(const void* image, const void* w, void* out, int B, int S, int patch, int D, long long ldo,
+                       void* stream);
+int a3_cast_f32_bf16(const float* in, void* out, long long n, void* stream);
 int a3_vit_assemble_lnpre(const void* patch_out, const void* cls, const void* pos, const void* ln_w,
                           const void* ln_b, void* x, int B, int Np, int D, float eps, void* stream);
 

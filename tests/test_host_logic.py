@@ -31,7 +31,7 @@ def test_layout_matches_reference_names_and_ffn_rule():
     assert ffn_hidden_dim(4096, 256, None) == 11008 and ffn_hidden_dim(5120, 256, None) == 13824
     a, v = _args(), _vis()
     decay, nodecay, frozen, kpad = build_layout(a, v)
-    assert kpad == 592
+    assert kpad == 768  # 3 channels x (14 x 14 window zero-padded to 16 x 16)
     ref = O.init_params(O.ModelArgs(dim=256, n_layers=3, n_heads=2, vocab_size=512, multiple_of=64),
                         O.VisionArgs(image_size=28, patch=14, width=128, layers=2, heads=2, mlp=256))
     ours = {}

@@ -186,3 +186,34 @@ def test_grouped_rmsnorm_matches_per_sample_launches():
     assert torch.equal(dx, dx_ref)
     assert bool((dx[:, :W] == 0).all())
     torch.testing.assert_close(dw, dw_ref, rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("B,S,P,D", [(2, 224, 14, 1024), (8, 336, 14, 1024), (1, 448, 14, 1024), (3, 28, 14, 128), (2, 56, 14, 256),
+                                     (2, 64, 16, 256)])
+def test_im2col_free_patch_embed(B, S, P, D):
+    """a3_vit_patch_embed: conv1 (kernel = stride = patch, no bias, llama_ens5.py:354-357) as one tcgen05 GEMM whose A
+    operand is loaded by 4-D TMA boxes straight from the NCHW bf16 image -- no patch matrix.  Against the fp32 conv
+    of the same bf16 operands (fp32-accumulate tolerance), at the BASELINE geometries 224 / 336 / 448 and at grids
+    that are not a multiple of the 8-row box (2, 4)."""
+    from a3vlm_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(S + B)
+    img = torch.randn(B, 3, S, S, device="cuda", generator=g)
+    w = (torch.randn(D, 3, P, P, device="cuda", generator=g) * 0.05).to(bf16)
+    grid = S // P
+    img16 = torch.full((B, 3, S, grid, 16), float("nan"), device="cuda", dtype=bf16)
+    ops.vit_pad_cast(img, img16, B, S, P)
+    assert torch.equal(img16[..., :P].reshape(B, 3, S, S), img.to(bf16)) and bool((img16[..., P:] == 0).all())
+    chk = torch.empty(B * 3 * S * S, device="cuda", dtype=bf16)
+    ops.cast_f32_bf16(img.view(-1), chk)
+    assert torch.equal(chk, img.to(bf16).view(-1))
+    w768 = torch.zeros(D, 3, 16, 16, device="cuda", dtype=bf16)
+    w768[:, :, :P, :P] = w
+    out = torch.full((B * grid * grid, D), float("nan"), device="cuda", dtype=bf16)
+    ops.vit_patch_embed(img16, w768.view(D, 768), out, B, S, P)
+    ref = torch.nn.functional.conv2d(img.to(bf16).float(), w.float(), stride=P)   # (B, D, g, g)
+    ref = ref.permute(0, 2, 3, 1).reshape(B * grid * grid, D)                     # rows (image, py, px)
+    err = (out.float() - ref).abs()
+    tol = 2.0 ** -8 * ref.abs() + 1e-3 * (3 * P * P) ** 0.5 * 0.05                # bf16 output rounding + accumulate order
+    assert bool(torch.isfinite(out.float()).all())
+    assert bool((err <= tol).all()), (err.max().item(), (err / tol).max().item())
