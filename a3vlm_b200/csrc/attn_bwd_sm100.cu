@@ -141,24 +141,33 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   if (warp_id == 17) {
     // =========================================================== TMA producer + dQ reduce
-    if (lane == 0 && n_iter > 0) {
-      auto load_q = [&](int it) {  // Q_i and dO_i -> stage it % 4
+    if (n_iter > 0) {  // warp-uniform; an elected lane issues (no waterfall loop around the TMA instructions)
+      const uint32_t sb = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+      const uint32_t b_qfull = __shfl_sync(0xffffffffu, smem_u32(q_full), 0);
+      const uint32_t b_kvfull = __shfl_sync(0xffffffffu, smem_u32(kv_full), 0);
+      auto load_q = [&](int it) {  // Q_i and dO_i -> stage it % BW_STAGES
         const int st = it % BW_STAGES, i = i_start + it;
-        mbar_arrive_expect_tx(&q_full[st], 2 * S::QT_BYTES);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&q_full[st], 2 * S::QT_BYTES);
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            tma_load_3d_s(sb + S::OFF_Q + st * S::QT_BYTES + c * (BW_Q * 128), &tmQ, b_qfull + st * 8,
+                          h * BW_HD + c * 64, i * BW_Q, b);
+            tma_load_3d_s(sb + S::OFF_DO + st * S::QT_BYTES + c * (BW_Q * 128), &tmDO, b_qfull + st * 8,
+                          h * BW_HD + c * 64, i * BW_Q, b);
+          }
+        }
+        __syncwarp();
+      };
+      if (elect_one()) {
+        mbar_arrive_expect_tx(kv_full, 2 * S::KV_BYTES);
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          tma_load_3d(smem + S::OFF_Q + st * S::QT_BYTES + c * (BW_Q * 128), &tmQ, &q_full[st],
-                      h * BW_HD + c * 64, i * BW_Q, b);
-          tma_load_3d(smem + S::OFF_DO + st * S::QT_BYTES + c * (BW_Q * 128), &tmDO, &q_full[st],
-                      h * BW_HD + c * 64, i * BW_Q, b);
+          tma_load_3d_s(sb + S::OFF_K + c * (BW_KEYS * 128), &tmK, b_kvfull, h * BW_HD + c * 64, key0, b);
+          tma_load_3d_s(sb + S::OFF_V + c * (BW_KEYS * 128), &tmV, b_kvfull, h * BW_HD + c * 64, key0, b);
         }
-      };
-      mbar_arrive_expect_tx(kv_full, 2 * S::KV_BYTES);
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        tma_load_3d(smem + S::OFF_K + c * (BW_KEYS * 128), &tmK, kv_full, h * BW_HD + c * 64, key0, b);
-        tma_load_3d(smem + S::OFF_V + c * (BW_KEYS * 128), &tmV, kv_full, h * BW_HD + c * 64, key0, b);
       }
+      __syncwarp();
       for (int it = 0; it < min(n_iter, BW_STAGES); ++it) load_q(it);
       for (int it = 0; it < n_iter; ++it) {
         if (it + BW_STAGES < n_iter) {  // refill the stage of tile `it` once its gradient MMAs have retired
@@ -168,16 +177,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         TR(2);  // refill issued
         mbar_wait(dq_staged, it & 1);
         TR(2);  // staged seen
-        if (!(p.debug_skip & 1)) {
-          tma_reduce_add_3d(&tmDQ, smem + S::OFF_PDS + (it & 1) * S::PDS_BYTES, h * BW_HD, (i_start + it) * BW_Q,
-                            b);  // rows >= T are clipped
-          bulk_commit_group();
-          bulk_wait_group_read0();  // the staging tile (= P^T | dS^T buffers) may be overwritten
+        // the reduce, its bulk group and the release belong to ONE thread (bulk groups are per thread); elect.sync
+        // picks the same lane for the same member mask every time
+        if (elect_one()) {
+          if (!(p.debug_skip & 1)) {
+            tma_reduce_add_3d_s(&tmDQ, sb + S::OFF_PDS + (it & 1) * S::PDS_BYTES, h * BW_HD, (i_start + it) * BW_Q,
+                                b);  // rows >= T are clipped
+            bulk_commit_group();
+            bulk_wait_group_read0();  // the staging tile (= P^T | dS^T buffers) may be overwritten
+          }
+          mbar_arrive(dq_free);
         }
-        mbar_arrive(dq_free);
+        __syncwarp();
         TR(2);  // reduce read done
       }
-      bulk_wait_group0();
+      if (elect_one()) bulk_wait_group0();
+      __syncwarp();
     }
   } else if (warp_id == 16) {
     // =========================================================== MMA issuer

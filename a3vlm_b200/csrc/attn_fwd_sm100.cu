@@ -467,8 +467,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
         }
       }
-    } else if (warp == 13 && lane == 0) {
-      // =========================================================== K/V producer
+    } else if (warp == 13) {
+      // =========================================================== K/V producer (warp-uniform, elected lane issues)
+      const uint32_t sb = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+      const uint32_t bfull = __shfl_sync(0xffffffffu, smem_u32(kv_full), 0);
       uint32_t slot = 0, phase = 0;
       for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
         const FaItem w = get_item(it);
@@ -477,20 +479,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const int j = i >> 1;
           mbar_wait(&kv_empty[slot], phase ^ 1);
           TR(4);  // slot free -> load issued
-          mbar_arrive_expect_tx(&kv_full[slot], S::KV_BYTES);
           const CUtensorMap* tm = (i & 1) ? &tmV : &tmK;
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&kv_full[slot], S::KV_BYTES);
 #pragma unroll
-          for (int c = 0; c < NCH; ++c)
-            tma_load_3d(smem + S::OFF_KV + slot * S::KV_BYTES + c * (FA_BN * 128), tm, &kv_full[slot],
-                        w.h * HD + c * 64, j * FA_BN, w.b);
+            for (int c = 0; c < NCH; ++c)
+              tma_load_3d_s(sb + S::OFF_KV + slot * S::KV_BYTES + c * (FA_BN * 128), tm, bfull + slot * 8,
+                            w.h * HD + c * 64, j * FA_BN, w.b);
+          }
+          __syncwarp();
           if (++slot == NS) {
             slot = 0;
             phase ^= 1;
           }
         }
       }
-    } else if (warp == 15 && lane == 0) {
-      // =========================================================== Q producer
+    } else if (warp == 15) {
+      // =========================================================== Q producer (warp-uniform, elected lane issues)
+      const uint32_t sb = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+      const uint32_t bfull = __shfl_sync(0xffffffffu, smem_u32(q_full), 0);
       uint32_t c_q0 = 0, c_q1 = 0;
       for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
         const FaItem w = get_item(it);
@@ -500,11 +507,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           uint32_t& c_q = s ? c_q1 : c_q0;
           mbar_wait(&q_free[s], (c_q & 1) ^ 1);  // the previous item's S_s MMAs have retired
           ++c_q;
-          mbar_arrive_expect_tx(&q_full[s], S::Q_BYTES);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&q_full[s], S::Q_BYTES);
 #pragma unroll
-          for (int c = 0; c < NCH; ++c)
-            tma_load_3d(smem + S::OFF_Q + s * S::Q_BYTES + c * (FA_BM * 128), &tmQ, &q_full[s], w.h * HD + c * 64,
-                        s ? w.q0_1 : w.q0_0, w.b);
+            for (int c = 0; c < NCH; ++c)
+              tma_load_3d_s(sb + S::OFF_Q + s * S::Q_BYTES + c * (FA_BM * 128), &tmQ, bfull + s * 8, w.h * HD + c * 64,
+                            s ? w.q0_1 : w.q0_0, w.b);
+          }
+          __syncwarp();
         }
       }
     }

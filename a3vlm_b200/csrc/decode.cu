@@ -10,6 +10,8 @@ constexpr int SM_MAXM = 16;
 constexpr int LIN_WARPS = 8;
 constexpr int LIN_COLS_PER_WARP = 2;
 
+// Weight rows are read exactly once per token: L1 no-allocate.  (An L2 evict-first cache-hint policy on these loads was
+// measured: 2.99 -> 5.59 ms/token at batch 1 -- the hinted loads lose more in the memory pipeline than the policy saves.)
 __device__ __forceinline__ uint4 ldg_stream(const void* p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
@@ -17,6 +19,8 @@ __device__ __forceinline__ uint4 ldg_stream(const void* p) {
                : "l"(p));
   return r;
 }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ float dot8(const uint4& a, const uint4& b) {
   const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
   float s = 0.f;
@@ -107,12 +111,12 @@ struct DecLinParams {
   const float2* rope; __nv_bfloat16* kc; __nv_bfloat16* vc; const int* pos_dev;
   long long ldx, ldw, ldy, ldr;
   int N, K, mode /*0 plain, 1 rmsnorm, 2 swiglu*/, out_fp32, n_heads, pos, max_seq;
+  int gate_F;  // > 0: W = w1 | w3 ([2F][K]); a warp owns ONE feature n (rows n and F + n) and writes
+               // y[n] = bf16(silu(g)) * u -- the gated SiLU as the epilogue (llama_ens5.py:213-214); N = F tasks
   float eps;
 };
 constexpr int DL_PF = 8;  // prefetched 16-byte chunks per lane per weight row (issued before the PDL wait)
 
-__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 template <int M>
 __global__ void __launch_bounds__(LIN_WARPS * 32)
@@ -121,11 +125,12 @@ decode_linear_kernel(const DecLinParams p) {
   __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(dl_smem);  // [M][K]
   __shared__ float s_red[LIN_WARPS][M];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = (blockIdx.x * LIN_WARPS + warp) * LIN_COLS_PER_WARP;
+  const int per_warp = p.gate_F > 0 ? 1 : LIN_COLS_PER_WARP;  // output indices a warp advances by
+  const int n0 = (blockIdx.x * LIN_WARPS + warp) * per_warp;
   const bool active = n0 < p.N;
   const int K = p.K, nchunks = K >> 3;
   const __nv_bfloat16* w0 = p.W + (long long)(active ? n0 : 0) * p.ldw;
-  const __nv_bfloat16* w1 = (n0 + 1 < p.N) ? w0 + p.ldw : w0;
+  const __nv_bfloat16* w1 = p.gate_F > 0 ? w0 + (long long)p.gate_F * p.ldw : ((n0 + 1 < p.N) ? w0 + p.ldw : w0);
   uint4 pa[DL_PF], pb[DL_PF];
 #pragma unroll
   for (int i = 0; i < DL_PF; ++i) {
@@ -209,11 +214,11 @@ decode_linear_kernel(const DecLinParams p) {
 
   // ---- persistent loop over column pairs: the activations are staged once per CTA, every warp walks
   // pairs n0, n0 + stride, ... ; the first pair's leading chunks were prefetched before the PDL wait
-  const int stride = gridDim.x * LIN_WARPS * LIN_COLS_PER_WARP;
+  const int stride = gridDim.x * LIN_WARPS * per_warp;
   bool first_pair = true;
   for (int n = n0; n < p.N; n += stride, first_pair = false) {
     const __nv_bfloat16* wa = p.W + (long long)n * p.ldw;
-    const __nv_bfloat16* wb = (n + 1 < p.N) ? wa + p.ldw : wa;
+    const __nv_bfloat16* wb = p.gate_F > 0 ? wa + (long long)p.gate_F * p.ldw : ((n + 1 < p.N) ? wa + p.ldw : wa);
     float acc[LIN_COLS_PER_WARP][M];
 #pragma unroll
     for (int c = 0; c < LIN_COLS_PER_WARP; ++c)
@@ -257,6 +262,14 @@ decode_linear_kernel(const DecLinParams p) {
         for (int o = 16; o > 0; o >>= 1) acc[c][m] += __shfl_xor_sync(0xffffffffu, acc[c][m], o);
     if (lane != 0) continue;
 
+    if (p.gate_F > 0) {  // both Linear outputs round to bf16, silu rounds, the product rounds
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        const float g = bf16_round(acc[0][m]), u = bf16_round(acc[1][m]);
+        reinterpret_cast<__nv_bfloat16*>(p.Y)[m * p.ldy + n] = __float2bfloat16_rn(bf16_round(g / (1.f + __expf(-g))) * u);
+      }
+      continue;
+    }
     if (p.rope) {
       // QKV projection: n is even, so this warp owns one RoPE pair (or a v pair)
       const int D = p.n_heads * 128;
@@ -308,10 +321,16 @@ attn_decode_partial_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloa
                            const __nv_bfloat16* __restrict__ vc, float* __restrict__ scratch, int H,
                            int ctx, int max_seq, long long ldq, float scale_log2,
                            const int* __restrict__ pos_dev, int* __restrict__ counters,
-                           __nv_bfloat16* __restrict__ o, long long ldo) {
+                           __nv_bfloat16* __restrict__ o, long long ldo, int prewait) {
   constexpr int HD = 128;
   __shared__ bool s_last;
-  if (pos_dev) ctx = *pos_dev + 1;  // CUDA-graph replay: the context length lives in device memory
+  const bool pre = prewait != 0;
+  if (!pre) {
+    griddep_launch();
+    griddep_wait();
+  }
+  if (pos_dev) ctx = *pos_dev + 1;  // CUDA-graph replay: the context length lives in device memory (written by the
+                                    // host before the step's first launch, so it may be read before the wait)
   __shared__ float s_acc[DEC_WARPS][HD];
   __shared__ float s_m[DEC_WARPS], s_l[DEC_WARPS];
   const int bh = blockIdx.x, b = bh / H, h = bh % H;
@@ -319,25 +338,51 @@ attn_decode_partial_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloa
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int per = (ctx + nsplit - 1) / nsplit;
   const int k_begin = split * per, k_end = min(ctx, k_begin + per);
-  const uint2 qraw = *reinterpret_cast<const uint2*>(q + b * ldq + h * HD + lane * 4);
-  const float2 q01 = unpack_bf16x2(qraw.x), q23 = unpack_bf16x2(qraw.y);
-  float m = -INFINITY, l = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f, a3v = 0.f;
   const long long base = ((long long)b * max_seq) * H * HD + h * HD + lane * 4;
   // 8 keys per warp in flight: all K / V loads of a group are issued before the dependent
   // online-softmax chain (one L2 round trip per group instead of per key)
   constexpr int KU = 8;
-  for (int t0 = k_begin + warp; t0 < k_end; t0 += DEC_WARPS * KU) {
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // a PDL successor may start prefetching weights
-    uint2 kr[KU], vr[KU];
+  uint2 kr[KU], vr[KU];
+  const int t_first = k_begin + warp;
+  auto load_round = [&](int t0, int limit) {
 #pragma unroll
     for (int u = 0; u < KU; ++u) {
       const int t = t0 + u * DEC_WARPS;
-      if (t < k_end) {
+      if (t < limit) {
         const long long off = base + (long long)t * H * HD;
         kr[u] = *reinterpret_cast<const uint2*>(kc + off);
         vr[u] = *reinterpret_cast<const uint2*>(vc + off);
       }
     }
+  };
+  if (pre) {
+    // Every cache position but the newest (ctx - 1, written by the projection that precedes this kernel) dates from
+    // earlier steps: the first round of K / V loads is issued -- and the later rounds' lines are requested into L2 --
+    // BEFORE the programmatic-dependent-launch wait, i.e. while the QKV projection is still streaming its weights.
+    load_round(t_first, min(k_end, ctx - 1));
+    for (int j = lane >> 2; j < 2 * KU; j += 8) {  // the next two rounds only: a bounded L2 footprint at large batch
+      const int t = t_first + DEC_WARPS * (KU + j);
+      if (t >= k_end) break;
+      const __nv_bfloat16* src = ((lane & 2) ? vc : kc) + ((long long)b * max_seq + t) * H * HD + h * HD + (lane & 1) * 64;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
+    }
+    griddep_launch();
+    griddep_wait();
+#pragma unroll
+    for (int u = 0; u < KU; ++u) {  // the newest key, if it falls into this warp's first round
+      const int t = t_first + u * DEC_WARPS;
+      if (t == ctx - 1 && t < k_end) {
+        const long long off = base + (long long)t * H * HD;
+        kr[u] = *reinterpret_cast<const uint2*>(kc + off);
+        vr[u] = *reinterpret_cast<const uint2*>(vc + off);
+      }
+    }
+  }
+  const uint2 qraw = *reinterpret_cast<const uint2*>(q + b * ldq + h * HD + lane * 4);
+  const float2 q01 = unpack_bf16x2(qraw.x), q23 = unpack_bf16x2(qraw.y);
+  float m = -INFINITY, l = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f, a3v = 0.f;
+  for (int t0 = t_first; t0 < k_end; t0 += DEC_WARPS * KU) {
+    if (!(pre && t0 == t_first)) load_round(t0, k_end);
     float sc[KU];
 #pragma unroll
     for (int u = 0; u < KU; ++u) {
@@ -398,14 +443,26 @@ attn_decode_partial_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloa
   if (!s_last) return;
   __threadfence();
   const volatile float* in = scratch + (long long)bh * nsplit * (HD + 2);
-  float Mx = -INFINITY;
-  for (int s = 0; s < nsplit; ++s) Mx = fmaxf(Mx, in[s * (HD + 2) + HD]);
-  float Lx = 0.f, Ax = 0.f;
-  for (int s = 0; s < nsplit; ++s) {
-    const float ms = in[s * (HD + 2) + HD];
-    const float c = ms == -INFINITY ? 0.f : exp2f(ms - Mx);
-    Lx += in[s * (HD + 2) + HD + 1] * c;
-    Ax += in[s * (HD + 2) + d] * c;
+  float Mx = -INFINITY, Lx = 0.f, Ax = 0.f;
+  for (int s0 = 0; s0 < nsplit; s0 += 8) {  // 3 x 8 independent loads in flight
+    float ms[8], ls[8], as[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int s = min(s0 + u, nsplit - 1);
+      ms[u] = in[s * (HD + 2) + HD];
+      ls[u] = in[s * (HD + 2) + HD + 1];
+      as[u] = in[s * (HD + 2) + d];
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (s0 + u < nsplit && ms[u] != -INFINITY) {
+        const float mn = fmaxf(Mx, ms[u]);
+        const float c0 = exp2f(Mx - mn), c1 = exp2f(ms[u] - mn);
+        Lx = Lx * c0 + ls[u] * c1;
+        Ax = Ax * c0 + as[u] * c1;
+        Mx = mn;
+      }
+    }
   }
   o[b * ldo + h * HD + d] = __float2bfloat16_rn(Ax / Lx);
 }
@@ -498,7 +555,7 @@ template <int M>
 static int launch_decode_linear(const DecLinParams& p, cudaStream_t s) {
   const size_t smem = (size_t)M * p.K * 2;
   if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&decode_linear_kernel<M>), smem)) return rc;
-  const int cols_per_block = LIN_WARPS * LIN_COLS_PER_WARP;
+  const int cols_per_block = LIN_WARPS * (p.gate_F > 0 ? 1 : LIN_COLS_PER_WARP);
   int grid = (p.N + cols_per_block - 1) / cols_per_block;
   const int slots = num_sms() * 2;  // persistent: one resident wave (2 CTAs per SM), X staged once per CTA
   if (grid > slots) grid = slots;
@@ -537,7 +594,28 @@ extern "C" int a3_decode_linear(const void* X, const void* W, void* Y, int M, in
   p.rope = reinterpret_cast<const float2*>(rope_table); p.kc = BFM(kcache); p.vc = BFM(vcache);
   p.pos_dev = pos_dev; p.ldx = ldx; p.ldw = ldw; p.ldy = ldy; p.ldr = ldr;
   p.N = N; p.K = K; p.mode = norm_w ? 1 : (swiglu ? 2 : 0); p.out_fp32 = out_fp32;
-  p.n_heads = n_heads; p.pos = pos; p.max_seq = max_seq; p.eps = eps;
+  p.n_heads = n_heads; p.pos = pos; p.max_seq = max_seq; p.eps = eps; p.gate_F = 0;
+  cudaStream_t s = ST(stream);
+#define CASE(m) case m: return launch_decode_linear<m>(p, s);
+  switch (M) { CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) }
+#undef CASE
+  return A3_ERR_ARG;
+}
+
+extern "C" int a3_decode_linear_gated(const void* X, const void* W13, void* Y, int M, int F, int K, long long ldx,
+                                      long long ldw, long long ldy, const void* norm_w, float eps, void* stream) {
+  if (M <= 0 || F <= 0) return A3_OK;
+  if (M > 8) return set_error(A3_ERR_ARG, "a3_decode_linear_gated: M <= 8");
+  if ((K & 7) || (ldx & 7) || (ldw & 7) || (reinterpret_cast<uintptr_t>(X) & 15) ||
+      (reinterpret_cast<uintptr_t>(W13) & 15))
+    return set_error(A3_ERR_ARG, "a3_decode_linear_gated: K, ldx, ldw % 8 == 0 and 16-byte alignment");
+  if ((size_t)M * K * 2 > 200 * 1024) return set_error(A3_ERR_ARG, "a3_decode_linear_gated: M*K too large for smem staging");
+  DecLinParams p;
+  p.X = BF(X); p.W = BF(W13); p.Y = Y; p.norm_w = BF(norm_w); p.residual = nullptr;
+  p.rope = nullptr; p.kc = nullptr; p.vc = nullptr; p.pos_dev = nullptr;
+  p.ldx = ldx; p.ldw = ldw; p.ldy = ldy; p.ldr = 0;
+  p.N = F; p.K = K; p.mode = norm_w ? 1 : 0; p.out_fp32 = 0; p.n_heads = 0; p.pos = 0; p.max_seq = 0; p.eps = eps;
+  p.gate_F = F;
   cudaStream_t s = ST(stream);
 #define CASE(m) case m: return launch_decode_linear<m>(p, s);
   switch (M) { CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) }
@@ -561,17 +639,39 @@ extern "C" int a3_decode_rope_kv(void* qkv, long long ld, void* kcache, void* vc
 extern "C" int a3_attn_decode(const void* q, const void* kcache, const void* vcache, void* o,
                               float* scratch, int B, int H, int head_dim, int ctx, int max_seq,
                               long long ldq, long long ldo, float scale, const int* pos_dev,
-                              void* stream) {
+                              int stable_prefix, void* stream) {
   if (head_dim != 128) return set_error(A3_ERR_UNSUPPORTED, "a3_attn_decode: head_dim must be 128");
   if (ctx <= 0 || ctx > max_seq) return set_error(A3_ERR_ARG, "a3_attn_decode: 0 < ctx <= max_seq");
   if (B * H <= 0) return A3_OK;
-  int nsplit = (2 * num_sms() + B * H - 1) / (B * H);
+  // ~192 keys per CTA (a warp scans its share in a few rounds of 8 loads), at least two CTAs per SM at small batch,
+  // at most ~64 CTAs per SM at large batch.  Measured at batch 1, ctx 900: 10 splits 2.95 ms/token, 32 splits 3.00;
+  // batch 16: 10 splits 6.0 ms, 1 split 8.3 ms.
+  const int BH = B * H;
+#ifdef A3_DEC_OLD_SPLIT  // round-1 heuristic, kept for A/B builds
+  int nsplit = (2 * num_sms() + BH - 1) / BH;
+#else
+  int nsplit = (ctx + 191) / 192;
+  nsplit = max(nsplit, (2 * num_sms() + BH - 1) / BH);
+  nsplit = min(nsplit, max(1, 64 * num_sms() / BH));
+#endif
   const int max_useful = (ctx + 4 * DEC_WARPS - 1) / (4 * DEC_WARPS);
   if (!pos_dev && nsplit > max_useful) nsplit = max_useful;  // graph mode: split count must not depend on ctx
   if (nsplit > DEC_MAX_SPLIT) nsplit = DEC_MAX_SPLIT;
   if (nsplit < 1) nsplit = 1;
-  attn_decode_partial_kernel<<<dim3(B * H, nsplit), DEC_WARPS * 32, 0, ST(stream)>>>(
-      BF(q), BF(kcache), BF(vcache), scratch, H, ctx, max_seq, ldq, scale * 1.4426950408889634f, pos_dev,
-      reinterpret_cast<int*>(scratch + (long long)B * H * DEC_MAX_SPLIT * (128 + 2)), BFM(o), ldo);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(B * H, nsplit);
+  cfg.blockDim = dim3(DEC_WARPS * 32);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = ST(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(
+      &cfg, attn_decode_partial_kernel, BF(q), BF(kcache), BF(vcache), scratch, H, ctx, max_seq, ldq,
+      scale * 1.4426950408889634f, pos_dev, reinterpret_cast<int*>(scratch + (long long)B * H * DEC_MAX_SPLIT * (128 + 2)),
+      BFM(o), ldo, stable_prefix ? 1 : 0);
+  if (e != cudaSuccess) return set_error(A3_ERR_CUDA, cudaGetErrorString(e));
   return check_launch("a3_attn_decode");
 }

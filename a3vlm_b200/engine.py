@@ -18,6 +18,7 @@ of the same layout (bucketed per layer for the all-reduce), fp32 master / m / v 
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -868,19 +869,37 @@ class Engine:
         B, D, F = d["B"], a.dim, self.ffn_dim
         ops.embed_splice(d["tok"], w["tok_embeddings.weight"], None, None, None, d["x"], B, 1, 0, D)
         x, x2 = d["x"], d["x2"]
+        # the attention kernel may read every cache position but the newest before the projection in front of it has
+        # finished (decode); A3_DEC_PREWAIT=0 turns that off for A/B timing
+        early = dict(stable_prefix=os.environ.get("A3_DEC_PREWAIT", "1") != "0")
         if B <= self.decode_fused_max_b:
             # five launches per layer: every norm / activation / RoPE / cache write is a prologue or
             # epilogue of the weight-streaming projection that consumes or produces it
+            skip = os.environ.get("A3_DEC_SKIP", "").split(",")  # timing experiments only: marginal cost of a launch
+            gated = os.environ.get("A3_DEC_GATED", "1") != "0"
             for i in range(a.n_layers):
                 p = f"layers.{i}."
-                ops.decode_linear(x, w[p + "wqkv"], d["qkv"], norm_w=w[p + "attention_norm.weight"], eps=a.norm_eps,
-                                  rope=self.rope, n_heads=a.n_heads, kcache=self.kcache[i], vcache=self.vcache[i],
-                                  pos_dev=d["pos"], max_seq=a.max_seq_len)
-                ops.attn_decode(d["qkv"][:, :D], self.kcache[i], self.vcache[i], d["o"], d["scratch"], B,
-                                a.n_heads, self.head_dim, a.max_seq_len, a.max_seq_len, self.scale, pos_dev=d["pos"])
-                ops.decode_linear(d["o"], w[p + "attention.wo.weight"], d["h"], residual=x)
-                ops.decode_linear(d["h"], w[p + "w13"], d["gu"], norm_w=w[p + "ffn_norm.weight"], eps=a.norm_eps)
-                ops.decode_linear(d["gu"], w[p + "feed_forward.w2.weight"], x2, K=F, swiglu=True, residual=d["h"])
+                if "qkv" not in skip:
+                    ops.decode_linear(x, w[p + "wqkv"], d["qkv"], norm_w=w[p + "attention_norm.weight"], eps=a.norm_eps,
+                                      rope=self.rope, n_heads=a.n_heads, kcache=self.kcache[i], vcache=self.vcache[i],
+                                      pos_dev=d["pos"], max_seq=a.max_seq_len)
+                if "attn" not in skip:
+                    ops.attn_decode(d["qkv"][:, :D], self.kcache[i], self.vcache[i], d["o"], d["scratch"], B,
+                                    a.n_heads, self.head_dim, a.max_seq_len, a.max_seq_len, self.scale, pos_dev=d["pos"],
+                                    **early)
+                if "wo" not in skip:
+                    ops.decode_linear(d["o"], w[p + "attention.wo.weight"], d["h"], residual=x)
+                if gated:  # the gate is the epilogue of the w1|w3 projection: gu never reaches HBM
+                    if "w13" not in skip:
+                        ops.decode_linear_gated(d["h"], w[p + "w13"], d["y"], norm_w=w[p + "ffn_norm.weight"], eps=a.norm_eps)
+                    if "w2" not in skip:
+                        ops.decode_linear(d["y"], w[p + "feed_forward.w2.weight"], x2, residual=d["h"])
+                    x, x2 = x2, x
+                    continue
+                if "w13" not in skip:
+                    ops.decode_linear(d["h"], w[p + "w13"], d["gu"], norm_w=w[p + "ffn_norm.weight"], eps=a.norm_eps)
+                if "w2" not in skip:
+                    ops.decode_linear(d["gu"], w[p + "feed_forward.w2.weight"], x2, K=F, swiglu=True, residual=d["h"])
                 x, x2 = x2, x
             ops.decode_linear(x, w["output.weight"], d["logits"], norm_w=w["norm.weight"], eps=a.norm_eps, out_fp32=True)
             return
@@ -897,7 +916,8 @@ class Engine:
             ops.decode_rope_kv(d["qkv"], self.kcache[i], self.vcache[i], B, a.n_heads, self.head_dim, self.rope,
                                0, a.max_seq_len, pos_dev=d["pos"])
             ops.attn_decode(d["qkv"][:, :D], self.kcache[i], self.vcache[i], d["o"], d["scratch"], B,
-                            a.n_heads, self.head_dim, a.max_seq_len, a.max_seq_len, self.scale, pos_dev=d["pos"])
+                            a.n_heads, self.head_dim, a.max_seq_len, a.max_seq_len, self.scale, pos_dev=d["pos"],
+                            **early)
             lin(d["o"], w[p + "attention.wo.weight"], d["h"], residual=x)
             ops.rmsnorm_fwd(d["h"], w[p + "ffn_norm.weight"], a.norm_eps, out=d["xn"])
             lin(d["xn"], w[p + "w13"], d["gu"])

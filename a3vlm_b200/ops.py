@@ -118,6 +118,15 @@ def decode_linear(x, w, out, *, K=None, norm_w=None, eps=1e-5, swiglu=False, res
     return out
 
 
+def decode_linear_gated(x, w13, out, *, norm_w=None, eps=1e-5):
+    """y [M][F] = bf16(silu(x w1^T)) * (x w3^T) with w13 = [2F][K] (w1 rows, then w3 rows); optional RMSNorm prologue."""
+    M, F, K = x.shape[0], w13.shape[0] // 2, w13.shape[1]
+    rc = _L().a3_decode_linear_gated(_p(x), _p(w13), _p(out), M, F, K, x.stride(0), w13.stride(0), out.stride(0),
+                                     _p(norm_w), float(eps), _st())
+    _lib.check(rc, "a3_decode_linear_gated")
+    return out
+
+
 def decode_gemm(x, w, out, residual=None, out_fp32=False):
     M, K = x.shape
     N = w.shape[0]
@@ -243,9 +252,9 @@ def attn_bwd(q, k, v, o, dout, lse, delta, dq_acc, dq, dk, dv, B, H, T, head_dim
     _lib.check(rc, "a3_attn_bwd")
 
 
-def attn_decode(q, kcache, vcache, out, scratch, B, H, head_dim, ctx, max_seq, scale, pos_dev=None):
+def attn_decode(q, kcache, vcache, out, scratch, B, H, head_dim, ctx, max_seq, scale, pos_dev=None, stable_prefix=False):
     rc = _L().a3_attn_decode(_p(q), _p(kcache), _p(vcache), _p(out), _p(scratch), B, H, head_dim, ctx,
-                             max_seq, q.stride(0), out.stride(0), float(scale), _p(pos_dev), _st())
+                             max_seq, q.stride(0), out.stride(0), float(scale), _p(pos_dev), int(bool(stable_prefix)), _st())
     _lib.check(rc, "a3_attn_decode")
     return out
 

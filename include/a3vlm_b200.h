@@ -94,6 +94,12 @@ int a3_decode_linear(const void* X, const void* W, void* Y, int M, int N, int K,
                      int n_heads, void* kcache, void* vcache, const int* pos_dev, int pos, int max_seq,
                      void* stream);
 
+/* The w1|w3 projection of a decode step with the gated SiLU as its epilogue (llama_ens5.py:213-214): a warp streams
+ * row n of w1 and row n of w3 (W13 = [2F][K], w1 rows first) and writes y[m][n] = bf16(bf16(silu(g)) * u) -- gu never
+ * reaches HBM and the w2 projection needs no activation prologue.  Optional RMSNorm prologue as a3_decode_linear. */
+int a3_decode_linear_gated(const void* X, const void* W13, void* Y, int M, int F, int K, long long ldx,
+                           long long ldw, long long ldy, const void* norm_w, float eps, void* stream);
+
 /* Decode projection for a batch of M <= 64 single-token rows on tcgen05 with swapped operands: the
  * weight tile is the 128-row MMA operand, the batch the narrow N side, split-K across a thread-block
  * cluster with a distributed-shared-memory reduction, 8-11 TMA stages in flight (HBM-bound weight
@@ -171,9 +177,13 @@ int a3_attn_bwd(const void* q, const void* k, const void* v, const void* o, cons
  * arrival counters that reset themselves; the last split to finish merges the partial results).
  * pos_dev != NULL (CUDA-graph replay): ctx = *pos_dev + 1 is read on the device and `ctx` is only an
  * upper bound used to size the split. */
+/* stable_prefix != 0: the caller guarantees that every cache position except the newest (ctx - 1) was written before
+ * the kernels still in flight on the stream started (true inside a decode step: the preceding projection writes only
+ * the newest position) and that *pos_dev was written by the host; the kernel is launched with programmatic dependent
+ * launch and reads those positions while its predecessor drains. */
 int a3_attn_decode(const void* q, const void* kcache, const void* vcache, void* o, float* scratch,
                    int B, int H, int head_dim, int ctx, int max_seq, long long ldq, long long ldo,
-                   float scale, const int* pos_dev, void* stream);
+                   float scale, const int* pos_dev, int stable_prefix, void* stream);
 /* Decode-step fusion of apply_rotary_emb + cache write (llama_ens5.py:118-127, seqlen 1): rotates q
  * and k of qkv [B][3*H*128] in place at position pos (or *pos_dev) and writes k, v into
  * cache[b, pos]. */

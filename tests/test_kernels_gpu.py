@@ -374,6 +374,15 @@ def test_decode_rope_kv_and_device_pos(ops):
     ops.attn_decode(got[:, :W], kc, vc, o1, scratch, B, H, hd, pos + 1, max_seq, 0.088)
     ops.attn_decode(got[:, :W], kc, vc, o2, scratch, B, H, hd, max_seq, max_seq, 0.088, pos_dev=pos_dev)
     close_bf16(o2, o1, atol=2e-3)
+    # early reads of the stable prefix (everything but position ctx - 1): same result, bit for bit
+    o3 = torch.empty_like(o2)
+    ops.attn_decode(got[:, :W], kc, vc, o3, scratch, B, H, hd, max_seq, max_seq, 0.088, pos_dev=pos_dev, stable_prefix=True)
+    assert torch.equal(o3, o2)
+    for ctx in (1, 2, 33, 64):  # newest key alone / in the first round / in a later round / full cache
+        pd = torch.tensor([ctx - 1], device=dev(), dtype=torch.int32)
+        ops.attn_decode(got[:, :W], kc, vc, o2, scratch, B, H, hd, max_seq, max_seq, 0.088, pos_dev=pd)
+        ops.attn_decode(got[:, :W], kc, vc, o3, scratch, B, H, hd, max_seq, max_seq, 0.088, pos_dev=pd, stable_prefix=True)
+        assert torch.equal(o3, o2), ctx
 
 
 @pytest.mark.parametrize("M", [1, 3, 8])
@@ -404,6 +413,15 @@ def test_decode_linear_fused(ops, M):
     ref = ops.linear_small_m(ops.swiglu_fwd(gu), w2, residual=res)
     got = torch.empty_like(ref)
     ops.decode_linear(gu, w2, got, K=F, swiglu=True, residual=res)
+    close_bf16(got, ref, atol=4e-3)
+    # gate as the epilogue of the w1|w3 projection == rmsnorm -> linear -> swiglu, bit for bit (same dot-product order)
+    w13 = rnd(2 * F, K, scale=0.06)
+    ref = ops.swiglu_fwd(ops.linear_small_m(ops.rmsnorm_fwd(x, nw, 1e-5), w13))
+    ref2 = torch.empty(M, 2 * F, device=dev(), dtype=bf16)
+    ops.decode_linear(x, w13, ref2, norm_w=nw, eps=1e-5)
+    got = torch.empty(M, F, device=dev(), dtype=bf16)
+    ops.decode_linear_gated(x, w13, got, norm_w=nw, eps=1e-5)
+    assert torch.equal(got, ops.swiglu_fwd(ref2))
     close_bf16(got, ref, atol=4e-3)
     # norm prologue + fp32 logits
     wo = rnd(1000, K, scale=0.05)
