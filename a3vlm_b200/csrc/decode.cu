@@ -118,29 +118,11 @@ struct DecLinParams {
 constexpr int DL_PF = 8;  // prefetched 16-byte chunks per lane per weight row (issued before the PDL wait)
 
 
+// ---- activation prologue shared by the decode projections (once per CTA, result in shared memory)
 template <int M>
-__global__ void __launch_bounds__(LIN_WARPS * 32)
-decode_linear_kernel(const DecLinParams p) {
-  extern __shared__ __align__(16) uint8_t dl_smem[];
-  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(dl_smem);  // [M][K]
-  __shared__ float s_red[LIN_WARPS][M];
+__device__ __forceinline__ void stage_activations(const DecLinParams& p, __nv_bfloat16* xs, float (*s_red)[M]) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int per_warp = p.gate_F > 0 ? 1 : LIN_COLS_PER_WARP;  // output indices a warp advances by
-  const int n0 = (blockIdx.x * LIN_WARPS + warp) * per_warp;
-  const bool active = n0 < p.N;
   const int K = p.K, nchunks = K >> 3;
-  const __nv_bfloat16* w0 = p.W + (long long)(active ? n0 : 0) * p.ldw;
-  const __nv_bfloat16* w1 = p.gate_F > 0 ? w0 + (long long)p.gate_F * p.ldw : ((n0 + 1 < p.N) ? w0 + p.ldw : w0);
-  uint4 pa[DL_PF], pb[DL_PF];
-#pragma unroll
-  for (int i = 0; i < DL_PF; ++i) {
-    const int ch = lane + i * 32;
-    if (ch < nchunks) { pa[i] = ldg_stream(w0 + ch * 8); pb[i] = ldg_stream(w1 + ch * 8); }
-  }
-  griddep_launch();
-  griddep_wait();
-
-  // ---- stage the (transformed) activations
   if (p.mode == 1) {
     // one global pass: raw rows -> smem while accumulating sum(x^2); the transform re-reads smem
     float ss[M];
@@ -210,6 +192,80 @@ decode_linear_kernel(const DecLinParams p) {
       for (int m = 0; m < M; ++m)
         *reinterpret_cast<uint4*>(xs + m * K + ch * 8) = *reinterpret_cast<const uint4*>(p.X + m * p.ldx + ch * 8);
   }
+}
+
+// ---- epilogue of one output pair (lane 0 of the owning warp): gate | RoPE + cache append | residual / logits
+template <int M>
+__device__ __forceinline__ void store_outputs(const DecLinParams& p, int n, const float (&acc)[LIN_COLS_PER_WARP][M]) {
+    if (p.gate_F > 0) {  // both Linear outputs round to bf16, silu rounds, the product rounds (SURVEY A.9)
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        const float g = bf16_round(acc[0][m]), u = bf16_round(acc[1][m]);
+        reinterpret_cast<__nv_bfloat16*>(p.Y)[m * p.ldy + n] = __float2bfloat16_rn(bf16_round(g / (1.f + __expf(-g))) * u);
+      }
+      return;
+    }
+    if (p.rope) {
+      // QKV projection: n is even, so this warp owns one RoPE pair (or a v pair)
+      const int D = p.n_heads * 128;
+      const int pos = p.pos_dev ? *p.pos_dev : p.pos;
+      const int sect = n / D, within = n - sect * D;  // 0 q, 1 k, 2 v
+      const float2 cs = p.rope[(long long)pos * 64 + ((within & 127) >> 1)];
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        float a = bf16_round(acc[0][m]), b = bf16_round(acc[1][m]);
+        if (sect < 2) { const float ra = a * cs.x - b * cs.y, rb = a * cs.y + b * cs.x; a = ra; b = rb; }
+        const uint32_t r = pack_bf16x2(a, b);
+        *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(p.Y) + m * p.ldy + n) = r;
+        if (sect >= 1) {
+          __nv_bfloat16* cache = sect == 1 ? p.kc : p.vc;
+          *reinterpret_cast<uint32_t*>(cache + ((long long)m * p.max_seq + pos) * D + within) = r;
+        }
+      }
+      return;
+    }
+#pragma unroll
+    for (int c = 0; c < LIN_COLS_PER_WARP; ++c) {
+      const int nn = n + c;
+      if (nn >= p.N) break;
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        float v = acc[c][m];
+        if (p.out_fp32) {
+          v = bf16_round(v);  // logits: .float() of a bf16 GEMM result (llama_ens5.py:530-531)
+          if (p.residual) v += __bfloat162float(p.residual[m * p.ldr + nn]);
+          reinterpret_cast<float*>(p.Y)[m * p.ldy + nn] = v;
+        } else {
+          if (p.residual) v = bf16_round(v) + __bfloat162float(p.residual[m * p.ldr + nn]);
+          reinterpret_cast<__nv_bfloat16*>(p.Y)[m * p.ldy + nn] = __float2bfloat16_rn(v);
+        }
+      }
+    }
+}
+
+template <int M>
+__global__ void __launch_bounds__(LIN_WARPS * 32)
+decode_linear_kernel(const DecLinParams p) {
+  extern __shared__ __align__(16) uint8_t dl_smem[];
+  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(dl_smem);  // [M][K]
+  __shared__ float s_red[LIN_WARPS][M];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per_warp = p.gate_F > 0 ? 1 : LIN_COLS_PER_WARP;  // output indices a warp advances by
+  const int n0 = (blockIdx.x * LIN_WARPS + warp) * per_warp;
+  const bool active = n0 < p.N;
+  const int K = p.K, nchunks = K >> 3;
+  const __nv_bfloat16* w0 = p.W + (long long)(active ? n0 : 0) * p.ldw;
+  const __nv_bfloat16* w1 = p.gate_F > 0 ? w0 + (long long)p.gate_F * p.ldw : ((n0 + 1 < p.N) ? w0 + p.ldw : w0);
+  uint4 pa[DL_PF], pb[DL_PF];
+#pragma unroll
+  for (int i = 0; i < DL_PF; ++i) {
+    const int ch = lane + i * 32;
+    if (ch < nchunks) { pa[i] = ldg_stream(w0 + ch * 8); pb[i] = ldg_stream(w1 + ch * 8); }
+  }
+  griddep_launch();
+  griddep_wait();
+
+  stage_activations<M>(p, xs, s_red);
   __syncthreads();
 
   // ---- persistent loop over column pairs: the activations are staged once per CTA, every warp walks
@@ -260,52 +316,7 @@ decode_linear_kernel(const DecLinParams p) {
       for (int m = 0; m < M; ++m)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc[c][m] += __shfl_xor_sync(0xffffffffu, acc[c][m], o);
-    if (lane != 0) continue;
-
-    if (p.gate_F > 0) {  // both Linear outputs round to bf16, silu rounds, the product rounds (SURVEY A.9)
-#pragma unroll
-      for (int m = 0; m < M; ++m) {
-        const float g = bf16_round(acc[0][m]), u = bf16_round(acc[1][m]);
-        reinterpret_cast<__nv_bfloat16*>(p.Y)[m * p.ldy + n] = __float2bfloat16_rn(bf16_round(g / (1.f + __expf(-g))) * u);
-      }
-      continue;
-    }
-    if (p.rope) {
-      // QKV projection: n is even, so this warp owns one RoPE pair (or a v pair)
-      const int D = p.n_heads * 128;
-      const int pos = p.pos_dev ? *p.pos_dev : p.pos;
-      const int sect = n / D, within = n - sect * D;  // 0 q, 1 k, 2 v
-      const float2 cs = p.rope[(long long)pos * 64 + ((within & 127) >> 1)];
-#pragma unroll
-      for (int m = 0; m < M; ++m) {
-        float a = bf16_round(acc[0][m]), b = bf16_round(acc[1][m]);
-        if (sect < 2) { const float ra = a * cs.x - b * cs.y, rb = a * cs.y + b * cs.x; a = ra; b = rb; }
-        const uint32_t r = pack_bf16x2(a, b);
-        *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(p.Y) + m * p.ldy + n) = r;
-        if (sect >= 1) {
-          __nv_bfloat16* cache = sect == 1 ? p.kc : p.vc;
-          *reinterpret_cast<uint32_t*>(cache + ((long long)m * p.max_seq + pos) * D + within) = r;
-        }
-      }
-      continue;
-    }
-#pragma unroll
-    for (int c = 0; c < LIN_COLS_PER_WARP; ++c) {
-      const int nn = n + c;
-      if (nn >= p.N) break;
-#pragma unroll
-      for (int m = 0; m < M; ++m) {
-        float v = acc[c][m];
-        if (p.out_fp32) {
-          v = bf16_round(v);  // logits: .float() of a bf16 GEMM result (llama_ens5.py:530-531)
-          if (p.residual) v += __bfloat162float(p.residual[m * p.ldr + nn]);
-          reinterpret_cast<float*>(p.Y)[m * p.ldy + nn] = v;
-        } else {
-          if (p.residual) v = bf16_round(v) + __bfloat162float(p.residual[m * p.ldr + nn]);
-          reinterpret_cast<__nv_bfloat16*>(p.Y)[m * p.ldy + nn] = __float2bfloat16_rn(v);
-        }
-      }
-    }
+    if (lane == 0) store_outputs<M>(p, n, acc);
   }
 }
 
@@ -551,6 +562,14 @@ extern "C" int a3_linear_small_m(const void* X, const void* W, void* Y, int M, i
 }
 
 
+// Two alternatives to the register-streamed main loop were built and measured at batch 1 (same box, 7B, ctx ~900;
+// profiles/r02_decode_stream_experiments.jsonl), both bit-identical in their results and both slower:
+//   * per-warp shared-memory rings filled by 1-D bulk copies (cp.async.bulk + mbarrier), 2-4 KB per request:
+//     4.0-5.9 ms/token against 2.89 -- small bulk requests sustain only 2.5-3.3 TB/s across the chip;
+//   * per-lane rings filled by cp.async (LDGSTS.128), depth 6 / 10 / 12: 6.1 / 4.5 / 4.3 ms/token.
+// The idea behind both (bytes in flight in shared memory instead of registers, so one CTA per SM suffices and the
+// PDL successor can fill its ring beside it) stays open; plain 16-byte loads into registers remain the fastest
+// way this chip streams a weight matrix from a CUDA-core kernel.
 template <int M>
 static int launch_decode_linear(const DecLinParams& p, cudaStream_t s) {
   const size_t smem = (size_t)M * p.K * 2;
