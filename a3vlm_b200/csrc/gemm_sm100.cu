@@ -18,6 +18,7 @@
 // stages, two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "ptx.cuh"
 #include "a3vlm_b200.h"
+#include <cstring>
 #include "common.cuh"
 #include <cstdlib>
 
@@ -45,6 +46,7 @@ struct GemmParams {
   int accumulate;
   float alpha;
   int group_m;  // M-blocks per rasterisation group
+  unsigned long long hint_a, hint_b;  // L2 cache policies of the operand loads (CTA-pair kernel)
   // fused gated-SiLU modes (llama_ens5.py:213-217):
   //   swiglu_F > 0 (CTA-pair kernel only): B = [w1; w3] ([2F][K]); CTA 0 of the pair loads 128 rows of
   //     w1, CTA 1 the same 128 rows of w3, so one accumulator tile holds g | u of 128 features; the
@@ -98,6 +100,21 @@ __device__ __forceinline__ void tile_coords(int tile, int m_blocks, int n_blocks
   nb = r / rows;
 }
 
+}  // namespace a3
+// L2 policies of the operand loads.  The raster walks all N-blocks for a band of group_m M-blocks, so the band's A
+// panel is re-read by every wave of the band while a B panel is read once per band: A3_GEMM_HINT=al_bf marks A
+// evict-last / B evict-first, af_bl the opposite, unset / 0 leaves both evict-normal (the measured default).
+static void set_cache_hints(a3::GemmParams& p) {
+  constexpr unsigned long long NORMAL = 0x1000000000000000ull, FIRST = 0x12F0000000000000ull, LAST = 0x14F0000000000000ull;
+  static const char* env = getenv("A3_GEMM_HINT");
+  p.hint_a = p.hint_b = NORMAL;
+  if (!env) return;
+  if (!strcmp(env, "al_bf")) { p.hint_a = LAST; p.hint_b = FIRST; }
+  else if (!strcmp(env, "af_bl")) { p.hint_a = FIRST; p.hint_b = LAST; }
+  else if (!strcmp(env, "al_bn")) { p.hint_a = LAST; }
+  else if (!strcmp(env, "an_bf")) { p.hint_b = FIRST; }
+}
+namespace a3 {
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == 1) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
   if (act == 2) return v / (1.0f + __expf(-1.702f * v));
@@ -603,18 +620,18 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (issuer) {
             if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);
             if (!p.a_mn) {
-              tma_load_2d_2sm_s(sa, &tmA, fb, k0, m0);
+              tma_load_2d_2sm_h(sa, &tmA, fb, k0, m0, p.hint_a);
             } else {
 #pragma unroll
               for (int c = 0; c < BM / 64; ++c)
-                tma_load_2d_2sm_s(sa + c * (BK * 128), &tmA, fb, m0 + c * 64, k0);
+                tma_load_2d_2sm_h(sa + c * (BK * 128), &tmA, fb, m0 + c * 64, k0, p.hint_a);
             }
             if (!p.b_mn) {
-              tma_load_2d_2sm_s(sb, &tmB, fb, k0, n0);
+              tma_load_2d_2sm_h(sb, &tmB, fb, k0, n0, p.hint_b);
             } else {
 #pragma unroll
               for (int c = 0; c < BNH / 64; ++c)
-                tma_load_2d_2sm_s(sb + c * (BK * 128), &tmB, fb, n0 + c * 64, k0);
+                tma_load_2d_2sm_h(sb + c * (BK * 128), &tmB, fb, n0 + c * 64, k0, p.hint_b);
             }
           }
           __syncwarp();
@@ -817,6 +834,7 @@ extern "C" int a3_gemm_bf16(const void* A, const void* B, void* C, int M, int N,
   p.alpha = alpha;
   static const int gm_env = getenv("A3_GEMM_GROUP_M") ? atoi(getenv("A3_GEMM_GROUP_M")) : 0;  // tuning experiments
   p.group_m = gm_env > 0 ? gm_env : 16;
+  set_cache_hints(p);
   p.swiglu_F = 0; p.C2 = nullptr; p.ldc2 = 0; p.dswiglu_gu = nullptr; p.ldgu = 0;
   p.a_rows = a_rows;
   p.patch_g = 0; p.patch_p = 0;
@@ -830,7 +848,7 @@ extern "C" int a3_gemm_bf16(const void* A, const void* B, void* C, int M, int N,
 static void init_params(a3::GemmParams& p, int M, int N, int K) {
   p.C = nullptr; p.bias = nullptr; p.residual = nullptr; p.rope = nullptr; p.ldc = 0; p.ldr = 0;
   p.rope_cols = 0; p.rope_period = 1; p.rope_pos0 = 0; p.M = M; p.N = N; p.K = K; p.a_mn = 0; p.b_mn = 0;
-  p.act = 0; p.out_fp32 = 0; p.accumulate = 0; p.alpha = 1.f; p.group_m = 16; p.swiglu_F = 0; p.C2 = nullptr;
+  p.act = 0; p.out_fp32 = 0; p.accumulate = 0; p.alpha = 1.f; p.group_m = 16; set_cache_hints(p); p.swiglu_F = 0; p.C2 = nullptr;
   p.ldc2 = 0; p.dswiglu_gu = nullptr; p.ldgu = 0; p.a_rows = a3::BM; p.patch_g = 0; p.patch_p = 0;
 }
 

@@ -331,6 +331,16 @@ __device__ __forceinline__ void tma_load_2d_2sm_s(uint32_t smem_dst, const CUten
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
 }
+// Same with an L2 cache-policy operand (createpolicy encodings: 0x1000000000000000 evict-normal,
+// 0x12F0000000000000 evict-first, 0x14F0000000000000 evict-last).
+__device__ __forceinline__ void tma_load_2d_2sm_h(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr,
+                                                  int c0, int c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_slot, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                    smem_u32(smem_slot)),
