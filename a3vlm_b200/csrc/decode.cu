@@ -332,16 +332,10 @@ attn_decode_partial_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloa
                            const __nv_bfloat16* __restrict__ vc, float* __restrict__ scratch, int H,
                            int ctx, int max_seq, long long ldq, float scale_log2,
                            const int* __restrict__ pos_dev, int* __restrict__ counters,
-                           __nv_bfloat16* __restrict__ o, long long ldo, int prewait) {
+                           __nv_bfloat16* __restrict__ o, long long ldo) {
   constexpr int HD = 128;
   __shared__ bool s_last;
-  const bool pre = prewait != 0;
-  if (!pre) {
-    griddep_launch();
-    griddep_wait();
-  }
-  if (pos_dev) ctx = *pos_dev + 1;  // CUDA-graph replay: the context length lives in device memory (written by the
-                                    // host before the step's first launch, so it may be read before the wait)
+  if (pos_dev) ctx = *pos_dev + 1;  // CUDA-graph replay: the context length lives in device memory
   __shared__ float s_acc[DEC_WARPS][HD];
   __shared__ float s_m[DEC_WARPS], s_l[DEC_WARPS];
   const int bh = blockIdx.x, b = bh / H, h = bh % H;
@@ -349,51 +343,25 @@ attn_decode_partial_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloa
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int per = (ctx + nsplit - 1) / nsplit;
   const int k_begin = split * per, k_end = min(ctx, k_begin + per);
+  const uint2 qraw = *reinterpret_cast<const uint2*>(q + b * ldq + h * HD + lane * 4);
+  const float2 q01 = unpack_bf16x2(qraw.x), q23 = unpack_bf16x2(qraw.y);
+  float m = -INFINITY, l = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f, a3v = 0.f;
   const long long base = ((long long)b * max_seq) * H * HD + h * HD + lane * 4;
   // 8 keys per warp in flight: all K / V loads of a group are issued before the dependent
   // online-softmax chain (one L2 round trip per group instead of per key)
   constexpr int KU = 8;
-  uint2 kr[KU], vr[KU];
-  const int t_first = k_begin + warp;
-  auto load_round = [&](int t0, int limit) {
+  for (int t0 = k_begin + warp; t0 < k_end; t0 += DEC_WARPS * KU) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // a PDL successor may start prefetching weights
+    uint2 kr[KU], vr[KU];
 #pragma unroll
     for (int u = 0; u < KU; ++u) {
       const int t = t0 + u * DEC_WARPS;
-      if (t < limit) {
+      if (t < k_end) {
         const long long off = base + (long long)t * H * HD;
         kr[u] = *reinterpret_cast<const uint2*>(kc + off);
         vr[u] = *reinterpret_cast<const uint2*>(vc + off);
       }
     }
-  };
-  if (pre) {
-    // Every cache position but the newest (ctx - 1, written by the projection that precedes this kernel) dates from
-    // earlier steps: the first round of K / V loads is issued -- and the later rounds' lines are requested into L2 --
-    // BEFORE the programmatic-dependent-launch wait, i.e. while the QKV projection is still streaming its weights.
-    load_round(t_first, min(k_end, ctx - 1));
-    for (int j = lane >> 2; j < 2 * KU; j += 8) {  // the next two rounds only: a bounded L2 footprint at large batch
-      const int t = t_first + DEC_WARPS * (KU + j);
-      if (t >= k_end) break;
-      const __nv_bfloat16* src = ((lane & 2) ? vc : kc) + ((long long)b * max_seq + t) * H * HD + h * HD + (lane & 1) * 64;
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
-    }
-    griddep_launch();
-    griddep_wait();
-#pragma unroll
-    for (int u = 0; u < KU; ++u) {  // the newest key, if it falls into this warp's first round
-      const int t = t_first + u * DEC_WARPS;
-      if (t == ctx - 1 && t < k_end) {
-        const long long off = base + (long long)t * H * HD;
-        kr[u] = *reinterpret_cast<const uint2*>(kc + off);
-        vr[u] = *reinterpret_cast<const uint2*>(vc + off);
-      }
-    }
-  }
-  const uint2 qraw = *reinterpret_cast<const uint2*>(q + b * ldq + h * HD + lane * 4);
-  const float2 q01 = unpack_bf16x2(qraw.x), q23 = unpack_bf16x2(qraw.y);
-  float m = -INFINITY, l = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f, a3v = 0.f;
-  for (int t0 = t_first; t0 < k_end; t0 += DEC_WARPS * KU) {
-    if (!(pre && t0 == t_first)) load_round(t0, k_end);
     float sc[KU];
 #pragma unroll
     for (int u = 0; u < KU; ++u) {
@@ -454,26 +422,14 @@ attn_decode_partial_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloa
   if (!s_last) return;
   __threadfence();
   const volatile float* in = scratch + (long long)bh * nsplit * (HD + 2);
-  float Mx = -INFINITY, Lx = 0.f, Ax = 0.f;
-  for (int s0 = 0; s0 < nsplit; s0 += 8) {  // 3 x 8 independent loads in flight
-    float ms[8], ls[8], as[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int s = min(s0 + u, nsplit - 1);
-      ms[u] = in[s * (HD + 2) + HD];
-      ls[u] = in[s * (HD + 2) + HD + 1];
-      as[u] = in[s * (HD + 2) + d];
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      if (s0 + u < nsplit && ms[u] != -INFINITY) {
-        const float mn = fmaxf(Mx, ms[u]);
-        const float c0 = exp2f(Mx - mn), c1 = exp2f(ms[u] - mn);
-        Lx = Lx * c0 + ls[u] * c1;
-        Ax = Ax * c0 + as[u] * c1;
-        Mx = mn;
-      }
-    }
+  float Mx = -INFINITY;
+  for (int s = 0; s < nsplit; ++s) Mx = fmaxf(Mx, in[s * (HD + 2) + HD]);
+  float Lx = 0.f, Ax = 0.f;
+  for (int s = 0; s < nsplit; ++s) {
+    const float ms = in[s * (HD + 2) + HD];
+    const float c = ms == -INFINITY ? 0.f : exp2f(ms - Mx);
+    Lx += in[s * (HD + 2) + HD + 1] * c;
+    Ax += in[s * (HD + 2) + d] * c;
   }
   o[b * ldo + h * HD + d] = __float2bfloat16_rn(Ax / Lx);
 }
@@ -658,39 +614,17 @@ extern "C" int a3_decode_rope_kv(void* qkv, long long ld, void* kcache, void* vc
 extern "C" int a3_attn_decode(const void* q, const void* kcache, const void* vcache, void* o,
                               float* scratch, int B, int H, int head_dim, int ctx, int max_seq,
                               long long ldq, long long ldo, float scale, const int* pos_dev,
-                              int stable_prefix, void* stream) {
+                              void* stream) {
   if (head_dim != 128) return set_error(A3_ERR_UNSUPPORTED, "a3_attn_decode: head_dim must be 128");
   if (ctx <= 0 || ctx > max_seq) return set_error(A3_ERR_ARG, "a3_attn_decode: 0 < ctx <= max_seq");
   if (B * H <= 0) return A3_OK;
-  // ~192 keys per CTA (a warp scans its share in a few rounds of 8 loads), at least two CTAs per SM at small batch,
-  // at most ~64 CTAs per SM at large batch.  Measured at batch 1, ctx 900: 10 splits 2.95 ms/token, 32 splits 3.00;
-  // batch 16: 10 splits 6.0 ms, 1 split 8.3 ms.
-  const int BH = B * H;
-#ifdef A3_DEC_OLD_SPLIT  // round-1 heuristic, kept for A/B builds
-  int nsplit = (2 * num_sms() + BH - 1) / BH;
-#else
-  int nsplit = (ctx + 191) / 192;
-  nsplit = max(nsplit, (2 * num_sms() + BH - 1) / BH);
-  nsplit = min(nsplit, max(1, 64 * num_sms() / BH));
-#endif
+  int nsplit = (2 * num_sms() + B * H - 1) / (B * H);
   const int max_useful = (ctx + 4 * DEC_WARPS - 1) / (4 * DEC_WARPS);
   if (!pos_dev && nsplit > max_useful) nsplit = max_useful;  // graph mode: split count must not depend on ctx
   if (nsplit > DEC_MAX_SPLIT) nsplit = DEC_MAX_SPLIT;
   if (nsplit < 1) nsplit = 1;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(B * H, nsplit);
-  cfg.blockDim = dim3(DEC_WARPS * 32);
-  cfg.dynamicSmemBytes = 0;
-  cfg.stream = ST(stream);
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(
-      &cfg, attn_decode_partial_kernel, BF(q), BF(kcache), BF(vcache), scratch, H, ctx, max_seq, ldq,
-      scale * 1.4426950408889634f, pos_dev, reinterpret_cast<int*>(scratch + (long long)B * H * DEC_MAX_SPLIT * (128 + 2)),
-      BFM(o), ldo, stable_prefix ? 1 : 0);
-  if (e != cudaSuccess) return set_error(A3_ERR_CUDA, cudaGetErrorString(e));
+  attn_decode_partial_kernel<<<dim3(B * H, nsplit), DEC_WARPS * 32, 0, ST(stream)>>>(
+      BF(q), BF(kcache), BF(vcache), scratch, H, ctx, max_seq, ldq, scale * 1.4426950408889634f, pos_dev,
+      reinterpret_cast<int*>(scratch + (long long)B * H * DEC_MAX_SPLIT * (128 + 2)), BFM(o), ldo);
   return check_launch("a3_attn_decode");
 }

@@ -869,9 +869,6 @@ class Engine:
         B, D, F = d["B"], a.dim, self.ffn_dim
         ops.embed_splice(d["tok"], w["tok_embeddings.weight"], None, None, None, d["x"], B, 1, 0, D)
         x, x2 = d["x"], d["x2"]
-        # the attention kernel may read every cache position but the newest before the projection in front of it has
-        # finished (decode); A3_DEC_PREWAIT=0 turns that off for A/B timing
-        early = dict(stable_prefix=os.environ.get("A3_DEC_PREWAIT", "1") != "0")
         if B <= self.decode_fused_max_b:
             # five launches per layer: every norm / activation / RoPE / cache write is a prologue or
             # epilogue of the weight-streaming projection that consumes or produces it
@@ -885,8 +882,7 @@ class Engine:
                                       pos_dev=d["pos"], max_seq=a.max_seq_len)
                 if "attn" not in skip:
                     ops.attn_decode(d["qkv"][:, :D], self.kcache[i], self.vcache[i], d["o"], d["scratch"], B,
-                                    a.n_heads, self.head_dim, a.max_seq_len, a.max_seq_len, self.scale, pos_dev=d["pos"],
-                                    **early)
+                                    a.n_heads, self.head_dim, a.max_seq_len, a.max_seq_len, self.scale, pos_dev=d["pos"])
                 if "wo" not in skip:
                     ops.decode_linear(d["o"], w[p + "attention.wo.weight"], d["h"], residual=x)
                 if gated:  # the gate is the epilogue of the w1|w3 projection: gu never reaches HBM
@@ -916,8 +912,7 @@ class Engine:
             ops.decode_rope_kv(d["qkv"], self.kcache[i], self.vcache[i], B, a.n_heads, self.head_dim, self.rope,
                                0, a.max_seq_len, pos_dev=d["pos"])
             ops.attn_decode(d["qkv"][:, :D], self.kcache[i], self.vcache[i], d["o"], d["scratch"], B,
-                            a.n_heads, self.head_dim, a.max_seq_len, a.max_seq_len, self.scale, pos_dev=d["pos"],
-                            **early)
+                            a.n_heads, self.head_dim, a.max_seq_len, a.max_seq_len, self.scale, pos_dev=d["pos"])
             lin(d["o"], w[p + "attention.wo.weight"], d["h"], residual=x)
             ops.rmsnorm_fwd(d["h"], w[p + "ffn_norm.weight"], a.norm_eps, out=d["xn"])
             lin(d["xn"], w[p + "w13"], d["gu"])

@@ -252,9 +252,9 @@ def attn_bwd(q, k, v, o, dout, lse, delta, dq_acc, dq, dk, dv, B, H, T, head_dim
     _lib.check(rc, "a3_attn_bwd")
 
 
-def attn_decode(q, kcache, vcache, out, scratch, B, H, head_dim, ctx, max_seq, scale, pos_dev=None, stable_prefix=False):
+def attn_decode(q, kcache, vcache, out, scratch, B, H, head_dim, ctx, max_seq, scale, pos_dev=None):
     rc = _L().a3_attn_decode(_p(q), _p(kcache), _p(vcache), _p(out), _p(scratch), B, H, head_dim, ctx,
-                             max_seq, q.stride(0), out.stride(0), float(scale), _p(pos_dev), int(bool(stable_prefix)), _st())
+                             max_seq, q.stride(0), out.stride(0), float(scale), _p(pos_dev), _st())
     _lib.check(rc, "a3_attn_decode")
     return out
 

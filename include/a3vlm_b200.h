@@ -177,13 +177,9 @@ int a3_attn_bwd(const void* q, const void* k, const void* v, const void* o, cons
  * arrival counters that reset themselves; the last split to finish merges the partial results).
  * pos_dev != NULL (CUDA-graph replay): ctx = *pos_dev + 1 is read on the device and `ctx` is only an
  * upper bound used to size the split. */
-/* stable_prefix != 0: the caller guarantees that every cache position except the newest (ctx - 1) was written before
- * the kernels still in flight on the stream started (true inside a decode step: the preceding projection writes only
- * the newest position) and that *pos_dev was written by the host; the kernel is launched with programmatic dependent
- * launch and reads those positions while its predecessor drains. */
 int a3_attn_decode(const void* q, const void* kcache, const void* vcache, void* o, float* scratch,
                    int B, int H, int head_dim, int ctx, int max_seq, long long ldq, long long ldo,
-                   float scale, const int* pos_dev, int stable_prefix, void* stream);
+                   float scale, const int* pos_dev, void* stream);
 /* Decode-step fusion of apply_rotary_emb + cache write (llama_ens5.py:118-127, seqlen 1): rotates q
  * and k of qkv [B][3*H*128] in place at position pos (or *pos_dev) and writes k, v into
  * cache[b, pos]. */
