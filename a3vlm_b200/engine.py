@@ -242,7 +242,12 @@ class Engine:
             raise NotImplementedError("decoder head_dim must be 128 (7B / 13B)")
         self.ffn_dim = ffn_hidden_dim(a.dim, a.multiple_of, a.ffn_dim_multiplier)
         self.fuse_swiglu = self.ffn_dim % 128 == 0      # forward: gate in the w1|w3 epilogue (-40 us / layer)
-        self.fuse_dswiglu = False  # backward: fused epilogue measured slower than dgrad + a3_swiglu_bwd
+        # backward: gate backward as the epilogue of the w2 dgrad (dy never reaches HBM), A3_FUSE_DSWIGLU=1: 675 us per layer
+        # against 489 + 138 unfused -- the epilogue is a latency chain as long as the main loop at K 4096.  Prefetching the
+        # saved g | u (and the residual rows of the generic epilogue) one chunk ahead was built in round 2: 568 us in
+        # isolation, but at 165 registers the GEMMs of a live step dropped from 0.82 to 0.77 of burst and the step did not
+        # move (272.9 vs 273.1 / 273.4 ms, power-capped) -- reverted; plain dgrad + a3_swiglu_bwd stays the default
+        self.fuse_dswiglu = os.environ.get("A3_FUSE_DSWIGLU", "0") == "1"
         self.n_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         self.rope = ops.rope_table(self.head_dim, a.max_seq_len * 2, a.rope_theta, device=self.device)
         # one view: start + N + end; reference tiling: 5 views of a (2S x 2S) image (llama_ens5.py:383-385)

@@ -214,18 +214,23 @@ def test_swiglu(ops):
     close_bf16(dgu[:, F:], uf.grad, rtol=2 ** -6, atol=2e-2)
 
 
-@pytest.mark.parametrize("M", [200, 835])
-def test_gemm_fused_swiglu_fwd_bwd(ops, M):
-    """The gate fused into the tcgen05 epilogues == the unfused kernel sequences it replaces."""
+@pytest.mark.parametrize("M,F", [(200, 640), (835, 640), (1000, 1160)])
+def test_gemm_fused_swiglu_fwd_bwd(ops, M, F):
+    """The gate fused into the tcgen05 epilogues == the unfused kernel sequences it replaces (single-CTA kernel at
+    M 200, the CTA-pair kernel with its coalesced staged gate-backward epilogue otherwise; F 1160 = 128 * 9 + 8 leaves a
+    partial 16-byte piece pattern in the last column tile of the backward)."""
     torch.manual_seed(M)
-    K, F = 256, 640
+    K = 256
     x, w13, w2, d = rnd(M, K), rnd(2 * F, K, scale=0.06), rnd(K, F, scale=0.05), rnd(M, K)
     gu_ref = ops.gemm(x, w13)
     y_ref = ops.swiglu_fwd(gu_ref)
-    gu, y = torch.empty_like(gu_ref), torch.empty_like(y_ref)
-    ops.gemm_swiglu(x, w13, gu, y)
-    close_bf16(gu, gu_ref, atol=2e-3)  # same MMAs, different tile shape -> same values up to accumulation order
-    close_bf16(y, ops.swiglu_fwd(gu), rtol=0, atol=0)  # y is exactly the gate of the gu it wrote
+    if F % 128 == 0:  # the fused forward needs whole 128-feature tiles
+        gu, y = torch.empty_like(gu_ref), torch.empty_like(y_ref)
+        ops.gemm_swiglu(x, w13, gu, y)
+        close_bf16(gu, gu_ref, atol=2e-3)  # same MMAs, different tile shape -> same values up to accumulation order
+        close_bf16(y, ops.swiglu_fwd(gu), rtol=0, atol=0)  # y is exactly the gate of the gu it wrote
+    else:
+        gu = gu_ref
     dy = ops.gemm(d, w2, b_mn=True)
     dgu_ref = torch.empty_like(gu)
     ops.swiglu_bwd(gu, dy, dgu_ref)
