@@ -110,7 +110,7 @@ struct DecLinParams {
   const __nv_bfloat16* norm_w; const __nv_bfloat16* residual;
   const float2* rope; __nv_bfloat16* kc; __nv_bfloat16* vc; const int* pos_dev;
   long long ldx, ldw, ldy, ldr;
-  int N, K, mode /*0 plain, 1 rmsnorm, 2 swiglu*/, out_fp32, n_heads, pos, max_seq;
+  int N, K, mode /*0 plain, 1 rmsnorm, 2 swiglu*/, out_fp32, n_heads, n_kv_heads, pos, max_seq;
   int gate_F;  // > 0: W = w1 | w3 ([2F][K]); a warp owns ONE feature n (rows n and F + n) and writes
                // y[n] = bf16(silu(g)) * u -- the gated SiLU as the epilogue (llama_ens5.py:213-214); N = F tasks
   float eps;
@@ -206,10 +206,11 @@ __device__ __forceinline__ void store_outputs(const DecLinParams& p, int n, cons
       return;
     }
     if (p.rope) {
-      // QKV projection: n is even, so this warp owns one RoPE pair (or a v pair)
-      const int D = p.n_heads * 128;
+      // QKV projection (columns q [0, D) | k [D, D + Dkv) | v): n is even, so this warp owns one RoPE pair (or a v pair)
+      const int D = p.n_heads * 128, Dkv = p.n_kv_heads * 128;
       const int pos = p.pos_dev ? *p.pos_dev : p.pos;
-      const int sect = n / D, within = n - sect * D;  // 0 q, 1 k, 2 v
+      const int sect = n < D ? 0 : (n < D + Dkv ? 1 : 2);  // 0 q, 1 k, 2 v
+      const int within = sect == 0 ? n : n - D - (sect - 1) * Dkv;
       const float2 cs = p.rope[(long long)pos * 64 + ((within & 127) >> 1)];
 #pragma unroll
       for (int m = 0; m < M; ++m) {
@@ -219,7 +220,7 @@ __device__ __forceinline__ void store_outputs(const DecLinParams& p, int n, cons
         *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(p.Y) + m * p.ldy + n) = r;
         if (sect >= 1) {
           __nv_bfloat16* cache = sect == 1 ? p.kc : p.vc;
-          *reinterpret_cast<uint32_t*>(cache + ((long long)m * p.max_seq + pos) * D + within) = r;
+          *reinterpret_cast<uint32_t*>(cache + ((long long)m * p.max_seq + pos) * Dkv + within) = r;
         }
       }
       return;
@@ -329,7 +330,7 @@ constexpr int DEC_MAX_SPLIT = 32;
 
 __global__ void __launch_bounds__(DEC_WARPS * 32)
 attn_decode_partial_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kc,
-                           const __nv_bfloat16* __restrict__ vc, float* __restrict__ scratch, int H,
+                           const __nv_bfloat16* __restrict__ vc, float* __restrict__ scratch, int H, int Hkv,
                            int ctx, int max_seq, long long ldq, float scale_log2,
                            const int* __restrict__ pos_dev, int* __restrict__ counters,
                            __nv_bfloat16* __restrict__ o, long long ldo) {
@@ -346,7 +347,7 @@ attn_decode_partial_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloa
   const uint2 qraw = *reinterpret_cast<const uint2*>(q + b * ldq + h * HD + lane * 4);
   const float2 q01 = unpack_bf16x2(qraw.x), q23 = unpack_bf16x2(qraw.y);
   float m = -INFINITY, l = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f, a3v = 0.f;
-  const long long base = ((long long)b * max_seq) * H * HD + h * HD + lane * 4;
+  const long long base = ((long long)b * max_seq) * Hkv * HD + (h / (H / Hkv)) * HD + lane * 4;  // group head of h
   // 8 keys per warp in flight: all K / V loads of a group are issued before the dependent
   // online-softmax chain (one L2 round trip per group instead of per key)
   constexpr int KU = 8;
@@ -357,7 +358,7 @@ attn_decode_partial_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloa
     for (int u = 0; u < KU; ++u) {
       const int t = t0 + u * DEC_WARPS;
       if (t < k_end) {
-        const long long off = base + (long long)t * H * HD;
+        const long long off = base + (long long)t * Hkv * HD;
         kr[u] = *reinterpret_cast<const uint2*>(kc + off);
         vr[u] = *reinterpret_cast<const uint2*>(vc + off);
       }
@@ -458,27 +459,28 @@ attn_decode_combine_kernel(const float* __restrict__ scratch, __nv_bfloat16* __r
 // pos_dev != null so the whole decode step can be replayed as one CUDA graph.
 __global__ void __launch_bounds__(64)
 decode_rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, long long ld, __nv_bfloat16* __restrict__ kc,
-                      __nv_bfloat16* __restrict__ vc, int H, const float2* __restrict__ table,
+                      __nv_bfloat16* __restrict__ vc, int H, int Hkv, const float2* __restrict__ table,
                       const int* __restrict__ pos_dev, int pos_host, int max_seq) {
   constexpr int HD = 128;
   const int pos = pos_dev ? *pos_dev : pos_host;
   const int b = blockIdx.x / H, h = blockIdx.x % H, j = threadIdx.x;
-  const long long D = (long long)H * HD;
+  const long long D = (long long)H * HD, Dkv = (long long)Hkv * HD;
   __nv_bfloat16* row = qkv + b * ld + h * HD + 2 * j;
   const float2 cs = table[(long long)pos * (HD / 2) + j];
-  const long long ci = (((long long)b * max_seq + pos) * H + h) * HD + 2 * j;
   {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // a PDL successor may start prefetching weights
     const float2 x = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(row));
     *reinterpret_cast<uint32_t*>(row) = pack_bf16x2(x.x * cs.x - x.y * cs.y, x.x * cs.y + x.y * cs.x);
   }
+  if (h >= Hkv) return;  // the blocks of the first Hkv heads also rotate / append the k and v head of the same index
+  const long long ci = (((long long)b * max_seq + pos) * Hkv + h) * HD + 2 * j;
   {
     const float2 x = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(row + D));
     const uint32_t r = pack_bf16x2(x.x * cs.x - x.y * cs.y, x.x * cs.y + x.y * cs.x);
     *reinterpret_cast<uint32_t*>(row + D) = r;
     *reinterpret_cast<uint32_t*>(kc + ci) = r;
   }
-  *reinterpret_cast<uint32_t*>(vc + ci) = *reinterpret_cast<const uint32_t*>(row + 2 * D);
+  *reinterpret_cast<uint32_t*>(vc + ci) = *reinterpret_cast<const uint32_t*>(row + D + Dkv);
 }
 
 }  // namespace a3
@@ -552,7 +554,7 @@ static int launch_decode_linear(const DecLinParams& p, cudaStream_t s) {
 extern "C" int a3_decode_linear(const void* X, const void* W, void* Y, int M, int N, int K,
                                 long long ldx, long long ldw, long long ldy, const void* norm_w,
                                 float eps, int swiglu, const void* residual, long long ldr,
-                                int out_fp32, const float* rope_table, int n_heads, void* kcache,
+                                int out_fp32, const float* rope_table, int n_heads, int n_kv_heads, void* kcache,
                                 void* vcache, const int* pos_dev, int pos, int max_seq,
                                 void* stream) {
   if (M <= 0 || N <= 0) return A3_OK;
@@ -562,14 +564,15 @@ extern "C" int a3_decode_linear(const void* X, const void* W, void* Y, int M, in
     return set_error(A3_ERR_ARG, "a3_decode_linear: K, ldx, ldw % 8 == 0 and 16-byte alignment");
   if ((size_t)M * K * 2 > 200 * 1024) return set_error(A3_ERR_ARG, "a3_decode_linear: M*K too large for smem staging");
   if (norm_w && swiglu) return set_error(A3_ERR_ARG, "a3_decode_linear: norm and swiglu prologues are exclusive");
-  if (rope_table && (N != 3 * n_heads * 128 || out_fp32 || residual || !kcache || !vcache || (ldy & 1)))
-    return set_error(A3_ERR_ARG, "a3_decode_linear: rope epilogue needs N == 3*H*128, bf16 out, caches");
+  if (rope_table && (n_kv_heads <= 0 || n_heads % n_kv_heads || N != (n_heads + 2 * n_kv_heads) * 128 || out_fp32 ||
+                     residual || !kcache || !vcache || (ldy & 1)))
+    return set_error(A3_ERR_ARG, "a3_decode_linear: rope epilogue needs N == (H + 2*Hkv)*128, H % Hkv == 0, bf16 out, caches");
   DecLinParams p;
   p.X = BF(X); p.W = BF(W); p.Y = Y; p.norm_w = BF(norm_w); p.residual = BF(residual);
   p.rope = reinterpret_cast<const float2*>(rope_table); p.kc = BFM(kcache); p.vc = BFM(vcache);
   p.pos_dev = pos_dev; p.ldx = ldx; p.ldw = ldw; p.ldy = ldy; p.ldr = ldr;
   p.N = N; p.K = K; p.mode = norm_w ? 1 : (swiglu ? 2 : 0); p.out_fp32 = out_fp32;
-  p.n_heads = n_heads; p.pos = pos; p.max_seq = max_seq; p.eps = eps; p.gate_F = 0;
+  p.n_heads = n_heads; p.n_kv_heads = n_kv_heads; p.pos = pos; p.max_seq = max_seq; p.eps = eps; p.gate_F = 0;
   cudaStream_t s = ST(stream);
 #define CASE(m) case m: return launch_decode_linear<m>(p, s);
   switch (M) { CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) }
@@ -589,7 +592,7 @@ extern "C" int a3_decode_linear_gated(const void* X, const void* W13, void* Y, i
   p.X = BF(X); p.W = BF(W13); p.Y = Y; p.norm_w = BF(norm_w); p.residual = nullptr;
   p.rope = nullptr; p.kc = nullptr; p.vc = nullptr; p.pos_dev = nullptr;
   p.ldx = ldx; p.ldw = ldw; p.ldy = ldy; p.ldr = 0;
-  p.N = F; p.K = K; p.mode = norm_w ? 1 : 0; p.out_fp32 = 0; p.n_heads = 0; p.pos = 0; p.max_seq = 0; p.eps = eps;
+  p.N = F; p.K = K; p.mode = norm_w ? 1 : 0; p.out_fp32 = 0; p.n_heads = 0; p.n_kv_heads = 0; p.pos = 0; p.max_seq = 0; p.eps = eps;
   p.gate_F = F;
   cudaStream_t s = ST(stream);
 #define CASE(m) case m: return launch_decode_linear<m>(p, s);
@@ -598,33 +601,34 @@ extern "C" int a3_decode_linear_gated(const void* X, const void* W13, void* Y, i
   return A3_ERR_ARG;
 }
 
-extern "C" int a3_decode_rope_kv(void* qkv, long long ld, void* kcache, void* vcache, int B, int H,
+extern "C" int a3_decode_rope_kv(void* qkv, long long ld, void* kcache, void* vcache, int B, int H, int Hkv,
                                  int head_dim, const float* table, int pos, const int* pos_dev,
                                  int max_seq, void* stream) {
   if (head_dim != 128) return set_error(A3_ERR_UNSUPPORTED, "a3_decode_rope_kv: head_dim must be 128");
-  if ((ld & 1) || (!pos_dev && (pos < 0 || pos >= max_seq)))
-    return set_error(A3_ERR_ARG, "a3_decode_rope_kv: 0 <= pos < max_seq");
+  if ((ld & 1) || (!pos_dev && (pos < 0 || pos >= max_seq)) || Hkv <= 0 || H % Hkv)
+    return set_error(A3_ERR_ARG, "a3_decode_rope_kv: 0 <= pos < max_seq, H % Hkv == 0");
   if (B * H <= 0) return A3_OK;
-  decode_rope_kv_kernel<<<B * H, 64, 0, ST(stream)>>>(BFM(qkv), ld, BFM(kcache), BFM(vcache), H,
+  decode_rope_kv_kernel<<<B * H, 64, 0, ST(stream)>>>(BFM(qkv), ld, BFM(kcache), BFM(vcache), H, Hkv,
                                                      reinterpret_cast<const float2*>(table), pos_dev, pos,
                                                      max_seq);
   return check_launch("a3_decode_rope_kv");
 }
 
 extern "C" int a3_attn_decode(const void* q, const void* kcache, const void* vcache, void* o,
-                              float* scratch, int B, int H, int head_dim, int ctx, int max_seq,
+                              float* scratch, int B, int H, int Hkv, int head_dim, int ctx, int max_seq,
                               long long ldq, long long ldo, float scale, const int* pos_dev,
                               void* stream) {
   if (head_dim != 128) return set_error(A3_ERR_UNSUPPORTED, "a3_attn_decode: head_dim must be 128");
   if (ctx <= 0 || ctx > max_seq) return set_error(A3_ERR_ARG, "a3_attn_decode: 0 < ctx <= max_seq");
   if (B * H <= 0) return A3_OK;
+  if (Hkv <= 0 || H % Hkv) return set_error(A3_ERR_ARG, "a3_attn_decode: n_heads % n_kv_heads == 0");
   int nsplit = (2 * num_sms() + B * H - 1) / (B * H);
   const int max_useful = (ctx + 4 * DEC_WARPS - 1) / (4 * DEC_WARPS);
   if (!pos_dev && nsplit > max_useful) nsplit = max_useful;  // graph mode: split count must not depend on ctx
   if (nsplit > DEC_MAX_SPLIT) nsplit = DEC_MAX_SPLIT;
   if (nsplit < 1) nsplit = 1;
   attn_decode_partial_kernel<<<dim3(B * H, nsplit), DEC_WARPS * 32, 0, ST(stream)>>>(
-      BF(q), BF(kcache), BF(vcache), scratch, H, ctx, max_seq, ldq, scale * 1.4426950408889634f, pos_dev,
+      BF(q), BF(kcache), BF(vcache), scratch, H, Hkv, ctx, max_seq, ldq, scale * 1.4426950408889634f, pos_dev,
       reinterpret_cast<int*>(scratch + (long long)B * H * DEC_MAX_SPLIT * (128 + 2)), BFM(o), ldo);
   return check_launch("a3_attn_decode");
 }

@@ -1,6 +1,7 @@
 // Gather / scatter, ViT front end, loss, sampling and optimiser kernels of the hot path.  All are
 // HBM-bound byte movers or row reductions: 16-byte vector accesses, one CTA per row or a
 // grid-stride over flat ranges sized in multiples of the SM count.
+#include <cstdio>
 #include "common.cuh"
 #include "ptx.cuh"
 #include <cuda_fp16.h>
@@ -495,6 +496,56 @@ __global__ void kv_append_kernel(const __nv_bfloat16* __restrict__ k, const __nv
   }
 }
 
+
+// ------------------------------------------------------------------ grouped-query attention glue
+// The reference materialises the repeated K / V heads for its SDPA branch (repeat_kv, absent LLM/llama.py; call
+// llama_ens5.py:131-133): expanded head h = group head h / n_rep.  expand: compact [rows][D + 2 Dkv] (q | k | v with Hkv
+// heads) -> expanded [rows][3 D]; reduce: its backward -- dq copied, dk / dv summed over the n_rep copies of a group
+// (fp32, one rounding).  16-byte vectors; one thread per 8 output elements.
+__global__ void __launch_bounds__(256)
+repeat_kv_kernel(const __nv_bfloat16* __restrict__ in, long long ld_in, __nv_bfloat16* __restrict__ out, long long ld_out,
+                 long long rows, int H, int Hkv, int hd) {
+  const int D = H * hd, Dkv = Hkv * hd, n_rep = H / Hkv, vec_per_row = 3 * D / 8;
+  const long long total = rows * vec_per_row;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / vec_per_row;
+    const int col = (int)(i - r * vec_per_row) * 8;
+    const int sect = col / D, within = col - sect * D;
+    const int src = sect == 0 ? col : D + (sect - 1) * Dkv + (within / hd / n_rep) * hd + within % hd;
+    *reinterpret_cast<uint4*>(out + r * ld_out + col) = *reinterpret_cast<const uint4*>(in + r * ld_in + src);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+reduce_kv_kernel(const __nv_bfloat16* __restrict__ in, long long ld_in, __nv_bfloat16* __restrict__ out, long long ld_out,
+                 long long rows, int H, int Hkv, int hd) {
+  const int D = H * hd, Dkv = Hkv * hd, n_rep = H / Hkv, vec_per_row = (D + 2 * Dkv) / 8;
+  const long long total = rows * vec_per_row;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / vec_per_row;
+    const int col = (int)(i - r * vec_per_row) * 8;
+    if (col < D) {
+      *reinterpret_cast<uint4*>(out + r * ld_out + col) = *reinterpret_cast<const uint4*>(in + r * ld_in + col);
+      continue;
+    }
+    const int sect = (col - D) / Dkv, within = (col - D) - sect * Dkv;  // 0 = k, 1 = v
+    const int g = within / hd, e = within % hd;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int rep = 0; rep < n_rep; ++rep) {
+      const uint4 q = *reinterpret_cast<const uint4*>(in + r * ld_in + (sect + 1) * D + (g * n_rep + rep) * hd + e);
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = unpack_bf16x2(w[t]);
+        acc[2 * t] += f.x;
+        acc[2 * t + 1] += f.y;
+      }
+    }
+    *reinterpret_cast<uint4*>(out + r * ld_out + col) =
+        make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+  }
+}
+
 }  // namespace a3
 
 using namespace a3;
@@ -634,6 +685,40 @@ extern "C" int a3_cast_f32_bf16(const float* in, void* out, long long n, void* s
   if (blocks < 1) blocks = 1;
   cast_f32_bf16_kernel<<<(int)blocks, 256, 0, ST(stream)>>>(in, BFM(out), n);
   return check_launch("a3_cast_f32_bf16");
+}
+
+
+static int gqa_args_ok(const char* who, const void* a, const void* b, long long lda, long long ldb, long long rows, int H,
+                       int Hkv, int hd) {
+  if (rows < 0 || H <= 0 || Hkv <= 0 || H % Hkv || hd <= 0 || (hd & 7) || (lda & 7) || (ldb & 7) ||
+      ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15)) {
+    char buf[160];
+    std::snprintf(buf, sizeof(buf), "%s: n_heads %% n_kv_heads == 0, head_dim %% 8 == 0, strides %% 8 == 0, 16-byte aligned pointers", who);
+    return set_error(A3_ERR_ARG, buf);
+  }
+  return A3_OK;
+}
+
+extern "C" int a3_repeat_kv(const void* qkv_compact, long long ld_compact, void* qkv, long long ld, long long rows,
+                            int n_heads, int n_kv_heads, int head_dim, void* stream) {
+  if (int rc = gqa_args_ok("a3_repeat_kv", qkv_compact, qkv, ld_compact, ld, rows, n_heads, n_kv_heads, head_dim)) return rc;
+  if (rows == 0) return A3_OK;
+  const long long vec = rows * (3LL * n_heads * head_dim / 8);
+  long long blocks = (vec + 255) / 256;
+  if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
+  repeat_kv_kernel<<<(int)blocks, 256, 0, ST(stream)>>>(BF(qkv_compact), ld_compact, BFM(qkv), ld, rows, n_heads, n_kv_heads, head_dim);
+  return check_launch("a3_repeat_kv");
+}
+
+extern "C" int a3_reduce_kv(const void* dqkv, long long ld, void* dqkv_compact, long long ld_compact, long long rows,
+                            int n_heads, int n_kv_heads, int head_dim, void* stream) {
+  if (int rc = gqa_args_ok("a3_reduce_kv", dqkv, dqkv_compact, ld, ld_compact, rows, n_heads, n_kv_heads, head_dim)) return rc;
+  if (rows == 0) return A3_OK;
+  const long long vec = rows * ((long long)(n_heads + 2 * n_kv_heads) * head_dim / 8);
+  long long blocks = (vec + 255) / 256;
+  if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
+  reduce_kv_kernel<<<(int)blocks, 256, 0, ST(stream)>>>(BF(dqkv), ld, BFM(dqkv_compact), ld_compact, rows, n_heads, n_kv_heads, head_dim);
+  return check_launch("a3_reduce_kv");
 }
 
 extern "C" int a3_vit_assemble_lnpre(const void* patch_out, const void* cls, const void* pos,

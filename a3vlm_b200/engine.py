@@ -46,6 +46,8 @@ def build_layout(args, vis):
     matrix, so the reference-named parameters are views.  `||` = decay / no-decay boundary."""
     D, V = args.dim, args.vocab_size
     F = ffn_hidden_dim(D, args.multiple_of, args.ffn_dim_multiplier)
+    n_kv = args.n_heads if getattr(args, "n_kv_heads", None) is None else args.n_kv_heads
+    Dkv = n_kv * (D // args.n_heads)  # grouped-query attention: wk / wv have n_kv_heads heads (llama_ens5.py:76-90)
     decay: List[Tuple[str, Tuple[int, ...]]] = []
     nodecay: List[Tuple[str, Tuple[int, ...]]] = []
     if vis is not None:
@@ -56,7 +58,7 @@ def build_layout(args, vis):
     decay.append(("tok_embeddings.weight", (V, D)))
     for i in range(args.n_layers):
         p = f"layers.{i}."
-        decay += [(p + "wqkv", (3 * D, D)), (p + "attention.wo.weight", (D, D)),
+        decay += [(p + "wqkv", (D + 2 * Dkv, D)), (p + "attention.wo.weight", (D, D)),
                   (p + "w13", (2 * F, D)), (p + "feed_forward.w2.weight", (D, F))]
         nodecay += [(p + "attention_norm.weight", (D,)), (p + "ffn_norm.weight", (D,))]
     decay.append(("output.weight", (V, D)))
@@ -232,14 +234,20 @@ class Engine:
             raise ops._lib.A3Error("a3vlm_b200.Engine needs a CUDA (sm_100a) device: there is no CPU path")
         ops._L()  # fail loudly now if the native library is missing
         a = args
-        if a.n_kv_heads not in (None, a.n_heads):
-            raise NotImplementedError("grouped-query attention (n_kv_heads != n_heads) is not built: "
-                                      "the 7B / 13B configs on the path use n_kv_heads = None")
+        # grouped-query attention (llama_ens5.py:66,76-90,131-133): wk / wv and the KV cache carry n_kv_heads heads; the
+        # prefill / training attention kernels run on the repeated heads (a3_repeat_kv, the reference's own repeat_kv
+        # materialisation), the decode kernels index the group head directly
+        self.n_kv = a.n_heads if a.n_kv_heads is None else a.n_kv_heads
+        if self.n_kv <= 0 or a.n_heads % self.n_kv:
+            raise ValueError("n_heads must be a multiple of n_kv_heads")
+        self.n_rep = a.n_heads // self.n_kv
         if a.rope_scaling is not None:
             raise NotImplementedError("rope_scaling: direction cannot be verified from the reference tree")
         self.head_dim = a.dim // a.n_heads
         if self.head_dim != 128:
             raise NotImplementedError("decoder head_dim must be 128 (7B / 13B)")
+        self.kv_dim = self.n_kv * self.head_dim
+        self._gqa_scratch: Dict[Tuple, torch.Tensor] = {}
         self.ffn_dim = ffn_hidden_dim(a.dim, a.multiple_of, a.ffn_dim_multiplier)
         self.fuse_swiglu = self.ffn_dim % 128 == 0      # forward: gate in the w1|w3 epilogue (-40 us / layer)
         # backward: gate backward as the epilogue of the w2 dgrad (dy never reaches HBM), A3_FUSE_DSWIGLU=1: 675 us per layer
@@ -305,7 +313,7 @@ class Engine:
         for name, t in self.w.views.items():
             if name.endswith(".wqkv"):
                 p = name[:-4] + "attention."
-                out[p + "wq.weight"], out[p + "wk.weight"], out[p + "wv.weight"] = t[:D], t[D:2 * D], t[2 * D:]
+                out[p + "wq.weight"], out[p + "wk.weight"], out[p + "wv.weight"] = t[:D], t[D:D + self.kv_dim], t[D + self.kv_dim:]
             elif name.endswith(".w13"):
                 p = name[:-3] + "feed_forward."
                 out[p + "w1.weight"], out[p + "w3.weight"] = t[:F], t[F:]
@@ -324,7 +332,7 @@ class Engine:
         for name, t in self.g.views.items():
             if name.endswith(".wqkv"):
                 p = name[:-4] + "attention."
-                out[p + "wq.weight"], out[p + "wk.weight"], out[p + "wv.weight"] = t[:D], t[D:2 * D], t[2 * D:]
+                out[p + "wq.weight"], out[p + "wk.weight"], out[p + "wv.weight"] = t[:D], t[D:D + self.kv_dim], t[D + self.kv_dim:]
             elif name.endswith(".w13"):
                 p = name[:-3] + "feed_forward."
                 out[p + "w1.weight"], out[p + "w3.weight"] = t[:F], t[F:]
@@ -435,22 +443,43 @@ class Engine:
                           mean=vw["mean"], rstd=vw["rstd"])
         return vw["tok"]
 
+    def _scratch(self, name: str, rows: int, cols: int) -> torch.Tensor:
+        key = (name, rows, cols)
+        t = self._gqa_scratch.get(key)
+        if t is None:
+            t = self._gqa_scratch[key] = torch.empty(rows, cols, device=self.device, dtype=bf16)
+        return t
+
     # ------------------------------------------------------------------------------------ decoder layer
     def _layer_fwd(self, i, x, xn, qkv, o, h, hn, gu, y, out, lse, rstd1, rstd2, B, L, pos0=0,
                    kv=None, skip_out=False):
         a, w, D = self.args, self.w.views, self.args.dim
         p = f"layers.{i}."
         ops.rmsnorm_fwd(x, w[p + "attention_norm.weight"], a.norm_eps, out=xn, rstd=rstd1)
-        ops.gemm(xn, w[p + "wqkv"], qkv, rope=self.rope, rope_cols=2 * D, rope_period=L, rope_pos0=pos0)
+        Dkv = self.kv_dim
+        if self.n_rep == 1:
+            ops.gemm(xn, w[p + "wqkv"], qkv, rope=self.rope, rope_cols=2 * D, rope_period=L, rope_pos0=pos0)
+            kc, vc = qkv[:, D:2 * D], qkv[:, 2 * D:]
+        else:  # compact q | k | v (Hkv key / value heads), then the repeated heads the attention kernels read
+            qc = self._scratch("qkv_c", qkv.shape[0], D + 2 * Dkv)
+            ops.gemm(xn, w[p + "wqkv"], qc, rope=self.rope, rope_cols=D + Dkv, rope_period=L, rope_pos0=pos0)
+            kc, vc = qc[:, D:D + Dkv], qc[:, D + Dkv:]
+            ops.repeat_kv(qc, qkv, a.n_heads, self.n_kv, self.head_dim)
         q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
         if kv is not None:  # LLM/llama_ens5.py:121-127
-            ops.kv_append(k, v, self.kcache[i], self.vcache[i], B, L, a.n_heads, self.head_dim, pos0,
+            ops.kv_append(kc, vc, self.kcache[i], self.vcache[i], B, L, self.n_kv, self.head_dim, pos0,
                           a.max_seq_len)
         if kv is not None and pos0 > 0:  # multi-token step against the cache, right-aligned causal
             Wd = a.n_heads * self.head_dim
-            ops.attn_fwd(q, self.kcache[i].view(-1, Wd), self.vcache[i].view(-1, Wd), B, a.n_heads, L,
+            if self.n_rep == 1:
+                kfull, vfull, bstride = self.kcache[i].view(-1, Wd), self.vcache[i].view(-1, Wd), a.max_seq_len * Wd
+            else:  # rare path (a multi-token append after the prefill): repeat the cached group heads, as the reference does
+                kfull = self.kcache[i][:, :pos0 + L].repeat_interleave(self.n_rep, dim=2).reshape(-1, Wd)
+                vfull = self.vcache[i][:, :pos0 + L].repeat_interleave(self.n_rep, dim=2).reshape(-1, Wd)
+                bstride = (pos0 + L) * Wd
+            ops.attn_fwd(q, kfull, vfull, B, a.n_heads, L,
                          pos0 + L, self.head_dim, self.scale, True, out=o, lse=lse,
-                         kv_bstride=a.max_seq_len * Wd)
+                         kv_bstride=bstride)
         else:
             ops.attn_fwd(q, k, v, B, a.n_heads, L, L, self.head_dim, self.scale, True, out=o, lse=lse)
         ops.gemm(o, w[p + "attention.wo.weight"], h, residual=x)
@@ -555,6 +584,9 @@ class Engine:
             ops.attn_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], ws.o[kb], t, ws.lse[kb], ws.delta, ws.dq_acc,
                          dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], B, a.n_heads, L, self.head_dim,
                          self.scale, True, rope=self.rope)  # backward of RoPE fused into the dq / dk stores
+            if self.n_rep > 1:  # backward of repeat_kv: sum the copies of every group head
+                dqkv = ops.reduce_kv(dqkv, self._scratch("dqkv_c", dqkv.shape[0], D + 2 * self.kv_dim), a.n_heads,
+                                     self.n_kv, self.head_dim)
             wg(dqkv, ws.xn[ks], g[p + "wqkv"])
             dg(dqkv, w[p + "wqkv"], t)
             ops.rmsnorm_bwd(t, ws.x[i], w[p + "attention_norm.weight"], ws.rstd1[ks], d, ws.part2, add_to_dx=True)
@@ -766,7 +798,7 @@ class Engine:
         if self.cache_B == B and self.kcache:
             return
         self.kcache = self.vcache = []
-        shape = (B, a.max_seq_len, a.n_heads, self.head_dim)
+        shape = (B, a.max_seq_len, self.n_kv, self.head_dim)
         self.kcache = [torch.empty(shape, device=self.device, dtype=bf16) for _ in range(a.n_layers)]
         self.vcache = [torch.empty(shape, device=self.device, dtype=bf16) for _ in range(a.n_layers)]
         self.cache_B = B
@@ -842,7 +874,7 @@ class Engine:
             raise ValueError("KV cache overflow")
         if self.dec is None or self.dec["B"] != B:
             e = lambda *s, dt=bf16: torch.empty(*s, device=self.device, dtype=dt)
-            self.dec = {"B": B, "x": e(B, D), "x2": e(B, D), "xn": e(B, D), "qkv": e(B, 3 * D), "o": e(B, D),
+            self.dec = {"B": B, "x": e(B, D), "x2": e(B, D), "xn": e(B, D), "qkv": e(B, D + 2 * self.kv_dim), "o": e(B, D),
                         "h": e(B, D), "gu": e(B, 2 * F), "y": e(B, F),
                         "scratch": torch.zeros(B * a.n_heads * (32 * (self.head_dim + 2) + 1), device=self.device,
                                                dtype=torch.float32),
@@ -883,11 +915,13 @@ class Engine:
                 p = f"layers.{i}."
                 if "qkv" not in skip:
                     ops.decode_linear(x, w[p + "wqkv"], d["qkv"], norm_w=w[p + "attention_norm.weight"], eps=a.norm_eps,
-                                      rope=self.rope, n_heads=a.n_heads, kcache=self.kcache[i], vcache=self.vcache[i],
+                                      rope=self.rope, n_heads=a.n_heads, n_kv_heads=self.n_kv, kcache=self.kcache[i],
+                                      vcache=self.vcache[i],
                                       pos_dev=d["pos"], max_seq=a.max_seq_len)
                 if "attn" not in skip:
                     ops.attn_decode(d["qkv"][:, :D], self.kcache[i], self.vcache[i], d["o"], d["scratch"], B,
-                                    a.n_heads, self.head_dim, a.max_seq_len, a.max_seq_len, self.scale, pos_dev=d["pos"])
+                                    a.n_heads, self.head_dim, a.max_seq_len, a.max_seq_len, self.scale, pos_dev=d["pos"],
+                                    n_kv_heads=self.n_kv)
                 if "wo" not in skip:
                     ops.decode_linear(d["o"], w[p + "attention.wo.weight"], d["h"], residual=x)
                 if gated:  # the gate is the epilogue of the w1|w3 projection: gu never reaches HBM
@@ -915,9 +949,10 @@ class Engine:
             ops.rmsnorm_fwd(x, w[p + "attention_norm.weight"], a.norm_eps, out=d["xn"])
             lin(d["xn"], w[p + "wqkv"], d["qkv"])
             ops.decode_rope_kv(d["qkv"], self.kcache[i], self.vcache[i], B, a.n_heads, self.head_dim, self.rope,
-                               0, a.max_seq_len, pos_dev=d["pos"])
+                               0, a.max_seq_len, pos_dev=d["pos"], n_kv_heads=self.n_kv)
             ops.attn_decode(d["qkv"][:, :D], self.kcache[i], self.vcache[i], d["o"], d["scratch"], B,
-                            a.n_heads, self.head_dim, a.max_seq_len, a.max_seq_len, self.scale, pos_dev=d["pos"])
+                            a.n_heads, self.head_dim, a.max_seq_len, a.max_seq_len, self.scale, pos_dev=d["pos"],
+                            n_kv_heads=self.n_kv)
             lin(d["o"], w[p + "attention.wo.weight"], d["h"], residual=x)
             ops.rmsnorm_fwd(d["h"], w[p + "ffn_norm.weight"], a.norm_eps, out=d["xn"])
             lin(d["xn"], w[p + "w13"], d["gu"])

@@ -105,7 +105,7 @@ def linear_small_m(x, w, out=None, residual=None, out_fp32=False):
 
 
 def decode_linear(x, w, out, *, K=None, norm_w=None, eps=1e-5, swiglu=False, residual=None, out_fp32=False,
-                  rope=None, n_heads=0, kcache=None, vcache=None, pos_dev=None, pos=0, max_seq=0):
+                  rope=None, n_heads=0, n_kv_heads=None, kcache=None, vcache=None, pos_dev=None, pos=0, max_seq=0):
     M = x.shape[0]
     N = w.shape[0]
     if K is None:
@@ -113,7 +113,8 @@ def decode_linear(x, w, out, *, K=None, norm_w=None, eps=1e-5, swiglu=False, res
     rc = _L().a3_decode_linear(_p(x), _p(w), _p(out), M, N, K, x.stride(0), w.stride(0), out.stride(0),
                                _p(norm_w), float(eps), int(swiglu), _p(residual),
                                residual.stride(0) if residual is not None else 0, int(out_fp32), _p(rope),
-                               n_heads, _p(kcache), _p(vcache), _p(pos_dev), int(pos), max_seq, _st())
+                               n_heads, n_heads if n_kv_heads is None else n_kv_heads, _p(kcache), _p(vcache), _p(pos_dev),
+                               int(pos), max_seq, _st())
     _lib.check(rc, "a3_decode_linear")
     return out
 
@@ -252,17 +253,35 @@ def attn_bwd(q, k, v, o, dout, lse, delta, dq_acc, dq, dk, dv, B, H, T, head_dim
     _lib.check(rc, "a3_attn_bwd")
 
 
-def attn_decode(q, kcache, vcache, out, scratch, B, H, head_dim, ctx, max_seq, scale, pos_dev=None):
-    rc = _L().a3_attn_decode(_p(q), _p(kcache), _p(vcache), _p(out), _p(scratch), B, H, head_dim, ctx,
+def attn_decode(q, kcache, vcache, out, scratch, B, H, head_dim, ctx, max_seq, scale, pos_dev=None, n_kv_heads=None):
+    rc = _L().a3_attn_decode(_p(q), _p(kcache), _p(vcache), _p(out), _p(scratch), B, H,
+                             H if n_kv_heads is None else n_kv_heads, head_dim, ctx,
                              max_seq, q.stride(0), out.stride(0), float(scale), _p(pos_dev), _st())
     _lib.check(rc, "a3_attn_decode")
     return out
 
 
-def decode_rope_kv(qkv, kcache, vcache, B, H, head_dim, table, pos, max_seq, pos_dev=None):
-    rc = _L().a3_decode_rope_kv(_p(qkv), qkv.stride(0), _p(kcache), _p(vcache), B, H, head_dim, _p(table),
+def decode_rope_kv(qkv, kcache, vcache, B, H, head_dim, table, pos, max_seq, pos_dev=None, n_kv_heads=None):
+    rc = _L().a3_decode_rope_kv(_p(qkv), qkv.stride(0), _p(kcache), _p(vcache), B, H,
+                                H if n_kv_heads is None else n_kv_heads, head_dim, _p(table),
                                 int(pos), _p(pos_dev), max_seq, _st())
     _lib.check(rc, "a3_decode_rope_kv")
+
+
+def repeat_kv(qkv_compact, qkv, n_heads, n_kv_heads, head_dim):
+    """[rows][(H + 2 Hkv) hd] (q | k | v) -> [rows][3 H hd]: expanded head h = group head h // (H // Hkv)."""
+    rc = _L().a3_repeat_kv(_p(qkv_compact), qkv_compact.stride(0), _p(qkv), qkv.stride(0), qkv.shape[0], n_heads,
+                           n_kv_heads, head_dim, _st())
+    _lib.check(rc, "a3_repeat_kv")
+    return qkv
+
+
+def reduce_kv(dqkv, dqkv_compact, n_heads, n_kv_heads, head_dim):
+    """Backward of repeat_kv: dq copied, dk / dv summed over the copies of each group."""
+    rc = _L().a3_reduce_kv(_p(dqkv), dqkv.stride(0), _p(dqkv_compact), dqkv_compact.stride(0), dqkv.shape[0], n_heads,
+                           n_kv_heads, head_dim, _st())
+    _lib.check(rc, "a3_reduce_kv")
+    return dqkv_compact
 
 
 def kv_append(k, v, kcache, vcache, B, T, H, head_dim, start, max_seq):

@@ -84,14 +84,15 @@ int a3_linear_small_m(const void* X, const void* W, void* Y, int M, int N, int K
 /* Fused decode projection for M <= 8 rows (one launch per projection of a decode step):
  *   prologue  norm_w != NULL: X <- RMSNorm(X) * norm_w (components.py:39-53)
  *             swiglu != 0:    X is gu [M][2K], X <- bf16(silu(g)) * u (llama_ens5.py:213-214)
- *   epilogue  residual | fp32 logits | rope_table != NULL (QKV projection, N = 3*H*128): RoPE of q, k
- *             at position pos (or *pos_dev) and k, v written into cache[m, pos] (llama_ens5.py:118-127).
+ *   epilogue  residual | fp32 logits | rope_table != NULL (QKV projection, N = (H + 2*Hkv)*128, columns q | k | v
+ *             with Hkv = n_kv_heads key / value heads): RoPE of q, k at position pos (or *pos_dev) and k, v written
+ *             into cache[m, pos] (llama_ens5.py:118-127).
  * Launched with programmatic dependent launch: weights are prefetched while the previous kernel of
  * the stream drains. */
 int a3_decode_linear(const void* X, const void* W, void* Y, int M, int N, int K, long long ldx,
                      long long ldw, long long ldy, const void* norm_w, float eps, int swiglu,
                      const void* residual, long long ldr, int out_fp32, const float* rope_table,
-                     int n_heads, void* kcache, void* vcache, const int* pos_dev, int pos, int max_seq,
+                     int n_heads, int n_kv_heads, void* kcache, void* vcache, const int* pos_dev, int pos, int max_seq,
                      void* stream);
 
 /* The w1|w3 projection of a decode step with the gated SiLU as its epilogue (llama_ens5.py:213-214): a warp streams
@@ -172,19 +173,28 @@ int a3_attn_bwd(const void* q, const void* k, const void* v, const void* o, cons
                 int H, int T, int head_dim, long long ldqkv, long long ldo, long long lddqkv,
                 float scale, int causal, const float* rope_table, void* stream);
 /* Single-query decode attention over the KV cache (llama_ens5.py:121-129,142-167 with seqlen 1):
- * cache layout [B][max_seq][H][128] bf16; q [B][H*128]; ctx = number of valid positions. */
+ * cache layout [B][max_seq][Hkv][128] bf16 (Hkv = n_kv_heads; query head h reads group head h / (H / Hkv), the
+ * reference's repeat_kv, llama_ens5.py:131-133); q [B][H*128]; ctx = number of valid positions. */
 /* scratch: B*H*(32*130 + 1) floats, ZERO-INITIALISED once by the caller (the tail holds per-(b,h)
  * arrival counters that reset themselves; the last split to finish merges the partial results).
  * pos_dev != NULL (CUDA-graph replay): ctx = *pos_dev + 1 is read on the device and `ctx` is only an
  * upper bound used to size the split. */
 int a3_attn_decode(const void* q, const void* kcache, const void* vcache, void* o, float* scratch,
-                   int B, int H, int head_dim, int ctx, int max_seq, long long ldq, long long ldo,
+                   int B, int H, int Hkv, int head_dim, int ctx, int max_seq, long long ldq, long long ldo,
                    float scale, const int* pos_dev, void* stream);
 /* Decode-step fusion of apply_rotary_emb + cache write (llama_ens5.py:118-127, seqlen 1): rotates q
- * and k of qkv [B][3*H*128] in place at position pos (or *pos_dev) and writes k, v into
+ * and k of qkv [B][(H + 2*Hkv)*128] in place at position pos (or *pos_dev) and writes k, v into
  * cache[b, pos]. */
-int a3_decode_rope_kv(void* qkv, long long ld, void* kcache, void* vcache, int B, int H, int head_dim,
+int a3_decode_rope_kv(void* qkv, long long ld, void* kcache, void* vcache, int B, int H, int Hkv, int head_dim,
                       const float* table, int pos, const int* pos_dev, int max_seq, void* stream);
+/* Grouped-query attention glue (n_kv_heads < n_heads; repeat_kv of the absent LLM/llama.py, call llama_ens5.py:131-133):
+ * a3_repeat_kv expands compact [rows][(H + 2*Hkv)*hd] (q | k | v) to [rows][3*H*hd] -- expanded head h = group head
+ * h / (H / Hkv) -- so the prefill / training attention kernels run unchanged on H heads; a3_reduce_kv is its backward
+ * (dq copied, dk / dv summed over the copies of a group in fp32, one rounding). */
+int a3_repeat_kv(const void* qkv_compact, long long ld_compact, void* qkv, long long ld, long long rows, int n_heads,
+                 int n_kv_heads, int head_dim, void* stream);
+int a3_reduce_kv(const void* dqkv, long long ld, void* dqkv_compact, long long ld_compact, long long rows, int n_heads,
+                 int n_kv_heads, int head_dim, void* stream);
 /* KV-cache append (llama_ens5.py:121-127): copy rows [B][T] of k and v (strided, ld) into
  * cache[:, start:start+T]. */
 int a3_kv_append(const void* k, const void* v, long long ld, void* kcache, void* vcache, int B,

@@ -239,3 +239,17 @@ def test_reference_ensemble_checkpoint_is_refused_clearly(tmp_path):
     ok.mkdir()
     torch.save({"model": {"llma.visual_proj.0.weight": torch.zeros(8, 1024)}}, ok / "consolidated.00-of-01.model.pth")
     ckpt.check_vision_branch(str(ok), 1024)
+
+
+def test_grouped_query_layout_is_pure_shape_arithmetic():
+    """n_kv_heads < n_heads: wk / wv rows shrink to n_kv_heads * head_dim inside the fused q|k|v matrix (llama_ens5.py:76-90)."""
+    import types
+
+    from a3vlm_b200.engine import build_layout
+
+    a = types.SimpleNamespace(dim=512, n_layers=2, n_heads=4, n_kv_heads=1, vocab_size=512, multiple_of=64, ffn_dim_multiplier=None)
+    decay, nodecay, frozen, kpad = build_layout(a, None)
+    shapes = dict(decay + nodecay)
+    assert shapes["layers.0.wqkv"] == (512 + 2 * 128, 512) and shapes["layers.1.attention.wo.weight"] == (512, 512)
+    a.n_kv_heads = None
+    assert dict(build_layout(a, None)[0])["layers.0.wqkv"] == (3 * 512, 512)
