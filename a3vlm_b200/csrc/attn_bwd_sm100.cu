@@ -72,7 +72,7 @@ struct BwdParams {
   int B, H, T;
   float scale;
   int causal;
-  int debug_skip;  // profiling experiments only (A3_ATTN_BWD_SKIP): 1 = no dQ reduce
+  int debug_skip;  // profiling builds only (always 0 in the library): 1 = no dQ reduce
   long long* trace;  // debug (A3_BW_TRACE_PTR): clock64 stamps [cta][role: worker, issuer, producer][128]
 };
 
@@ -544,7 +544,7 @@ extern "C" int a3_attn_bwd(const void* q, const void* k, const void* v, const vo
   p.B = B; p.H = H; p.T = T;
   p.scale = scale;
   p.causal = causal ? 1 : 0;
-  p.debug_skip = getenv("A3_ATTN_BWD_SKIP") ? atoi(getenv("A3_ATTN_BWD_SKIP")) : 0;
+  p.debug_skip = 0;
   static long long* const trace_ptr =
       getenv("A3_BW_TRACE_PTR") ? reinterpret_cast<long long*>(strtoull(getenv("A3_BW_TRACE_PTR"), nullptr, 0)) : nullptr;
   p.trace = trace_ptr;

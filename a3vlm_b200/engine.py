@@ -909,31 +909,21 @@ class Engine:
         if B <= self.decode_fused_max_b:
             # five launches per layer: every norm / activation / RoPE / cache write is a prologue or
             # epilogue of the weight-streaming projection that consumes or produces it
-            skip = os.environ.get("A3_DEC_SKIP", "").split(",")  # timing experiments only: marginal cost of a launch
-            gated = os.environ.get("A3_DEC_GATED", "1") != "0"
+            gated = os.environ.get("A3_DEC_GATED", "1") != "0"  # 0: round-1 form (gate as the prologue of w2), for A/B timing
             for i in range(a.n_layers):
                 p = f"layers.{i}."
-                if "qkv" not in skip:
-                    ops.decode_linear(x, w[p + "wqkv"], d["qkv"], norm_w=w[p + "attention_norm.weight"], eps=a.norm_eps,
-                                      rope=self.rope, n_heads=a.n_heads, n_kv_heads=self.n_kv, kcache=self.kcache[i],
-                                      vcache=self.vcache[i],
-                                      pos_dev=d["pos"], max_seq=a.max_seq_len)
-                if "attn" not in skip:
-                    ops.attn_decode(d["qkv"][:, :D], self.kcache[i], self.vcache[i], d["o"], d["scratch"], B,
-                                    a.n_heads, self.head_dim, a.max_seq_len, a.max_seq_len, self.scale, pos_dev=d["pos"],
-                                    n_kv_heads=self.n_kv)
-                if "wo" not in skip:
-                    ops.decode_linear(d["o"], w[p + "attention.wo.weight"], d["h"], residual=x)
+                ops.decode_linear(x, w[p + "wqkv"], d["qkv"], norm_w=w[p + "attention_norm.weight"], eps=a.norm_eps,
+                                  rope=self.rope, n_heads=a.n_heads, n_kv_heads=self.n_kv, kcache=self.kcache[i],
+                                  vcache=self.vcache[i], pos_dev=d["pos"], max_seq=a.max_seq_len)
+                ops.attn_decode(d["qkv"][:, :D], self.kcache[i], self.vcache[i], d["o"], d["scratch"], B,
+                                a.n_heads, self.head_dim, a.max_seq_len, a.max_seq_len, self.scale, pos_dev=d["pos"],
+                                n_kv_heads=self.n_kv)
+                ops.decode_linear(d["o"], w[p + "attention.wo.weight"], d["h"], residual=x)
                 if gated:  # the gate is the epilogue of the w1|w3 projection: gu never reaches HBM
-                    if "w13" not in skip:
-                        ops.decode_linear_gated(d["h"], w[p + "w13"], d["y"], norm_w=w[p + "ffn_norm.weight"], eps=a.norm_eps)
-                    if "w2" not in skip:
-                        ops.decode_linear(d["y"], w[p + "feed_forward.w2.weight"], x2, residual=d["h"])
-                    x, x2 = x2, x
-                    continue
-                if "w13" not in skip:
+                    ops.decode_linear_gated(d["h"], w[p + "w13"], d["y"], norm_w=w[p + "ffn_norm.weight"], eps=a.norm_eps)
+                    ops.decode_linear(d["y"], w[p + "feed_forward.w2.weight"], x2, residual=d["h"])
+                else:
                     ops.decode_linear(d["h"], w[p + "w13"], d["gu"], norm_w=w[p + "ffn_norm.weight"], eps=a.norm_eps)
-                if "w2" not in skip:
                     ops.decode_linear(d["gu"], w[p + "feed_forward.w2.weight"], x2, K=F, swiglu=True, residual=d["h"])
                 x, x2 = x2, x
             ops.decode_linear(x, w["output.weight"], d["logits"], norm_w=w["norm.weight"], eps=a.norm_eps, out_fp32=True)
