@@ -229,7 +229,7 @@ def run_reference(args, cfg):
     line = {"impl": "reference", "metric": "images/sec (336x336 + 256-tok prompt) fwd+bwd", "value": val, "unit": "images/s",
             "n_gpus": args.gpus, "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": statistics.mean(walls) * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": workload_config(args, cfg, fl, 1),
+            "config": workload_config(args, cfg, fl, max(1, args.gpus)),  # the same workload description as our arm at this N
             "value_is": "EXTRAPOLATED: seconds per image = t(ViT + head + their AdamW) + n_layers/sample_layers * t(sampled decoder "
                         "layers fwd+bwd+AdamW), batch 1, scaled linearly to the batch; ms_per_step is the measured sample",
             "extrapolation": {**det, "extrapolated_ms_per_image": sec * 1e3, "full_depth_check": check},
