@@ -1,5 +1,6 @@
 // Host-side plumbing behind the C ABI: error slot, launch accounting, device queries and TMA
 // tensor-map encoding through the driver entry point (resolved at run time: no libcuda link).
+#include <cstdlib>
 #include "common.cuh"
 
 #include <atomic>
@@ -113,10 +114,59 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
+// A tensor map is a pure function of (address, rank, dims, strides, box, dtype, swizzle), and a training step asks for
+// the same ~1 500 of them every step (every GEMM operand, every attention Q / K / V / dO / dQ view).  A per-thread
+// direct-mapped cache (no lock, no allocation; a colliding key simply re-encodes) answers the repeats.
+struct TmapKey {
+  const void* ptr;
+  int rank, dtype, swz, pad;
+  cuuint64_t dims[5], strides[4];
+  cuuint32_t box[5], pad2;
+};
+struct TmapSlot {
+  TmapKey key;
+  CUtensorMap map;
+  bool valid;
+};
+constexpr int TMAP_SLOTS = 2048;
+
+static inline uint64_t tmap_hash(const TmapKey& k) {
+  const unsigned char* b = reinterpret_cast<const unsigned char*>(&k);
+  uint64_t h = 1469598103934665603ull;  // FNV-1a
+  for (size_t i = 0; i < sizeof(TmapKey); ++i) h = (h ^ b[i]) * 1099511628211ull;
+  return h;
+}
+
+static int encode_uncached(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims,
+                           const cuuint64_t* strides, const cuuint32_t* box, CUtensorMapDataType dtype,
+                           CUtensorMapSwizzle swz);
+
 static int encode(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims,
                   const cuuint64_t* strides, const cuuint32_t* box,
                   CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
                   CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+  static const bool cache_off = getenv("A3_TMAP_CACHE") && atoi(getenv("A3_TMAP_CACHE")) == 0;
+  if (cache_off || rank < 1 || rank > 5) return encode_uncached(tm, ptr, rank, dims, strides, box, dtype, swz);
+  thread_local static TmapSlot* slots = nullptr;
+  if (!slots) slots = new TmapSlot[TMAP_SLOTS]();  // zero-initialised: valid = false
+  TmapKey k;
+  std::memset(&k, 0, sizeof(k));
+  k.ptr = ptr; k.rank = rank; k.dtype = (int)dtype; k.swz = (int)swz;
+  for (int i = 0; i < rank; ++i) { k.dims[i] = dims[i]; k.box[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) k.strides[i] = strides[i];
+  TmapSlot& s = slots[tmap_hash(k) & (TMAP_SLOTS - 1)];
+  if (s.valid && std::memcmp(&s.key, &k, sizeof(k)) == 0) {
+    *tm = s.map;
+    return A3_OK;
+  }
+  if (int rc = encode_uncached(tm, ptr, rank, dims, strides, box, dtype, swz)) return rc;
+  s.key = k; s.map = *tm; s.valid = true;
+  return A3_OK;
+}
+
+static int encode_uncached(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims,
+                           const cuuint64_t* strides, const cuuint32_t* box, CUtensorMapDataType dtype,
+                           CUtensorMapSwizzle swz) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return set_error(A3_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
