@@ -92,3 +92,30 @@ def test_product_code_never_imports_the_oracle_or_a_cpu_fallback():
                     if "oracle" in n or n.startswith("accessory") or n.startswith("/root/reference"):
                         offenders.append((os.path.relpath(path, root), n))
     assert not offenders, offenders
+
+
+def test_every_python_call_site_passes_the_declared_number_of_arguments():
+    """The wrappers bind by position through ctypes: a call with the wrong number of arguments only fails on a GPU
+    box.  Statically compare every `<lib>.a3_xxx(...)` call in the package (and bench.py) with the header."""
+    import ast
+
+    from a3vlm_b200 import _lib
+
+    files = [os.path.join(ROOT, "bench.py")]
+    for d, _, names in os.walk(os.path.join(ROOT, "a3vlm_b200")):
+        files += [os.path.join(d, n) for n in names if n.endswith(".py")]
+    seen = set()
+    for path in files:
+        for node in ast.walk(ast.parse(open(path).read())):
+            if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and node.func.attr.startswith("a3_"):
+                name = node.func.attr
+                assert name in _lib.PROTOS, (path, node.lineno, name)
+                if any(isinstance(a, ast.Starred) for a in node.args):
+                    continue
+                assert not node.keywords, (path, node.lineno, name)
+                want = len(_lib.PROTOS[name][1])
+                assert len(node.args) == want, f"{os.path.relpath(path, ROOT)}:{node.lineno}: {name} takes {want} arguments, call passes {len(node.args)}"
+                seen.add(name)
+    # every compute entry point is reachable from Python
+    unused = set(_lib.PROTOS) - seen - {"a3_last_error", "a3_version"}
+    assert not unused, unused
