@@ -18,6 +18,7 @@
 // stages, two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "ptx.cuh"
 #include "a3vlm_b200.h"
+#include <atomic>
 #include <cstring>
 #include "common.cuh"
 #include <cstdlib>
@@ -47,6 +48,7 @@ struct GemmParams {
   float alpha;
   int group_m;  // M-blocks per rasterisation group
   unsigned long long hint_a, hint_b;  // L2 cache policies of the operand loads (CTA-pair kernel)
+  unsigned int* tile_ctr;             // dynamic tile claim (CTA-pair kernel, A3_GEMM_DYNAMIC=1): zero at launch, self-resetting
   // fused gated-SiLU modes (llama_ens5.py:213-217):
   //   swiglu_F > 0 (CTA-pair kernel only): B = [w1; w3] ([2F][K]); CTA 0 of the pair loads 128 rows of
   //     w1, CTA 1 the same 128 rows of w3, so one accumulator tile holds g | u of 128 features; the
@@ -547,6 +549,16 @@ struct Gemm2Smem {
   static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
 };
 
+// DYN: tiles are claimed at run time instead of walked in a fixed stride -- a CTA pair that shares its SMs with a
+// collective or optimiser CTA simply takes fewer tiles.  The leader's producer warp draws tile ids from a global
+// counter (one atomicAdd per tile, issued a whole tile ahead of its use) and publishes them through a 4-entry ring in
+// BOTH CTAs' shared memory (st.shared::cluster + remote mbarrier arrive); the peer's producer, the MMA issuer and the
+// epilogue warps read the ring in order and release each entry on the leader's `sched_empty` barrier; id -1 ends the
+// stream.  The leader that draws the last sentinel resets the counter for the next launch that uses the same word.
+constexpr int SCHED_RING = 4;
+__device__ unsigned int g_tile_ctr[64];
+
+template <bool DYN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const GemmParams p) {
@@ -561,6 +573,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tmem_full = bars + 2 * S::STAGES;
   uint64_t* tmem_empty = bars + 2 * S::STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::STAGES + 4);
+  uint64_t* sched_full = bars + 2 * S::STAGES + 6;               // [SCHED_RING], one arrival (the claimer) per entry
+  uint64_t* sched_empty = sched_full + SCHED_RING;              // [SCHED_RING], leader's copy counts every reader of the pair
+  volatile int* sched_tile = reinterpret_cast<volatile int*>(sched_empty + SCHED_RING);  // [SCHED_RING]
+  static_assert((2 * S::STAGES + 6 + 2 * SCHED_RING) * 8 + SCHED_RING * 4 <= S::BAR_BYTES, "barrier area");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -586,9 +602,25 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], 2 * ((blockDim.x >> 5) - 4));  // epilogue warps of both CTAs
     }
+    if (DYN) {
+      for (int s = 0; s < SCHED_RING; ++s) {
+        mbar_init(&sched_full[s], 1);
+        // readers of an entry: the peer's producer warp, the leader's MMA warp, the epilogue warps of both CTAs
+        mbar_init(&sched_empty[s], 2 + 2 * ((blockDim.x >> 5) - 4));
+      }
+    }
     fence_mbar_init();
   }
   cluster_sync_all();  // peer barriers are initialised before anyone signals them
+  // ring reader (every lane of the calling warp): next tile id of the stream, -1 at its end
+  auto ring_next = [&](int& slot, uint32_t& ph) -> int {
+    mbar_wait_cluster(&sched_full[slot], ph);
+    const int t = sched_tile[slot];
+    __syncwarp();
+    if (lane == 0) mbar_arrive_cluster(mapa_u32(&sched_empty[slot], 0));
+    if (++slot == SCHED_RING) { slot = 0; ph ^= 1; }
+    return t;
+  };
   if (warp == 2) {
     tmem_alloc_2sm(tmem_slot, 2 * BN);
     tmem_relinquish_2sm();
@@ -605,7 +637,39 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t smem0 = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+      // tile stream of this warp: fixed stride, or (DYN) claimed by the leader / read from the ring by the peer
+      int rslot = 0;
+      uint32_t rphase = 0;
+      const int n_pairs = gridDim.x >> 1;
+      auto claim = [&]() -> int {  // warp-uniform; the counter word returns to 0 after the last sentinel draw
+        unsigned int t = 0;
+        if (lane == 0) {
+          t = atomicAdd(p.tile_ctr, 1u);
+          if (t == (unsigned int)(num_tiles + n_pairs - 1)) *p.tile_ctr = 0u;
+        }
+        t = __shfl_sync(0xffffffffu, t, 0);
+        return t < (unsigned int)num_tiles ? (int)t : -1;
+      };
+      int tile = first_tile, next_claim = -1;
+      if (DYN) tile = leader ? claim() : ring_next(rslot, rphase);
+      for (;;) {
+        if (DYN) {
+          if (leader) {  // publish the tile (or the end marker) to every reader of the pair, then draw the next one
+            mbar_wait(&sched_empty[rslot], rphase ^ 1);
+            if (lane == 0) {
+              sched_tile[rslot] = tile;
+              st_shared_cluster_u32(mapa_u32(const_cast<int*>(&sched_tile[rslot]), 1), (uint32_t)tile);
+              mbar_arrive(&sched_full[rslot]);
+              mbar_arrive_cluster(mapa_u32(&sched_full[rslot], 1));
+            }
+            __syncwarp();
+            if (++rslot == SCHED_RING) { rslot = 0; rphase ^= 1; }
+            if (tile >= 0) next_claim = claim();  // in flight while this tile's operands are loaded
+          }
+          if (tile < 0) break;
+        } else if (tile >= num_tiles) {
+          break;
+        }
         int mb, nb;
         tile_coords(tile, m_blocks, n_blocks, p.group_m, mb, nb);
         const int m0 = mb * (2 * BM) + rank * BM;
@@ -637,6 +701,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           __syncwarp();
           if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
         }
+        if (DYN) tile = leader ? next_claim : ring_next(rslot, rphase);
+        else tile += tile_step;
       }
     }
   } else if (warp == 1) {
@@ -653,7 +719,14 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t phase = 0;
       int acc_stage = 0;
       uint32_t acc_phase = 0;
-      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+      int rslot = 0;
+      uint32_t rphase = 0;
+      for (int tile = first_tile;; tile += tile_step) {
+        if (DYN) {
+          if (ring_next(rslot, rphase) < 0) break;
+        } else if (tile >= num_tiles) {
+          break;
+        }
         mbar_wait(&tmem_empty[acc_stage], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tm + acc_stage * BN;
@@ -684,7 +757,15 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int ew = (warp - 4) & 3, eh = (warp - 4) >> 2;
     int acc_stage = 0;
     uint32_t acc_phase = 0;
-    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+    int rslot = 0;
+    uint32_t rphase = 0;
+    for (int tile = first_tile;; tile += tile_step) {
+      if (DYN) {
+        tile = ring_next(rslot, rphase);
+        if (tile < 0) break;
+      } else if (tile >= num_tiles) {
+        break;
+      }
       int mb, nb;
       tile_coords(tile, m_blocks, n_blocks, p.group_m, mb, nb);
       const int row = mb * (2 * BM) + rank * BM + ew * 32 + lane;
@@ -747,13 +828,26 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
 static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
                         cudaStream_t stream) {
   using S = Gemm2Smem;
-  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&gemm2_bf16_kernel), S::TOTAL)) return rc;
+  static const bool dynamic = getenv("A3_GEMM_DYNAMIC") && atoi(getenv("A3_GEMM_DYNAMIC")) == 1;
   const int m_blocks = (p.M + 2 * BM - 1) / (2 * BM);
   const int n_blocks = p.swiglu_F ? p.swiglu_F / S::BNH : (p.N + S::BN - 1) / S::BN;
   const int tiles = m_blocks * n_blocks;
   const int pairs = num_sms() / 2;
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
-  gemm2_bf16_kernel<<<grid, epilogue_threads(p), S::TOTAL, stream>>>(tmA, tmB, p);
+  if (dynamic) {
+    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&gemm2_bf16_kernel<true>), S::TOTAL)) return rc;
+    // one of 64 self-resetting counter words, round-robin: a word is reused 64 launches later, long after its reset
+    static std::atomic<unsigned int> seq{0};
+    unsigned int* base = nullptr;
+    if (cudaGetSymbolAddress(reinterpret_cast<void**>(&base), g_tile_ctr) != cudaSuccess)
+      return set_error(A3_ERR_CUDA, "a3_gemm_bf16: tile counter symbol");
+    GemmParams q = p;
+    q.tile_ctr = base + (seq.fetch_add(1, std::memory_order_relaxed) & 63u);
+    gemm2_bf16_kernel<true><<<grid, epilogue_threads(p), S::TOTAL, stream>>>(tmA, tmB, q);
+    return check_launch("a3_gemm_bf16(2cta, dynamic)");
+  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&gemm2_bf16_kernel<false>), S::TOTAL)) return rc;
+  gemm2_bf16_kernel<false><<<grid, epilogue_threads(p), S::TOTAL, stream>>>(tmA, tmB, p);
   return check_launch("a3_gemm_bf16(2cta)");
 }
 
@@ -835,6 +929,7 @@ extern "C" int a3_gemm_bf16(const void* A, const void* B, void* C, int M, int N,
   static const int gm_env = getenv("A3_GEMM_GROUP_M") ? atoi(getenv("A3_GEMM_GROUP_M")) : 0;  // tuning experiments
   p.group_m = gm_env > 0 ? gm_env : 16;
   set_cache_hints(p);
+  p.tile_ctr = nullptr;
   p.swiglu_F = 0; p.C2 = nullptr; p.ldc2 = 0; p.dswiglu_gu = nullptr; p.ldgu = 0;
   p.a_rows = a_rows;
   p.patch_g = 0; p.patch_p = 0;
@@ -848,7 +943,7 @@ extern "C" int a3_gemm_bf16(const void* A, const void* B, void* C, int M, int N,
 static void init_params(a3::GemmParams& p, int M, int N, int K) {
   p.C = nullptr; p.bias = nullptr; p.residual = nullptr; p.rope = nullptr; p.ldc = 0; p.ldr = 0;
   p.rope_cols = 0; p.rope_period = 1; p.rope_pos0 = 0; p.M = M; p.N = N; p.K = K; p.a_mn = 0; p.b_mn = 0;
-  p.act = 0; p.out_fp32 = 0; p.accumulate = 0; p.alpha = 1.f; p.group_m = 16; set_cache_hints(p); p.swiglu_F = 0; p.C2 = nullptr;
+  p.act = 0; p.out_fp32 = 0; p.accumulate = 0; p.alpha = 1.f; p.group_m = 16; set_cache_hints(p); p.tile_ctr = nullptr; p.swiglu_F = 0; p.C2 = nullptr;
   p.ldc2 = 0; p.dswiglu_gu = nullptr; p.ldgu = 0; p.a_rows = a3::BM; p.patch_g = 0; p.patch_p = 0;
 }
 

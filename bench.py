@@ -247,6 +247,7 @@ def workload_config(args, cfg, fl, n):
             "parallelism": f"dp{n}", "optimizer": ("sharded over the ranks (reduce-scatter grads, all-gather weights), pipelined under the next forward" if n > 1
                           else "pipelined under the next forward" if getattr(args, "overlap_opt", 0) else "in line"),
             "l2_policy": "working set (>= 13.5 GB of weights + activations) >> 126 MB L2, no flush needed",
+            "gemm_tile_order": "claimed at run time (atomic counter, ring through the CTA pair)" if os.environ.get("A3_GEMM_DYNAMIC") == "1" else "fixed stride",
             "tflop_per_image": fl["total"] / 1e12}
 
 
@@ -275,6 +276,11 @@ def main():
     cfg = MODELS[args.model]
     if args.impl == "reference":
         return run_reference(args, cfg)
+    # N > 1: the CTA-pair GEMM claims its tiles at run time (a pair that shares SMs with a collective CTA takes fewer
+    # tiles): 266.6 / 268.6 ms per step against 273.5 / 274.1 with the fixed tile order at N = 2, alternating runs on one
+    # box.  On one GPU the two orders time the same (277.7 vs 278.4 ms) and the fixed order stays the default.
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        os.environ.setdefault("A3_GEMM_DYNAMIC", "1")
 
     import torch
     import torch.distributed as dist
